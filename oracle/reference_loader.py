@@ -1,0 +1,54 @@
+"""TEST INFRASTRUCTURE — import the live reference (build container only).
+
+``/root/reference`` exists only in the build container; the GPU box never has it, so nothing under
+``tests -m gpu``, ``smoke()`` or ``bench.py`` may call this.  It is used by ``tests/golden/gen_golden.py``
+to produce the committed fixtures and by the ``not gpu`` tests that re-check the oracle against the
+live reference when it is present (they skip otherwise).  SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("VDN_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "video_depth_anything"))
+
+
+def _install_shims():
+    sys.dont_write_bytecode = True  # the reference tree is read-only
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    if "easydict" not in sys.modules:
+        class EasyDict(dict):  # stand-in for the missing `easydict` (used only at dpt_temporal.py:35-40)
+            def __init__(self, d=None, **kw):
+                super().__init__()
+                self.update(dict(d or {}, **kw))
+            __getattr__ = dict.__getitem__
+            __setattr__ = dict.__setitem__
+        sys.modules["easydict"] = types.SimpleNamespace(EasyDict=EasyDict)
+
+
+def load_vda(encoder: str, state_dict):
+    """Reference VideoDepthAnything (video_depth_anything/video_depth.py:35) with our recipe weights, strict."""
+    from .init_recipe import ENCODERS
+    _install_shims()
+    from video_depth_anything.video_depth import VideoDepthAnything
+    cfg = ENCODERS[encoder]
+    m = VideoDepthAnything(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
+    m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+def load_v5(encoder: str, state_dict):
+    """Reference models/video_depth_model_v5.py:128 VideoDepthAnything with our recipe weights, strict."""
+    from .init_recipe import ENCODERS
+    _install_shims()
+    from models.video_depth_model_v5 import VideoDepthAnything as V5
+    cfg = ENCODERS[encoder]
+    m = V5(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
+    m.load_state_dict(state_dict, strict=True)
+    return m

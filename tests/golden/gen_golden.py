@@ -1,0 +1,114 @@
+"""Generate the committed golden fixtures by running the LIVE reference (/root/reference) in this container.
+
+    python tests/golden/gen_golden.py            # writes tests/golden/*.npz (small, committed)
+
+The reference has no golden vectors of its own, so these pin the oracle
+(`oracle/vdn_oracle.py`) to the reference's actual outputs.  Weights come from
+`oracle/init_recipe.make_state_dict` and are loaded into the reference modules with
+`load_state_dict(strict=True)` — which also proves the recipe reproduces the reference's key names/shapes.
+Inputs are regenerated from seeds by the tests, only outputs are stored.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import reference_loader as RL  # noqa: E402
+from oracle.init_recipe import make_input, make_state_dict  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# (name, encoder, T, H, W, seed, subsample stride for storage)
+VDA_CASES = [
+    ("vda_vits_t4_70x84", "vits", 4, 70, 84, 0, 1),
+    ("vda_vits_t2_518x518", "vits", 2, 518, 518, 1, 4),   # native 37x37 grid -> pos_embed untouched branch
+    ("vda_vitl_t2_56x70", "vitl", 2, 56, 70, 2, 1),
+]
+V5_CASES = [("v5_vits_s4_60x80", "vits", 4, 60, 80, 3)]
+VIDEO_CASES = [("video_vits_n50_56x70", "vits", 50, 56, 70, 4)]
+SCHEDULE_NS = [1, 5, 21, 22, 23, 32, 44, 45, 50, 60, 100]
+
+
+def video_frames(n, h, w, seed):
+    """Deterministic uint8 RGB frames with slow temporal drift (so alignment has something to fit)."""
+    rng = np.random.RandomState(seed)
+    base = rng.randint(0, 256, size=(h, w, 3)).astype(np.float32)
+    frames = []
+    for i in range(n):
+        noise = rng.randint(-20, 21, size=(h, w, 3)).astype(np.float32)
+        frames.append(np.clip(np.roll(base, i, axis=1) + noise, 0, 255).astype(np.uint8))
+    return np.stack(frames)
+
+
+def main():
+    assert RL.available(), "reference not present"
+    torch.set_grad_enabled(False)
+    for name, enc, T, H, W, seed, stride in VDA_CASES:
+        sd = make_state_dict("vda", enc, seed)
+        m = RL.load_vda(enc, sd)
+        x = make_input("rgb", (1, T, 3, H, W), seed)
+        stages = {}
+        feats = m.pretrained.get_intermediate_layers(x.flatten(0, 1), m.intermediate_layer_idx[enc], return_class_token=True)
+        y = m(x)
+        np.savez_compressed(
+            os.path.join(OUT, name + ".npz"),
+            depth=y[:, :, ::stride, ::stride].numpy(),
+            depth_sum=np.float64(y.double().sum().item()),
+            tap3=feats[3][0][:, ::7, ::5].numpy(),
+            meta=np.array([T, H, W, seed, stride]),
+        )
+        print(name, tuple(y.shape), float(y.mean()), float(y.min()))
+        del m
+    for name, enc, S, H, W, seed in V5_CASES:
+        sd = make_state_dict("v5", enc, seed)
+        m = RL.load_v5(enc, sd)
+        d = make_input("depth", (1, S, H, W), seed)
+        y = m(d)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), out=y.numpy(), meta=np.array([S, H, W, seed]))
+        print(name, tuple(y.shape), float((y - d).abs().mean()))
+        del m
+    for name, enc, N, H, W, seed in VIDEO_CASES:
+        sd = make_state_dict("vda", enc, seed)
+        m = RL.load_vda(enc, sd)
+        frames = video_frames(N, H, W, seed)
+        captured = []
+        orig_forward = m.forward
+
+        def fwd(x):
+            captured.append(x.clone())
+            return orig_forward(x)
+        m.forward = fwd
+        depths, _ = m.infer_video_depth(frames, 30, input_size=min(H, W), device="cpu", fp32=True)
+        assert captured[0].shape[-2:] == (H, W), captured[0].shape  # Resize must be the identity for these sizes
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), depths=depths.astype(np.float32), meta=np.array([N, H, W, seed]))
+        print(name, depths.shape, float(depths.mean()))
+        del m
+    # window schedules: run the reference driver with a stub forward and unique per-frame inputs
+    sd = make_state_dict("vda", "vits", 0)
+    m = RL.load_vda("vits", sd)
+    sched = {}
+    for N in SCHEDULE_NS:
+        frames = np.zeros((N, 14, 14, 3), np.uint8)
+        frames[:, 0, 0, 0] = np.arange(N) % 256
+        rec = []
+
+        def stub(x, rec=rec):
+            # recover the source frame index of each slot from the red channel of pixel (0,0)
+            v = x[0, :, 0, 0, 0].double() * 0.229 + 0.485
+            rec.append(torch.round(v * 255).long().tolist())
+            return torch.zeros(1, x.shape[1], x.shape[3], x.shape[4])
+        m.forward = stub
+        out, _ = m.infer_video_depth(frames, 30, input_size=14, device="cpu", fp32=True)
+        assert out.shape == (N, 14, 14)
+        sched[f"n{N}"] = np.array(rec, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "window_schedule.npz"), **sched)
+    print("schedules", {k: v.shape for k, v in sched.items()})
+
+
+if __name__ == "__main__":
+    main()
