@@ -1,0 +1,137 @@
+/* vdn_b200 — C ABI of the B200-native (sm_100a) depth/normal inference kernels.
+ *
+ * The reference (injun-baek/Video-Depth-Normal-v2) has no FFI layer: its "operator API" is the
+ * nn.Module surface.  Each entry point below replaces the PyTorch/library op(s) the
+ * reference calls at the cited lines; the Python host (video_depth_normal_v2_b200/) binds them with
+ * ctypes and mirrors the reference's module API on top.  Plain pointers and sizes only: every pointer is
+ * a CUDA device pointer unless noted, `stream` is a cudaStream_t passed as void*.
+ *
+ * All functions return 0 on success, non-zero on error (message via vdn_last_error()).  Kernels never
+ * allocate; outputs/workspaces are caller-owned.  "16-bit" tensors are fp16 or bf16 according to
+ * vdn_set_operand_format (library-wide; fp16 default).
+ */
+#ifndef VDN_B200_H_
+#define VDN_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state ------------------------------------------------------------------------- */
+const char* vdn_last_error(void);
+int vdn_version(void);
+/* 0 = fp16 operands, 1 = bf16 operands (tcgen05 kind::f16 runs both at the same rate). */
+int vdn_set_operand_format(int fmt);
+int vdn_get_operand_format(void);
+/* number of kernel launches issued by this library since the last reset (bench.py "gpu_launches"). */
+int64_t vdn_launch_count(void);
+void vdn_reset_launch_count(void);
+
+/* ---- tcgen05 GEMM / implicit-GEMM convolution with fused epilogue ---------------------------
+ * out = epilogue( A[M,K] * W[N,K]^T ), fp32 accumulation in TMEM.
+ * Replaces: nn.Linear qkv/proj/fc1/fc2 (dinov2_layers/attention.py:52,60; mlp.py:36-40) incl. LayerScale
+ * (layer_scale.py:27-28) and the residual adds (block.py:105-106); PatchEmbed conv (patch_embed.py:76);
+ * DPT 1x1 / 3x3 / ConvTranspose convs (dpt.py:60-124, util/blocks.py:20-32,78-91,159); motion-module linears,
+ * GEGLU (motion_module/attention.py:382-384) and proj_out + residual (motion_module.py:128-133).            */
+enum { VDN_ACT_NONE = 0, VDN_ACT_GELU = 1, VDN_ACT_RELU = 2 };
+enum {
+  VDN_ROWMAP_IDENTITY = 0,
+  VDN_ROWMAP_PIXEL_SHUFFLE = 1, /* ConvTranspose k==stride: rm0=H_in rm1=W_in rm2=stride rm3=C_out; N = stride^2*C_out, col=(i*s+j)*C_out+co */
+  VDN_ROWMAP_TEMPORAL = 2,      /* rows (b*D+d)*T+f -> (b*T+f)*D+d : rm0=T rm1=D (applies to out, res, res2, out2) */
+  VDN_ROWMAP_PATCH_TOKENS = 3,  /* rows b*P+p -> b*(P+1)+1+p, residual row 1+p (pos_embed) : rm0=P */
+  VDN_ROWMAP_QKV_SPLIT = 4      /* cols [0,2C) -> out[row, col]; cols [2C,3C) -> out2 = V^T[(b*heads+h)*64+d][t] : rm0=tokens rm1=ld of V^T rm2=C */
+};
+
+typedef struct vdn_gemm_desc {
+  const void* a;   /* plain: [M, K] 16-bit row-major, row stride lda elements (lda*2 % 16 == 0).
+                      conv : NHWC [B, H, W, K] 16-bit, dense */
+  const void* w;   /* [N, Kw] 16-bit, K contiguous, row stride ldw.  conv: Kw = 9 * roundup(K,64), tap-major (r*3+s) */
+  int64_t M, N, K; /* conv: M = B*H*W, K = C_in */
+  int64_t lda, ldw;
+  int32_t conv;    /* 0 = plain GEMM, 1 = 3x3 stride-1 pad-1 convolution (implicit GEMM, 9 shifted TMA boxes) */
+  int32_t B, H, W; /* conv geometry */
+  const float* bias;  /* [N] or NULL */
+  const float* gamma; /* [N] or NULL: out = res + gamma * (acc + bias)  (LayerScale) */
+  const void* res;    /* residual or NULL */
+  int32_t res_f32;    /* residual is fp32 (else 16-bit) */
+  int64_t ld_res;
+  const void* res2;   /* second residual, 16-bit, or NULL */
+  int64_t ld_res2;
+  void* out;
+  int32_t out_f32;    /* output is fp32 (else 16-bit) */
+  int64_t ldc;
+  void* out2;         /* optional second 16-bit output: copy (or ReLU copy) of out; V^T for QKV_SPLIT */
+  int32_t out2_relu;
+  int64_t ld_out2;
+  int32_t act;        /* VDN_ACT_* applied to (acc + bias) */
+  int32_t geglu;      /* weights interleaved (value_j, gate_j): out[:, j] = value_j * gelu(gate_j); out has N/2 columns */
+  int32_t row_map;
+  int32_t rm0, rm1, rm2, rm3;
+  const float* head_w; /* if non-NULL (N <= 32): out_f32[row] = relu(sum_j relu(acc_j+bias_j) * head_w[j] + head_b) */
+  float head_b;
+} vdn_gemm_desc;
+
+int vdn_gemm(const vdn_gemm_desc* d, void* stream);
+
+/* ---- spatial (ViT) flash attention, tcgen05 ---------------------------------------------------
+ * softmax(q k^T / sqrt(64)) v per (frame, head), head_dim 64.  Replaces attention.py:53-58 / the xformers
+ * memory_efficient_attention call at attention.py:76.
+ * qk : [B*tokens, ld_qk] 16-bit, q at cols [0,C), k at cols [C,2C) (head h = cols h*64..h*64+63)
+ * vT : [B*heads, 64, ld_vT] 16-bit (written by vdn_gemm with VDN_ROWMAP_QKV_SPLIT)
+ * out: [B*tokens, C] 16-bit                                                                              */
+int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens,
+                   int32_t heads, void* stream);
+
+/* ---- temporal attention over T frames per (pixel, head) ----------------------------------------
+ * Replaces CrossAttention._attention (motion_module/attention.py:182-211) as called from
+ * TemporalAttention.forward (motion_module.py:296-313).  qkv: [D*T, 3C] rows (d, f), q|k|v column blocks.
+ * out: [D*T, C].  head_dim = C/heads (any multiple of 8).                                              */
+int vdn_temporal_attn(const void* qkv, void* out, int32_t D, int32_t T, int32_t C, int32_t heads, void* stream);
+
+/* ---- normalisation ----------------------------------------------------------------------------- */
+/* LayerNorm over C of fp32 rows -> 16-bit.  out row = map(row):
+ *   drop_first == 0: same row.  drop_first == 1 (ViT taps, dinov2.py:309-316): rows_per_batch rows per batch,
+ *   row 0 (cls) is dropped, row j>0 of batch b goes to b*(rows_per_batch-1)+j-1.
+ * pe (optional, fp32 [pe_len, C]): added after the affine, row r uses pe[r % pe_len] (motion_module.py:211). */
+int vdn_layernorm(const float* x, const float* w, const float* b, void* out, int64_t rows, int32_t C, float eps, int32_t drop_first,
+                  int32_t rows_per_batch, const float* pe, int32_t pe_len, void* stream);
+/* GroupNorm(32) statistics of NHWC 16-bit frames: stats[f*32+g] = (mean, rstd).  motion_module.py:84,111 */
+int vdn_groupnorm_stats(const void* x, float* stats, int32_t frames, int32_t D, int32_t C, int32_t groups, float eps, void* stream);
+/* apply GroupNorm + affine and transpose frame-major [T, D, C] -> pixel-major rows (b*D+d)*T+f, 16-bit.  motion_module.py:111-114,253 */
+int vdn_groupnorm_apply_tc(const void* x, const float* stats, const float* w, const float* b, void* out, int32_t Bv, int32_t T, int32_t D,
+                           int32_t C, int32_t groups, void* stream);
+
+/* ---- layout / elementwise ------------------------------------------------------------------------ */
+/* fp32 NCHW image [B,3,H,W] -> 16-bit patch rows [B*ph*pw, Kp] (Kp >= 588, zero padded), col = c*196 + i*14 + j. patch_embed.py:76 */
+int vdn_patch_im2col(const float* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Kp, void* stream);
+/* x[b, 0, :] = cls + pos[0]  for every frame (dinov2.py:219-220) */
+int vdn_write_cls(float* x, const float* cls, const float* pos, int32_t B, int32_t tokens, int32_t C, void* stream);
+/* im2col for the 3x3 stride-2 pad-1 conv (dpt.py:84-89): NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] */
+int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* bilinear resize, align_corners=True, NHWC 16-bit (F.interpolate at util/blocks.py:155-157, dpt_temporal.py:104-106).
+ * optional second input added before interpolation is NOT supported; relu_out writes max(x,0). */
+int vdn_bilinear_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, int32_t relu_out,
+                      void* stream);
+/* bilinear resize of fp32 planes [N,H,W] -> [N,Ho,Wo], align_corners=True, optional ReLU (video_depth.py:63-64,110) */
+int vdn_bilinear_f32(const float* x, float* out, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t relu, void* stream);
+/* out = relu(x), 16-bit, n elements (util/blocks.py:78) */
+int vdn_relu16(const void* x, void* out, int64_t n, void* stream);
+/* out16 = x (fp32 -> 16-bit), n elements */
+int vdn_cast_f32_to_16(const float* x, void* out, int64_t n, void* stream);
+
+/* ---- window alignment (video_depth.py:118-154, utils/util.py:40-74) ------------------------------- */
+/* sums[0..4] = (sum p*p, sum p, n, sum p*t, sum t) over n elements, accumulated in fp64 on device */
+int vdn_lsq_sums(const float* pred, const float* target, int64_t n, double* sums5, void* stream);
+/* out = max(x*scale + shift, 0) */
+int vdn_affine_clamp(const float* x, float* out, int64_t n, const float* scale_shift, void* stream);
+/* out = pre*(1-w) + max(post*scale+shift,0)*w */
+int vdn_crossfade(const float* pre, const float* post, float* out, int64_t n, const float* scale_shift, float w, void* stream);
+
+/* ---- depth -> normals (utils/normal_utils.py:4-52): reflect-pad Sobel/8, n = normalize(-Ix,-Iy,1) ------- */
+int vdn_sobel_normals(const float* depth, float* normals, int32_t N, int32_t H, int32_t W, int32_t channels_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDN_B200_H_ */

@@ -1,0 +1,390 @@
+"""`-m gpu`: every C-ABI kernel against a plain PyTorch fp32 reference of the same op, on the same (pre-rounded) inputs.
+
+Tolerances: operands are rounded to the 16-bit operand format *before* both sides run, so differences are only fp32
+accumulation order and the final 16-bit output rounding (2^-11 relative for fp16, 2^-8 for bf16)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from video_depth_normal_v2_b200 import ops as _ops
+    _ops.set_operand_dtype(torch.float16)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _ops
+
+
+def _r16(ops, *shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(ops.operand_dtype())
+
+
+def _f32(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+def _close(name, got, ref, rtol=3e-3, atol_frac=2e-3):
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{name}: non-finite output"
+    atol = atol_frac * float(ref.abs().max()) + 1e-6
+    err = (got - ref).abs()
+    bad = err > (atol + rtol * ref.abs())
+    msg = f"{name}: max_abs_err={float(err.max()):.3e} ref_max={float(ref.abs().max()):.3e} bad_frac={float(bad.float().mean()):.4f}"
+    print(msg)
+    assert not bad.any(), msg
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(300, 256, 192), (128, 32, 64), (1000, 48, 384), (777, 96, 1024), (2000, 384, 384),
+                                   (1370 * 2, 1152, 384), (4096, 1024, 4096), (5000, 3072, 1024), (333, 64, 592)])
+def test_gemm_plain_bias(ops, M, N, K):
+    a, w = _r16(ops, M, K, seed=1), _r16(ops, N, K, scale=K ** -0.5, seed=2)
+    bias = _f32(N, seed=3)
+    out = torch.empty(M, N, device="cuda", dtype=ops.operand_dtype())
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias)
+    torch.cuda.synchronize()
+    _close(f"gemm {M}x{N}x{K}", out, a.float() @ w.float().T + bias)
+
+
+def test_gemm_layerscale_residual_fp32_inplace(ops):
+    M, N, K = 1370 * 3, 384, 1536
+    a, w = _r16(ops, M, K, seed=1), _r16(ops, N, K, scale=K ** -0.5, seed=2)
+    bias, gamma = _f32(N, seed=3), _f32(N, seed=4)
+    x = _f32(M, N, seed=5)
+    ref = x + gamma * (a.float() @ w.float().T + bias)
+    ops.gemm(a, w, x, M=M, N=N, K=K, bias=bias, gamma=gamma, res=x)
+    torch.cuda.synchronize()
+    _close("gemm ls+res", x, ref, rtol=1e-4, atol_frac=1e-5)
+
+
+def test_gemm_gelu_and_out2(ops):
+    M, N, K = 1111, 1536, 384
+    a, w = _r16(ops, M, K, seed=1), _r16(ops, N, K, scale=K ** -0.5, seed=2)
+    bias = _f32(N, seed=3)
+    out = torch.empty(M, N, device="cuda", dtype=ops.operand_dtype())
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias, act=ops.ACT_GELU)
+    ref = F.gelu(a.float() @ w.float().T + bias)
+    torch.cuda.synchronize()
+    _close("gemm gelu", out, ref)
+    out32 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    out2 = torch.empty(M, N, device="cuda", dtype=ops.operand_dtype())
+    ops.gemm(a, w, out32, M=M, N=N, K=K, bias=bias, out2=out2, out2_relu=True)
+    torch.cuda.synchronize()
+    lin = a.float() @ w.float().T + bias
+    _close("gemm f32 out", out32, lin, rtol=1e-4, atol_frac=1e-5)
+    _close("gemm relu out2", out2, F.relu(lin))
+
+
+def test_gemm_geglu(ops):
+    M, C = 999, 192
+    a = _r16(ops, M, C, seed=1)
+    w = _r16(ops, 8 * C, C, scale=C ** -0.5, seed=2)  # reference layout: rows [0,4C) value, [4C,8C) gate
+    bias = _f32(8 * C, seed=3)
+    wi = torch.stack([w[:4 * C], w[4 * C:]], dim=1).reshape(8 * C, C).contiguous()
+    bi = torch.stack([bias[:4 * C], bias[4 * C:]], dim=1).reshape(8 * C).contiguous()
+    out = torch.empty(M, 4 * C, device="cuda", dtype=ops.operand_dtype())
+    ops.gemm(a, wi, out, M=M, N=8 * C, K=C, bias=bi, geglu=True)
+    val, gate = (a.float() @ w.float().T + bias).chunk(2, dim=-1)
+    torch.cuda.synchronize()
+    _close("gemm geglu", out, val * F.gelu(gate))
+
+
+def _pack_conv3x3(w, dtype):
+    co, ci = w.shape[:2]
+    cip = (ci + 63) // 64 * 64
+    p = torch.zeros(co, 9, cip, device=w.device, dtype=torch.float32)
+    p[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    return p.reshape(co, 9 * cip).to(dtype).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(2, 37, 37, 64, 64), (1, 19, 19, 384, 64), (3, 20, 24, 48, 64), (1, 74, 74, 256, 256), (2, 40, 48, 96, 128),
+                                         (1, 148, 148, 64, 32)])
+def test_conv3x3_implicit_gemm(ops, B, H, W, Ci, Co):
+    od = ops.operand_dtype()
+    x = _r16(ops, B, H, W, Ci, seed=1)
+    w = (_f32(Co, Ci, 3, 3, scale=(9 * Ci) ** -0.5, seed=2)).to(od)
+    bias = _f32(Co, seed=3)
+    res, res2 = _r16(ops, B, H, W, Co, seed=4), _r16(ops, B, H, W, Co, seed=5)
+    out = torch.empty(B, H, W, Co, device="cuda", dtype=od)
+    out2 = torch.empty_like(out)
+    ops.gemm(x, _pack_conv3x3(w.float(), od), out, M=B * H * W, N=Co, K=Ci, conv=(B, H, W), bias=bias, res=res, res2=res2, out2=out2, out2_relu=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float() + res2.float()
+    torch.cuda.synchronize()
+    _close(f"conv3x3 {B}x{H}x{W} {Ci}->{Co}", out, ref)
+    _close("conv3x3 relu copy", out2, F.relu(ref))
+    # relu epilogue, no residual
+    ops.gemm(x, _pack_conv3x3(w.float(), od), out, M=B * H * W, N=Co, K=Ci, conv=(B, H, W), bias=bias, act=ops.ACT_RELU)
+    torch.cuda.synchronize()
+    _close("conv3x3 relu", out, F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)))
+
+
+@pytest.mark.parametrize("Ci", [32, 128])
+def test_conv3x3_depth_head(ops, Ci):
+    od = ops.operand_dtype()
+    B, H, W = 2, 70, 84
+    x = _r16(ops, B, H, W, Ci, seed=1)
+    w = _f32(32, Ci, 3, 3, scale=(9 * Ci) ** -0.5, seed=2).to(od)
+    bias, hw = _f32(32, seed=3), _f32(32, seed=4).abs()
+    out = torch.empty(B, H, W, device="cuda", dtype=torch.float32)
+    ops.gemm(x, _pack_conv3x3(w.float(), od), out, M=B * H * W, N=32, K=Ci, conv=(B, H, W), bias=bias, head_w=hw, head_b=0.05)
+    mid = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1))
+    ref = F.relu((mid * hw.view(1, 32, 1, 1)).sum(1) + 0.05)
+    torch.cuda.synchronize()
+    _close("conv3x3 head", out, ref, rtol=1e-4, atol_frac=1e-5)
+
+
+@pytest.mark.parametrize("s,Co", [(4, 48), (2, 96), (4, 256)])
+def test_gemm_pixel_shuffle_convtranspose(ops, s, Co):
+    od = ops.operand_dtype()
+    B, H, W, Ci = 2, 5, 6, Co
+    x = _r16(ops, B, H, W, Ci, seed=1)
+    wt = _f32(Ci, Co, s, s, scale=Ci ** -0.5, seed=2).to(od)  # ConvTranspose2d layout (in, out, kh, kw)
+    bt = _f32(Co, seed=3)
+    wg = wt.float().permute(2, 3, 1, 0).reshape(s * s * Co, Ci).to(od).contiguous()  # row (i*s+j)*Co+co
+    bg = bt.repeat(s * s).contiguous()
+    out = torch.empty(B, H * s, W * s, Co, device="cuda", dtype=od)
+    ops.gemm(x, wg, out, M=B * H * W, N=s * s * Co, K=Ci, bias=bg, ldc=Co, row_map=ops.ROWMAP_PIXEL_SHUFFLE, rm=(H, W, s, Co))
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), bt, stride=s).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    _close(f"convT s{s}", out, ref)
+
+
+def test_gemm_temporal_rowmap(ops):
+    od = ops.operand_dtype()
+    Bv, T, D, C = 2, 4, 30, 64
+    h = _r16(ops, Bv * D * T, C, seed=1)  # rows (b*D+d)*T+f
+    w, bias = _r16(ops, C, C, scale=C ** -0.5, seed=2), _f32(C, seed=3)
+    xin = _r16(ops, Bv * T, D, C, seed=4)  # frame-major NHWC residual
+    out = torch.empty(Bv * T, D, C, device="cuda", dtype=od)
+    ops.gemm(h, w, out, M=Bv * D * T, N=C, K=C, bias=bias, res=xin, row_map=ops.ROWMAP_TEMPORAL, rm=(T, D, 0, 0))
+    lin = (h.float() @ w.float().T + bias).reshape(Bv, D, T, C).permute(0, 2, 1, 3).reshape(Bv * T, D, C)
+    torch.cuda.synchronize()
+    _close("gemm temporal map", out, lin + xin.float())
+
+
+def test_gemm_patch_tokens(ops):
+    od = ops.operand_dtype()
+    B, P, C, Kp = 3, 30, 384, 592
+    a = _r16(ops, B * P, Kp, seed=1)
+    a[:, 588:] = 0
+    w, bias = _r16(ops, C, Kp, scale=588 ** -0.5, seed=2), _f32(C, seed=3)
+    pos = _f32(P + 1, C, seed=4)
+    x = torch.zeros(B * (P + 1), C, device="cuda")
+    ops.gemm(a, w, x, M=B * P, N=C, K=Kp, bias=bias, res=pos, row_map=ops.ROWMAP_PATCH_TOKENS, rm=(P, 0, 0, 0))
+    ref = torch.zeros(B, P + 1, C, device="cuda")
+    ref[:, 1:] = (a.float() @ w.float().T + bias).reshape(B, P, C) + pos[1:]
+    torch.cuda.synchronize()
+    _close("gemm patch tokens", x, ref.reshape(-1, C), rtol=1e-4, atol_frac=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,tokens,heads", [(2, 300, 6), (1, 1370, 16), (3, 31, 6), (1, 129, 2), (2, 2443, 6)])
+def test_qkv_split_and_flash_attention(ops, B, tokens, heads):
+    od = ops.operand_dtype()
+    C = heads * 64
+    x = _r16(ops, B * tokens, C, seed=1)
+    w, bias = _r16(ops, 3 * C, C, scale=C ** -0.5, seed=2), _f32(3 * C, seed=3)
+    npad = (tokens + 7) // 8 * 8
+    qk = torch.empty(B * tokens, 2 * C, device="cuda", dtype=od)
+    vT = torch.full((B * heads, 64, npad), float("nan"), device="cuda", dtype=od)  # padding must never be read as data
+    ops.gemm(x, w, qk, M=B * tokens, N=3 * C, K=C, bias=bias, ldc=2 * C, out2=vT, row_map=ops.ROWMAP_QKV_SPLIT, rm=(tokens, npad, C, 0))
+    qkv = (x.float() @ w.float().T + bias)
+    torch.cuda.synchronize()
+    _close("qkv split q|k", qk, qkv[:, :2 * C])
+    v_ref = qkv[:, 2 * C:].reshape(B, tokens, heads, 64).permute(0, 2, 3, 1).reshape(B * heads, 64, tokens)
+    _close("qkv split vT", vT[:, :, :tokens], v_ref)
+    out = torch.empty(B * tokens, C, device="cuda", dtype=od)
+    ops.flash_attn(qk, vT, out, B, tokens, heads)
+    torch.cuda.synchronize()
+    q, k = qk[:, :C].float().reshape(B, tokens, heads, 64).transpose(1, 2), qk[:, C:].float().reshape(B, tokens, heads, 64).transpose(1, 2)
+    v = vT[:, :, :tokens].float().reshape(B, heads, 64, tokens).transpose(2, 3)
+    att = ((q * 0.125) @ k.transpose(-1, -2)).softmax(-1)
+    ref = (att @ v).transpose(1, 2).reshape(B * tokens, C)
+    _close(f"flash attn B{B} N{tokens} H{heads}", out, ref, rtol=5e-3, atol_frac=3e-3)
+
+
+@pytest.mark.parametrize("D,T,C", [(50, 32, 192), (37, 32, 1024), (20, 4, 64), (9, 32, 384), (100, 7, 256)])
+def test_temporal_attention(ops, D, T, C):
+    od = ops.operand_dtype()
+    heads = 8
+    qkv = _r16(ops, D * T, 3 * C, seed=1)
+    out = torch.empty(D * T, C, device="cuda", dtype=od)
+    ops.temporal_attn(qkv, out, D, T, C, heads)
+    torch.cuda.synchronize()
+    dh = C // heads
+    q, k, v = [t.float().reshape(D, T, heads, dh).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+    ref = ((q @ k.transpose(-1, -2) * dh ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(D * T, C)
+    _close(f"temporal attn D{D} T{T} C{C}", out, ref)
+
+
+# ----------------------------------------------------------------------------------------------- norms / layout
+@pytest.mark.parametrize("rows,C", [(1370 * 2, 384), (1000, 1024), (77, 64), (300, 192), (64, 256)])
+def test_layernorm(ops, rows, C):
+    x, w, b = _f32(rows, C, scale=3.0, seed=1) + 0.5, _f32(C, seed=2), _f32(C, seed=3)
+    out = torch.empty(rows, C, device="cuda", dtype=ops.operand_dtype())
+    ops.layernorm(x, w, b, out, 1e-6)
+    torch.cuda.synchronize()
+    _close("layernorm", out, F.layer_norm(x, (C,), w, b, 1e-6))
+    pe = _f32(32, C, seed=4)
+    ops.layernorm(x, w, b, out, 1e-5, pe=pe[:4].contiguous())
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x, (C,), w, b, 1e-5) + pe[:4].repeat((rows + 3) // 4, 1)[:rows]
+    _close("layernorm+pe", out, ref)
+
+
+def test_layernorm_drop_cls(ops):
+    B, N, C = 3, 31, 384
+    x, w, b = _f32(B * N, C, seed=1), _f32(C, seed=2), _f32(C, seed=3)
+    out = torch.empty(B * (N - 1), C, device="cuda", dtype=ops.operand_dtype())
+    ops.layernorm(x, w, b, out, 1e-6, drop_first=True, rows_per_batch=N)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x, (C,), w, b, 1e-6).reshape(B, N, C)[:, 1:].reshape(-1, C)
+    _close("layernorm drop cls", out, ref)
+
+
+@pytest.mark.parametrize("Bv,T,D,C", [(1, 4, 30, 192), (2, 3, 25, 64), (1, 32, 361, 1024), (1, 5, 40, 384)])
+def test_groupnorm_transpose(ops, Bv, T, D, C):
+    od = ops.operand_dtype()
+    x = (_f32(Bv * T, D, C, scale=2.0, seed=1) + 0.3).to(od)
+    w, b = _f32(C, seed=2), _f32(C, seed=3)
+    stats = torch.empty(Bv * T * 32 * 2, device="cuda")
+    ops.groupnorm_stats(x, stats, Bv * T, D, C, 32, 1e-6)
+    out = torch.empty(Bv * D * T, C, device="cuda", dtype=od)
+    ops.groupnorm_apply_tc(x, stats, w, b, out, Bv, T, D, C, 32)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, w, b, 1e-6).permute(0, 2, 1)  # (BT, D, C)
+    ref = ref.reshape(Bv, T, D, C).permute(0, 2, 1, 3).reshape(Bv * D * T, C)
+    _close("groupnorm+transpose", out, ref)
+
+
+def test_patch_im2col_and_cls(ops):
+    B, H, W, C = 2, 42, 56, 384
+    img = _f32(B, 3, H, W, seed=1)
+    P = (H // 14) * (W // 14)
+    out = torch.empty(B * P, 592, device="cuda", dtype=ops.operand_dtype())
+    ops.patch_im2col(img, out, B, H, W, 592)
+    torch.cuda.synchronize()
+    ref = F.unfold(img, kernel_size=14, stride=14).transpose(1, 2).reshape(B * P, 588)
+    _close("patch im2col", out[:, :588], ref, rtol=1e-3, atol_frac=1e-3)
+    assert (out[:, 588:] == 0).all()
+    x = torch.zeros(B * (P + 1), C, device="cuda")
+    cls, pos = _f32(C, seed=2), _f32(P + 1, C, seed=3)
+    ops.write_cls(x, cls, pos, B, P + 1, C)
+    torch.cuda.synchronize()
+    assert torch.allclose(x.reshape(B, P + 1, C)[:, 0], (cls + pos[0]).expand(B, C))
+    assert (x.reshape(B, P + 1, C)[:, 1:] == 0).all()
+
+
+def test_im2col_3x3_s2(ops):
+    od = ops.operand_dtype()
+    B, H, W, C = 2, 37, 23, 64
+    x = _r16(ops, B, H, W, C, seed=1)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(B * Ho * Wo, 9 * C, device="cuda", dtype=od)
+    ops.im2col_3x3_s2(x, out, B, H, W, C)
+    torch.cuda.synchronize()
+    ref = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # (B, C*9, L) with index c*9+tap
+    ref = ref.reshape(B, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * C)
+    assert torch.equal(out.float(), ref)
+
+
+@pytest.mark.parametrize("H,W,Ho,Wo,C", [(19, 19, 37, 37, 64), (37, 37, 74, 74, 256), (10, 12, 20, 24, 64), (40, 48, 70, 84, 32), (5, 6, 5, 6, 8)])
+def test_bilinear_nhwc(ops, H, W, Ho, Wo, C):
+    od = ops.operand_dtype()
+    x = _r16(ops, 2, H, W, C, seed=1)
+    out = torch.empty(2, Ho, Wo, C, device="cuda", dtype=od)
+    ops.bilinear_nhwc(x, out, 2, H, W, Ho, Wo, C)
+    torch.cuda.synchronize()
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    _close("bilinear nhwc", out, ref)
+
+
+def test_bilinear_f32_and_relu(ops):
+    x = _f32(3, 70, 84, seed=1)
+    out = torch.empty(3, 90, 120, device="cuda")
+    ops.bilinear_f32(x, out, 3, 70, 84, 90, 120, relu=True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.interpolate(x[:, None], size=(90, 120), mode="bilinear", align_corners=True)[:, 0])
+    _close("bilinear f32", out, ref, rtol=1e-5, atol_frac=1e-6)
+    out2 = torch.empty_like(x)
+    ops.bilinear_f32(x, out2, 3, 70, 84, 70, 84, relu=False)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, x)  # same-size align_corners resize is the identity
+
+
+def test_relu_cast(ops):
+    x = _r16(ops, 1024, 72, seed=1)
+    out = torch.empty_like(x)
+    ops.relu16(x, out)
+    xf = _f32(333, 64, seed=2)
+    o16 = torch.empty(333, 64, device="cuda", dtype=ops.operand_dtype())
+    ops.cast_f32_to_16(xf, o16)
+    torch.cuda.synchronize()
+    assert torch.equal(out, F.relu(x))
+    assert torch.equal(o16, xf.to(ops.operand_dtype()))
+
+
+# ----------------------------------------------------------------------------------------------- post-processing
+def test_alignment_kernels(ops):
+    import numpy as np
+    from oracle import vdn_oracle as O
+    p, t = _f32(2 * 70 * 84, seed=1).abs() + 0.1, _f32(2 * 70 * 84, seed=2).abs() * 2 + 0.3
+    sums = torch.empty(5, device="cuda", dtype=torch.float64)
+    ops.lsq_sums(p, t, sums)
+    torch.cuda.synchronize()
+    a00, a01, a11, b0, b1 = [float(v) for v in sums.cpu()]
+    det = a00 * a11 - a01 * a01
+    scale, shift = (a11 * b0 - a01 * b1) / det, (-a01 * b0 + a00 * b1) / det
+    s_ref, t_ref = O.compute_scale_and_shift(p.cpu().numpy(), t.cpu().numpy())
+    assert abs(scale - s_ref) < 1e-4 * abs(s_ref) + 1e-6 and abs(shift - t_ref) < 1e-4 * abs(t_ref) + 1e-5
+    ss = torch.tensor([-0.7, 0.4], device="cuda")
+    out = torch.empty_like(p)
+    ops.affine_clamp(p, out, ss)
+    out2 = torch.empty_like(p)
+    ops.crossfade(t, p, out2, ss, 3.0 / 7.0)
+    torch.cuda.synchronize()
+    assert torch.allclose(out, (p * -0.7 + 0.4).clamp_min(0), atol=1e-6)
+    assert torch.allclose(out2, t * (1 - 3.0 / 7.0) + (p * -0.7 + 0.4).clamp_min(0) * (3.0 / 7.0), atol=1e-6)
+
+
+def test_sobel_normals(ops):
+    from oracle import vdn_oracle as O
+    d = _f32(3, 60, 80, seed=1).abs()
+    n = torch.empty(3, 3, 60, 80, device="cuda")
+    ops.sobel_normals(d, n, 3, 60, 80, 3)
+    torch.cuda.synchronize()
+    ref = O.sobel_normals(d[:, None])
+    assert O.normal_angle_deg(n, ref) < 0.05
+    _close("sobel normals", n, ref, rtol=1e-4, atol_frac=1e-5)
+
+
+def test_errors_are_loud(ops):
+    a = torch.zeros(8, 64)  # CPU tensor
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, a, a, M=8, N=8, K=64)
+    x = torch.zeros(2, 3, 15, 28, device="cuda")
+    with pytest.raises(RuntimeError, match="multiples of the patch size"):
+        ops.patch_im2col(x, torch.empty(4, 592, device="cuda", dtype=ops.operand_dtype()), 2, 15, 28, 592)
+
+
+def test_bf16_operand_mode(ops):
+    ops.set_operand_dtype(torch.bfloat16)
+    try:
+        M, N, K = 500, 256, 320
+        a, w = _r16(ops, M, K, seed=1), _r16(ops, N, K, scale=K ** -0.5, seed=2)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, w, out, M=M, N=N, K=K)
+        torch.cuda.synchronize()
+        _close("gemm bf16", out, a.float() @ w.float().T, rtol=1e-2, atol_frac=8e-3)
+    finally:
+        ops.set_operand_dtype(torch.float16)

@@ -1,0 +1,400 @@
+// Attention kernels.
+//
+// 1. vdn_flash_attn — spatial ViT attention (head_dim 64, non-causal) on tcgen05:
+//      S  = Q K^T   : UMMA 128 x 128 x 64, Q/K tiles K-major in 128B-swizzled smem (TMA, 5-D map straight out of the QKV GEMM output)
+//      P  = softmax : 4 softmax warps, one query row per thread, S read from TMEM twice (max pass, exp pass) to keep registers low,
+//                     online rescaling in fp32, P written to smem as a 128B-swizzled K-major A operand
+//      O += P V     : UMMA 128 x 64 x 128 with V^T (d-major rows, keys contiguous; produced transposed by the QKV GEMM epilogue)
+//                     fresh TMEM accumulator per KV tile, running O kept in registers and rescaled there
+//    One CTA per (128-query tile, head, frame); K/V^T double-buffered through TMA; 2 CTAs per SM overlap softmax with MMA.
+//
+// 2. vdn_temporal_attn — motion-module attention over T <= 32 frames per (pixel, head): tiny 32x32 problems, CUDA cores,
+//    one warp per (pixel, head), lane = query frame, K/V broadcast from padded shared memory.
+#include "../../include/vdn_b200.h"
+#include "vdn_common.cuh"
+#include "vdn_host.h"
+
+namespace vdn {
+
+// ------------------------------------------------------------------------------------------------
+// flash attention
+// ------------------------------------------------------------------------------------------------
+constexpr int FA_BM = 128;     // queries per CTA
+constexpr int FA_BN = 128;     // keys per tile
+constexpr int FA_D = 64;       // head dim
+constexpr int FA_THREADS = 160;
+constexpr int FA_TILE = FA_BM * FA_D * 2;  // 16 KB : Q tile, K tile, V^T tile (2 x 8 KB chunks), P chunk
+constexpr int FA_SMEM = FA_TILE /*Q*/ + 2 * FA_TILE /*K*/ + 2 * FA_TILE /*V^T*/ + 2 * FA_TILE /*P, two 64-key chunks*/ + 256;
+constexpr int FA_TMEM_COLS = 256;  // S: cols [0,128), PV: cols [128,192)
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT, void* __restrict__ out, int tokens,
+                  int heads, int C, int fmt) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + FA_TILE;            // 2 buffers
+  uint8_t* sV = smem + 3 * FA_TILE;        // 2 buffers, each = 2 chunks [64 d rows x 64 keys]
+  uint8_t* sP = smem + 5 * FA_TILE;        // 2 chunks [128 rows x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * FA_TILE);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_free = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_full = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FA_BM;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nt = (tokens + FA_BN - 1) / FA_BN;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1024-byte alignment
+
+  if (warp_idx == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQK);
+      tma_prefetch_desc(&tmVT);
+      mbar_init(q_full, 1);
+      mbar_init(&kv_full[0], 1);
+      mbar_init(&kv_full[1], 1);
+      mbar_init(&kv_empty[0], 1);
+      mbar_init(&kv_empty[1], 1);
+      mbar_init(s_full, 1);
+      mbar_init(s_free, 128);
+      mbar_init(p_full, 128);
+      mbar_init(pv_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, FA_TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_PV = tmem_base + 128;
+
+  if (warp_idx == 4) {
+    if (lane == 0) {
+      // ---------------- TMA producer + MMA issuer (one thread) ----------------
+      auto load_kv = [&](int j) {
+        const int buf = j & 1;
+        mbar_arrive_expect_tx(&kv_full[buf], 2 * FA_TILE);
+        tma_load_5d(sK + buf * FA_TILE, &tmQK, &kv_full[buf], 0, h, 1, j * FA_BN, b);
+        tma_load_3d(sV + buf * FA_TILE, &tmVT, &kv_full[buf], j * FA_BN, 0, b * heads + h);
+        tma_load_3d(sV + buf * FA_TILE + FA_TILE / 2, &tmVT, &kv_full[buf], j * FA_BN + 64, 0, b * heads + h);
+      };
+      const uint32_t idesc_s = make_idesc(fmt ? 1u : 0u, 128, 128);
+      const uint32_t idesc_pv = make_idesc(fmt ? 1u : 0u, 128, 64);
+      auto issue_s = [&](int j) {
+        const uint64_t dq = make_sdesc_sw128(smem_u32(sQ));
+        const uint64_t dk = make_sdesc_sw128(smem_u32(sK + (j & 1) * FA_TILE));
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tmem_S, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      mbar_arrive_expect_tx(q_full, FA_TILE);
+      tma_load_5d(sQ, &tmQK, q_full, 0, h, 0, q0, b);
+      load_kv(0);
+      if (nt > 1) load_kv(1);
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < nt; ++j) {
+        const int buf = j & 1;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        {
+          const uint32_t pbase = smem_u32(sP);
+          const uint32_t vbase = smem_u32(sV + buf * FA_TILE);
+#pragma unroll
+          for (int kk = 0; kk < FA_BN / 16; ++kk) {
+            const uint32_t chunk = kk >> 2, sub = kk & 3;
+            const uint64_t dp = make_sdesc_sw128(pbase + chunk * FA_TILE) + 2 * sub;
+            const uint64_t dv = make_sdesc_sw128(vbase + chunk * (FA_TILE / 2)) + 2 * sub;
+            umma_f16(tmem_PV, dp, dv, idesc_pv, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(pv_full);
+          umma_commit(&kv_empty[buf]);
+        }
+        if (j + 1 < nt) {
+          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(s_free, j & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        if (j + 2 < nt) {
+          mbar_wait(&kv_empty[buf], (j >> 1) & 1);
+          load_kv(j + 2);
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax / output warps: one query row per thread ----------------
+    const int r = threadIdx.x;  // 0..127 == TMEM lane
+    const uint32_t lane_off = uint32_t(warp_idx * 32) << 16;
+    const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+    float m = -INFINITY, l = 0.0f;
+    float O[FA_D];
+#pragma unroll
+    for (int i = 0; i < FA_D; ++i) O[i] = 0.0f;
+    uint8_t* p_row = sP + r * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < nt; ++j) {
+      const int kv0 = j * FA_BN;
+      const int nvalid = min(FA_BN, tokens - kv0);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx * sc);
+      const float alpha = exp2f(m - m_new);
+      // fold in the previous tile's P V, then rescale the running output
+      if (j > 0) {
+        mbar_wait(pv_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_PV + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < FA_D; ++i) O[i] *= alpha;
+      l *= alpha;
+      // pass 2: probabilities -> swizzled smem (A operand of the P V MMA)
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c * 32 + i < nvalid) ? exp2f(__uint_as_float(v[i]) * sc - m_new) : 0.0f;
+          float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(__uint_as_float(v[i + 1]) * sc - m_new) : 0.0f;
+          l += p0 + p1;
+          pk[i >> 1] = pack16(p0, p1, fmt);
+        }
+        // 32 keys = 4 x 16-byte pieces; piece index within the 64-key chunk = (c & 1) * 4 + q
+        uint8_t* chunk_row = p_row + (c >> 1) * FA_TILE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int piece = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(chunk_row + ((piece ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      m = m_new;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(s_free);
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_full, (nt - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_PV + lane_off + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
+    }
+    if (q0 + r < tokens) {
+      const float inv = 1.0f / l;
+      uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q0 + r) * C + h * FA_D;
+#pragma unroll
+      for (int i = 0; i < FA_D; i += 8) {
+        uint4 u;
+        u.x = pack16(O[i] * inv, O[i + 1] * inv, fmt);
+        u.y = pack16(O[i + 2] * inv, O[i + 3] * inv, fmt);
+        u.z = pack16(O[i + 4] * inv, O[i + 5] * inv, fmt);
+        u.w = pack16(O[i + 6] * inv, O[i + 7] * inv, fmt);
+        *reinterpret_cast<uint4*>(o + i) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// temporal attention (T <= 32)
+// ------------------------------------------------------------------------------------------------
+constexpr int TA_WARPS = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(TA_WARPS * 32)
+temporal_attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int D, int Tn, int C, int heads) {
+  extern __shared__ __align__(16) uint8_t ta_smem[];
+  const int dh = C / heads;
+  const int ldp = dh + 2;  // padded row (elements): odd number of 32-bit words -> conflict-free per-lane rows
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  T* sq = reinterpret_cast<T*>(ta_smem) + (size_t)warp * 3 * 32 * ldp;
+  T* sk = sq + 32 * ldp;
+  T* sv = sk + 32 * ldp;
+  const float scale = rsqrtf((float)dh);
+  const long long npairs = (long long)D * heads;
+  const int vec_per_row = dh / 8;  // 16-byte vectors per head row
+
+  for (long long pair = (long long)blockIdx.x * TA_WARPS + warp; pair < npairs; pair += (long long)gridDim.x * TA_WARPS) {
+    const long long d = pair / heads;
+    const int hd = int(pair - d * heads);
+    const T* base = qkv + (d * Tn) * (3LL * C) + hd * dh;
+    // cooperative load of the q, k, v tiles [Tn x dh]
+    for (int idx = lane; idx < 3 * Tn * vec_per_row; idx += 32) {
+      const int which = idx / (Tn * vec_per_row);
+      const int rem = idx - which * Tn * vec_per_row;
+      const int f = rem / vec_per_row, v8 = rem - f * vec_per_row;
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)f * 3 * C + which * C + v8 * 8);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sq + (which * 32 + f) * ldp + v8 * 8);
+      dst[0] = u.x; dst[1] = u.y; dst[2] = u.z; dst[3] = u.w;
+    }
+    __syncwarp();
+    float s[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s[j] = 0.0f;
+    const int f = lane < Tn ? lane : 0;
+    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(sq + f * ldp);
+    for (int c2 = 0; c2 < dh / 2; ++c2) {
+      const float2 q2 = T16<T>::unpack(qrow[c2]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < Tn) {
+          const float2 k2 = T16<T>::unpack(reinterpret_cast<const uint32_t*>(sk + j * ldp)[c2]);
+          s[j] = fmaf(q2.x, k2.x, fmaf(q2.y, k2.y, s[j]));
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < Tn) mx = fmaxf(mx, s[j] * scale);
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s[j] = (j < Tn) ? __expf(s[j] * scale - mx) : 0.0f;
+      sum += s[j];
+    }
+    const float inv = 1.0f / sum;
+    T* orow = out + (d * Tn + f) * (long long)C + hd * dh;
+    for (int c0 = 0; c0 < dh; c0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < Tn) {
+          const uint32_t* vr = reinterpret_cast<const uint32_t*>(sv + j * ldp + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 v2 = T16<T>::unpack(vr[i]);
+            acc[2 * i] = fmaf(s[j], v2.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(s[j], v2.y, acc[2 * i + 1]);
+          }
+        }
+      }
+      if (lane < Tn) {
+        uint4 u;
+        u.x = T16<T>::pack(acc[0] * inv, acc[1] * inv);
+        u.y = T16<T>::pack(acc[2] * inv, acc[3] * inv);
+        u.z = T16<T>::pack(acc[4] * inv, acc[5] * inv);
+        u.w = T16<T>::pack(acc[6] * inv, acc[7] * inv);
+        *reinterpret_cast<uint4*>(orow + c0) = u;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace vdn
+
+using namespace vdn;
+
+extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens, int32_t heads,
+                              void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!qk || !vT || !out) return set_error("vdn_flash_attn: null pointer");
+  if (B <= 0 || tokens <= 0 || heads <= 0) return set_error("vdn_flash_attn: bad shape");
+  const int C = heads * FA_D;
+  if (ld_qk < 2 * C || (ld_qk * 2) % 16 != 0) return set_error("vdn_flash_attn: ld_qk must be >= 2*C and 16-byte aligned");
+  if (ld_vT < tokens || (ld_vT * 2) % 16 != 0) return set_error("vdn_flash_attn: ld_vT must be >= tokens and a multiple of 8");
+  const int fmt = get_operand_format();
+  CUtensorMap tmQK, tmVT;
+  {
+    // element (b, t, s, h, d) of the q|k buffer; innermost first: d, h, s (0 = q, 1 = k), t, b
+    const uint64_t dims[5] = {(uint64_t)FA_D, (uint64_t)heads, 2, (uint64_t)tokens, (uint64_t)B};
+    const uint64_t strides[4] = {(uint64_t)FA_D * 2, (uint64_t)C * 2, (uint64_t)ld_qk * 2, (uint64_t)ld_qk * 2 * tokens};
+    const uint32_t box[5] = {(uint32_t)FA_D, 1, 1, (uint32_t)FA_BM, 1};
+    if (make_tensor_map(&tmQK, qk, fmt, 5, dims, strides, box)) return 1;
+  }
+  {
+    // V^T: (bh, d, t) with t contiguous; innermost first: t, d, bh.  Columns >= tokens are out of bounds -> zero filled.
+    const uint64_t dims[3] = {(uint64_t)tokens, (uint64_t)FA_D, (uint64_t)B * heads};
+    const uint64_t strides[2] = {(uint64_t)ld_vT * 2, (uint64_t)ld_vT * 2 * FA_D};
+    const uint32_t box[3] = {64, (uint32_t)FA_D, 1};
+    if (make_tensor_map(&tmVT, vT, fmt, 3, dims, strides, box)) return 1;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(flash_attn): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((tokens + FA_BM - 1) / FA_BM, heads, B);
+  flash_attn_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQK, tmVT, out, tokens, heads, C, fmt);
+  count_launch();
+  return check_launch("flash_attn_kernel");
+}
+
+extern "C" int vdn_temporal_attn(const void* qkv, void* out, int32_t D, int32_t T, int32_t C, int32_t heads, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!qkv || !out) return set_error("vdn_temporal_attn: null pointer");
+  if (T <= 0 || T > 32) return set_error("vdn_temporal_attn: T must be in [1, 32]");
+  if (heads <= 0 || C % heads != 0 || (C / heads) % 8 != 0) return set_error("vdn_temporal_attn: head_dim must be a multiple of 8");
+  const int dh = C / heads;
+  const size_t smem = (size_t)TA_WARPS * 3 * 32 * (dh + 2) * 2;
+  const long long npairs = (long long)D * heads;
+  long long blocks = (npairs + TA_WARPS - 1) / TA_WARPS;
+  const long long max_blocks = (long long)num_sms() * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  const int fmt = get_operand_format();
+  cudaError_t e;
+  if (fmt) {
+    e = cudaFuncSetAttribute(temporal_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(std::string("temporal_attn smem: ") + cudaGetErrorString(e));
+    temporal_attn_kernel<__nv_bfloat16><<<(unsigned)blocks, TA_WARPS * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                                          reinterpret_cast<__nv_bfloat16*>(out), D, T, C, heads);
+  } else {
+    e = cudaFuncSetAttribute(temporal_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(std::string("temporal_attn smem: ") + cudaGetErrorString(e));
+    temporal_attn_kernel<__half><<<(unsigned)blocks, TA_WARPS * 32, smem, stream>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out),
+                                                                                 D, T, C, heads);
+  }
+  count_launch();
+  return check_launch("temporal_attn_kernel");
+}

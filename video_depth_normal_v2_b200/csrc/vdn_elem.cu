@@ -1,0 +1,540 @@
+// Bandwidth-bound kernels: LayerNorm, GroupNorm (+ frame->pixel-major transpose), patch im2col, stride-2 im2col,
+// bilinear resize (align_corners=True), ReLU / casts, window alignment reductions, Sobel normals.
+// All are coalesced, 16-byte vectorised where the layout allows, warp-shuffle reductions, no shared-memory staging
+// beyond block reductions (each element is touched once).
+#include "../../include/vdn_b200.h"
+#include "vdn_common.cuh"
+#include "vdn_host.h"
+
+namespace vdn {
+
+static inline unsigned grid_for(long long work_items, int per_block, int waves = 16) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (C <= 1024), fp32 statistics, 16-bit output
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 8;  // float4 per lane -> C <= 32 * 8 * 4 = 1024
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, void* __restrict__ out, long long rows,
+                 int C, float eps, int drop_first, int rows_per_batch, const float* __restrict__ pe, int pe_len, int fmt) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = C >> 2;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    long long orow = row;
+    if (drop_first) {
+      const long long bb = row / rows_per_batch;
+      const int j = int(row - bb * rows_per_batch);
+      if (j == 0) continue;
+      orow = bb * (rows_per_batch - 1) + j - 1;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    float4 v[LN_MAXV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        v[i] = xr[idx];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + bq * bq) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    const float4* pr = pe ? reinterpret_cast<const float4*>(pe + (row % pe_len) * C) : nullptr;
+    uint2* orow_p = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + orow * C);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w) + idx);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(b) + idx);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + be.x;
+        y.y = (v[i].y - mean) * rstd * g.y + be.y;
+        y.z = (v[i].z - mean) * rstd * g.z + be.z;
+        y.w = (v[i].w - mean) * rstd * g.w + be.w;
+        if (pr) {
+          const float4 p4 = __ldg(pr + idx);
+          y.x += p4.x; y.y += p4.y; y.z += p4.z; y.w += p4.w;
+        }
+        uint2 u;
+        u.x = pack16(y.x, y.y, fmt);
+        u.y = pack16(y.z, y.w, fmt);
+        orow_p[idx] = u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: one block per (frame, group); two passes over an L2-resident slice
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, int D, int C, int groups, float eps, int fmt) {
+  const int f = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cg = C / groups;
+  const uint16_t* base = reinterpret_cast<const uint16_t*>(x) + (long long)f * D * C + g * cg;
+  __shared__ double red[8];
+  __shared__ float s_mean;
+  const long long n = (long long)D * cg;
+  // pass 1: mean
+  float s = 0.0f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long d = i / cg;
+    const int c = int(i - d * cg);
+    s += load16(base, d * C + c, fmt);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (double)s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    s_mean = (float)(t / (double)n);
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  float q = 0.0f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long d = i / cg;
+    const int c = int(i - d * cg);
+    const float v = load16(base, d * C + c, fmt) - mean;
+    q += v * v;
+  }
+  q = warp_sum(q);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (double)q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    stats[2 * blockIdx.x] = mean;
+    stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(t / (double)n + (double)eps));
+  }
+}
+
+// apply + transpose: one warp per (frame, pixel) row; out row = (b*D + d)*T + f
+__global__ void __launch_bounds__(256)
+groupnorm_apply_tc_kernel(const void* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w, const float* __restrict__ b,
+                          void* __restrict__ out, int Bv, int T, int D, int C, int groups, int fmt) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows = (long long)Bv * T * D;
+  const int cg = C / groups;
+  const int nvec = C >> 3;  // 8 x 16-bit per 16-byte vector
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const long long frame = row / D;  // b*T + f
+    const int d = int(row - frame * D);
+    const long long bb = frame / T;
+    const int f = int(frame - bb * T);
+    const long long orow = (bb * D + d) * T + f;
+    const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x) + row * C);
+    uint4* orp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + orow * C);
+    for (int idx = lane; idx < nvec; idx += 32) {
+      const uint4 u = xr[idx];
+      const int c0 = idx * 8;
+      float v[8];
+      float2 t;
+      t = unpack16(u.x, fmt); v[0] = t.x; v[1] = t.y;
+      t = unpack16(u.y, fmt); v[2] = t.x; v[3] = t.y;
+      t = unpack16(u.z, fmt); v[4] = t.x; v[5] = t.y;
+      t = unpack16(u.w, fmt); v[6] = t.x; v[7] = t.y;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        const int g = c / cg;
+        const float mean = __ldg(stats + 2 * (frame * groups + g));
+        const float rstd = __ldg(stats + 2 * (frame * groups + g) + 1);
+        v[i] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+      }
+      uint4 o;
+      o.x = pack16(v[0], v[1], fmt);
+      o.y = pack16(v[2], v[3], fmt);
+      o.z = pack16(v[4], v[5], fmt);
+      o.w = pack16(v[6], v[7], fmt);
+      orp[idx] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patch_im2col_kernel(const float* __restrict__ img, void* __restrict__ out, int B, int H, int W, int Kp, int fmt) {
+  const int ph = H / 14, pw = W / 14;
+  const long long total = (long long)B * ph * pw * Kp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / Kp;
+    const int k = int(idx - row * Kp);
+    float v = 0.0f;
+    if (k < 588) {
+      const int c = k / 196, rem = k - c * 196;
+      const int i = rem / 14, j = rem - i * 14;
+      const long long bimg = row / (ph * pw);
+      const int p = int(row - bimg * ph * pw);
+      const int py = p / pw, px = p - py * pw;
+      v = img[((bimg * 3 + c) * H + py * 14 + i) * (long long)W + px * 14 + j];
+    }
+    store16(out, idx, v, fmt);
+  }
+}
+
+__global__ void write_cls_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int B, int tokens, int C) {
+  const int total = B * C;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int bb = idx / C, c = idx - bb * C;
+    x[(long long)bb * tokens * C + c] = cls[c] + pos[c];
+  }
+}
+
+// NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] for the 3x3 stride-2 pad-1 conv; column = (r*3+s)*C + c; 8 channels per thread
+__global__ void __launch_bounds__(256)
+im2col_3x3_s2_kernel(const void* __restrict__ x, void* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int cv = C >> 3;
+  const long long total = (long long)B * Ho * Wo * 9 * cv;
+  const uint4* xin = reinterpret_cast<const uint4*>(x);
+  uint4* o = reinterpret_cast<uint4*>(out);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(idx % cv);
+    long long t = idx / cv;
+    const int tap = int(t % 9);
+    t /= 9;
+    const int wo = int(t % Wo);
+    t /= Wo;
+    const int ho = int(t % Ho);
+    const long long bimg = t / Ho;
+    const int hi = ho * 2 - 1 + tap / 3, wi = wo * 2 - 1 + tap % 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = xin[((bimg * H + hi) * W + wi) * cv + c8];
+    o[idx] = v;
+  }
+}
+
+// PyTorch's align_corners=True source index: scale = (in-1)/(out-1) (0 if out==1), src = scale*dst
+__device__ __forceinline__ void ac_coords(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  const float src = scale * (float)dst;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_kernel(const void* __restrict__ x, void* __restrict__ out, int B, int H, int W, int Ho, int Wo, int C, int relu_out, int fmt) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * Ho * Wo * cv;
+  const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.0f;
+  const float sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.0f;
+  const uint4* xin = reinterpret_cast<const uint4*>(x);
+  uint4* o = reinterpret_cast<uint4*>(out);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(idx % cv);
+    long long t = idx / cv;
+    const int wo = int(t % Wo);
+    t /= Wo;
+    const int ho = int(t % Ho);
+    const long long bimg = t / Ho;
+    int h0, h1, w0, w1;
+    float lh, lw;
+    ac_coords(ho, sh, H, h0, h1, lh);
+    ac_coords(wo, sw, W, w0, w1, lw);
+    const uint4 a = xin[((bimg * H + h0) * W + w0) * cv + c8];
+    const uint4 b = xin[((bimg * H + h0) * W + w1) * cv + c8];
+    const uint4 c = xin[((bimg * H + h1) * W + w0) * cv + c8];
+    const uint4 d = xin[((bimg * H + h1) * W + w1) * cv + c8];
+    const float w00 = (1.0f - lh) * (1.0f - lw), w01 = (1.0f - lh) * lw, w10 = lh * (1.0f - lw), w11 = lh * lw;
+    const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
+    uint4 r;
+    uint32_t* pr = &r.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fa = unpack16(pa[i], fmt), fb = unpack16(pb[i], fmt), fc = unpack16(pc[i], fmt), fd = unpack16(pd[i], fmt);
+      float y0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
+      float y1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+      if (relu_out) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
+      pr[i] = pack16(y0, y1, fmt);
+    }
+    o[idx] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H, int W, int Ho, int Wo, int relu) {
+  const long long total = (long long)N * Ho * Wo;
+  const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.0f;
+  const float sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.0f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int wo = int(idx % Wo);
+    long long t = idx / Wo;
+    const int ho = int(t % Ho);
+    const long long n = t / Ho;
+    int h0, h1, w0, w1;
+    float lh, lw;
+    ac_coords(ho, sh, H, h0, h1, lh);
+    ac_coords(wo, sw, W, w0, w1, lw);
+    const float* p = x + n * (long long)H * W;
+    // same association as ATen's upsample_bilinear2d: h0lambda*(w0lambda*a + w1lambda*b) + h1lambda*(w0lambda*c + w1lambda*d)
+    float y = (1.0f - lh) * ((1.0f - lw) * p[h0 * (long long)W + w0] + lw * p[h0 * (long long)W + w1]) +
+              lh * ((1.0f - lw) * p[h1 * (long long)W + w0] + lw * p[h1 * (long long)W + w1]);
+    if (relu) y = fmaxf(y, 0.0f);
+    out[idx] = y;
+  }
+}
+
+__global__ void __launch_bounds__(256) relu16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long nvec, int fmt) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = x[idx];
+    const uint32_t* pu = &u.x;
+    uint4 r;
+    uint32_t* pr = &r.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack16(pu[i], fmt);
+      pr[i] = pack16(fmaxf(f.x, 0.0f), fmaxf(f.y, 0.0f), fmt);
+    }
+    out[idx] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_to_16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, long long nvec, int fmt) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[idx];
+    uint2 u;
+    u.x = pack16(v.x, v.y, fmt);
+    u.y = pack16(v.z, v.w, fmt);
+    out[idx] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// window alignment (least-squares scale/shift sums, affine + clamp, cross-fade)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lsq_sums_kernel(const float* __restrict__ p, const float* __restrict__ t, long long n, double* __restrict__ sums) {
+  double a00 = 0, a01 = 0, b0 = 0, b1 = 0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const double pv = p[idx], tv = t[idx];
+    a00 += pv * pv;
+    a01 += pv;
+    b0 += pv * tv;
+    b1 += tv;
+  }
+  __shared__ double red[4][8];
+  double vals[4] = {a00, a01, b0, b1};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0;
+    for (int i = 0; i < 8; ++i) v += red[threadIdx.x][i];
+    const int slot = threadIdx.x == 0 ? 0 : threadIdx.x == 1 ? 1 : threadIdx.x == 2 ? 3 : 4;
+    atomicAdd(&sums[slot], v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 4) atomicAdd(&sums[2], (double)n);
+}
+
+__global__ void __launch_bounds__(256) affine_clamp_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, const float* __restrict__ ss) {
+  const float sc = ss[0], sh = ss[1];
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+    out[idx] = fmaxf(x[idx] * sc + sh, 0.0f);
+}
+
+__global__ void __launch_bounds__(256)
+crossfade_kernel(const float* __restrict__ pre, const float* __restrict__ post, float* __restrict__ out, long long n, const float* __restrict__ ss, float w) {
+  const float sc = ss[0], sh = ss[1];
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const float pv = fmaxf(post[idx] * sc + sh, 0.0f);
+    out[idx] = pre[idx] * (1.0f - w) + pv * w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sobel normals (reflect padding, kernel / 8): n = normalize(-Ix, -Iy, 1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void __launch_bounds__(256)
+sobel_normals_kernel(const float* __restrict__ depth, float* __restrict__ normals, int N, int H, int W, int ch) {
+  const long long total = (long long)N * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = int(idx % W);
+    long long t = idx / W;
+    const int y = int(t % H);
+    const long long n = t / H;
+    const float* p = depth + n * (long long)H * W;
+    const int ym = reflect(y - 1, H), yp = reflect(y + 1, H), xm = reflect(x - 1, W), xp = reflect(x + 1, W);
+    const float a = p[ym * (long long)W + xm], b = p[ym * (long long)W + x], c = p[ym * (long long)W + xp];
+    const float d = p[y * (long long)W + xm], f = p[y * (long long)W + xp];
+    const float g = p[yp * (long long)W + xm], h = p[yp * (long long)W + x], i = p[yp * (long long)W + xp];
+    const float ix = ((a - c) + 2.0f * (d - f) + (g - i)) * 0.125f;
+    const float iy = ((a + 2.0f * b + c) - (g + 2.0f * h + i)) * 0.125f;
+    const float nx = -ix, ny = -iy;
+    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + 1.0f + 1e-8f);
+    float* o = normals + n * (long long)ch * H * W + (long long)y * W + x;
+    o[0] = nx * inv;
+    if (ch > 1) o[(long long)H * W] = ny * inv;
+    if (ch > 2) o[2LL * H * W] = inv;
+  }
+}
+
+}  // namespace vdn
+
+using namespace vdn;
+#define VDN_STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v)
+
+extern "C" int vdn_layernorm(const float* x, const float* w, const float* b, void* out, int64_t rows, int32_t C, float eps, int32_t drop_first,
+                             int32_t rows_per_batch, const float* pe, int32_t pe_len, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !w || !b || !out) return set_error("vdn_layernorm: null pointer");
+  if (C % 4 != 0 || C > 32 * LN_MAXV * 4) return set_error("vdn_layernorm: C must be a multiple of 4 and <= 1024");
+  if (drop_first && (rows_per_batch < 2 || rows % rows_per_batch != 0)) return set_error("vdn_layernorm: bad rows_per_batch");
+  if (pe && pe_len <= 0) return set_error("vdn_layernorm: bad pe_len");
+  layernorm_kernel<<<grid_for(rows, 8), 256, 0, stream>>>(x, w, b, out, rows, C, eps, drop_first, rows_per_batch, pe, pe_len, get_operand_format());
+  count_launch();
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int vdn_groupnorm_stats(const void* x, float* stats, int32_t frames, int32_t D, int32_t C, int32_t groups, float eps, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !stats) return set_error("vdn_groupnorm_stats: null pointer");
+  if (groups <= 0 || C % groups != 0) return set_error("vdn_groupnorm_stats: C must be divisible by groups");
+  groupnorm_stats_kernel<<<frames * groups, 256, 0, stream>>>(x, stats, D, C, groups, eps, get_operand_format());
+  count_launch();
+  return check_launch("groupnorm_stats_kernel");
+}
+
+extern "C" int vdn_groupnorm_apply_tc(const void* x, const float* stats, const float* w, const float* b, void* out, int32_t Bv, int32_t T, int32_t D,
+                                      int32_t C, int32_t groups, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !stats || !w || !b || !out) return set_error("vdn_groupnorm_apply_tc: null pointer");
+  if (C % 8 != 0 || C % groups != 0) return set_error("vdn_groupnorm_apply_tc: C must be a multiple of 8 and of groups");
+  groupnorm_apply_tc_kernel<<<grid_for((long long)Bv * T * D, 8), 256, 0, stream>>>(x, stats, w, b, out, Bv, T, D, C, groups, get_operand_format());
+  count_launch();
+  return check_launch("groupnorm_apply_tc_kernel");
+}
+
+extern "C" int vdn_patch_im2col(const float* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Kp, void* stream_v) {
+  VDN_STREAM;
+  if (!img || !out) return set_error("vdn_patch_im2col: null pointer");
+  if (H % 14 != 0 || W % 14 != 0) return set_error("vdn_patch_im2col: H and W must be multiples of the patch size 14");  // patch_embed.py:73-74
+  if (Kp < 588 || Kp % 8 != 0) return set_error("vdn_patch_im2col: Kp must be >= 588 and a multiple of 8");
+  patch_im2col_kernel<<<grid_for((long long)B * (H / 14) * (W / 14) * Kp, 256), 256, 0, stream>>>(img, out, B, H, W, Kp, get_operand_format());
+  count_launch();
+  return check_launch("patch_im2col_kernel");
+}
+
+extern "C" int vdn_write_cls(float* x, const float* cls, const float* pos, int32_t B, int32_t tokens, int32_t C, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !cls || !pos) return set_error("vdn_write_cls: null pointer");
+  write_cls_kernel<<<grid_for((long long)B * C, 256), 256, 0, stream>>>(x, cls, pos, B, tokens, C);
+  count_launch();
+  return check_launch("write_cls_kernel");
+}
+
+extern "C" int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !out) return set_error("vdn_im2col_3x3_s2: null pointer");
+  if (C % 8 != 0) return set_error("vdn_im2col_3x3_s2: C must be a multiple of 8");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  im2col_3x3_s2_kernel<<<grid_for((long long)B * Ho * Wo * 9 * (C / 8), 256), 256, 0, stream>>>(x, out, B, H, W, C);
+  count_launch();
+  return check_launch("im2col_3x3_s2_kernel");
+}
+
+extern "C" int vdn_bilinear_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, int32_t relu_out,
+                                 void* stream_v) {
+  VDN_STREAM;
+  if (!x || !out) return set_error("vdn_bilinear_nhwc: null pointer");
+  if (C % 8 != 0) return set_error("vdn_bilinear_nhwc: C must be a multiple of 8");
+  bilinear_nhwc_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256, 32), 256, 0, stream>>>(x, out, B, H, W, Ho, Wo, C, relu_out,
+                                                                                             get_operand_format());
+  count_launch();
+  return check_launch("bilinear_nhwc_kernel");
+}
+
+extern "C" int vdn_bilinear_f32(const float* x, float* out, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t relu, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !out) return set_error("vdn_bilinear_f32: null pointer");
+  bilinear_f32_kernel<<<grid_for((long long)N * Ho * Wo, 256, 32), 256, 0, stream>>>(x, out, N, H, W, Ho, Wo, relu);
+  count_launch();
+  return check_launch("bilinear_f32_kernel");
+}
+
+extern "C" int vdn_relu16(const void* x, void* out, int64_t n, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !out) return set_error("vdn_relu16: null pointer");
+  if (n % 8 != 0) return set_error("vdn_relu16: n must be a multiple of 8");
+  relu16_kernel<<<grid_for(n / 8, 256, 32), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n / 8, get_operand_format());
+  count_launch();
+  return check_launch("relu16_kernel");
+}
+
+extern "C" int vdn_cast_f32_to_16(const float* x, void* out, int64_t n, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !out) return set_error("vdn_cast_f32_to_16: null pointer");
+  if (n % 4 != 0) return set_error("vdn_cast_f32_to_16: n must be a multiple of 4");
+  cast_f32_to_16_kernel<<<grid_for(n / 4, 256, 32), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(out), n / 4,
+                                                                    get_operand_format());
+  count_launch();
+  return check_launch("cast_f32_to_16_kernel");
+}
+
+extern "C" int vdn_lsq_sums(const float* pred, const float* target, int64_t n, double* sums5, void* stream_v) {
+  VDN_STREAM;
+  if (!pred || !target || !sums5) return set_error("vdn_lsq_sums: null pointer");
+  cudaError_t e = cudaMemsetAsync(sums5, 0, 5 * sizeof(double), stream);
+  if (e != cudaSuccess) return set_error(std::string("vdn_lsq_sums memset: ") + cudaGetErrorString(e));
+  lsq_sums_kernel<<<grid_for(n, 256 * 8, 4), 256, 0, stream>>>(pred, target, n, sums5);
+  count_launch();
+  return check_launch("lsq_sums_kernel");
+}
+
+extern "C" int vdn_affine_clamp(const float* x, float* out, int64_t n, const float* scale_shift, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !out || !scale_shift) return set_error("vdn_affine_clamp: null pointer");
+  affine_clamp_kernel<<<grid_for(n, 256 * 4), 256, 0, stream>>>(x, out, n, scale_shift);
+  count_launch();
+  return check_launch("affine_clamp_kernel");
+}
+
+extern "C" int vdn_crossfade(const float* pre, const float* post, float* out, int64_t n, const float* scale_shift, float w, void* stream_v) {
+  VDN_STREAM;
+  if (!pre || !post || !out || !scale_shift) return set_error("vdn_crossfade: null pointer");
+  crossfade_kernel<<<grid_for(n, 256 * 4), 256, 0, stream>>>(pre, post, out, n, scale_shift, w);
+  count_launch();
+  return check_launch("crossfade_kernel");
+}
+
+extern "C" int vdn_sobel_normals(const float* depth, float* normals, int32_t N, int32_t H, int32_t W, int32_t channels_out, void* stream_v) {
+  VDN_STREAM;
+  if (!depth || !normals) return set_error("vdn_sobel_normals: null pointer");
+  if (H < 2 || W < 2 || channels_out < 1 || channels_out > 3) return set_error("vdn_sobel_normals: bad shape");
+  sobel_normals_kernel<<<grid_for((long long)N * H * W, 256, 32), 256, 0, stream>>>(depth, normals, N, H, W, channels_out);
+  count_launch();
+  return check_launch("sobel_normals_kernel");
+}

@@ -1,0 +1,378 @@
+"""Drop-in host modules for the reference's model API, running entirely on the sm_100a kernels.
+
+  VideoDepthAnything   <-> video_depth_anything/video_depth.py:35-156  (forward, infer_video_depth)
+  VideoDepthRefinerV5  <-> models/video_depth_model_v5.py:128-192      (forward; the class is also exported under the
+                                                                        reference's name ``VideoDepthAnything`` in .v5)
+
+Same constructor kwargs, same ``state_dict`` key names (packed once by packing.py), same tensor shapes in and out.
+Activations are token-major / NHWC 16-bit between kernels; the ViT residual stream and the motion-module hidden state
+stay fp32; every statistic / softmax / accumulator is fp32.  No PyTorch compute op is on the path — torch only allocates.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, packing
+
+ENCODER_CONFIGS = {
+    # video_depth.py:48-51 / run_video.py:28-33
+    "vits": dict(embed_dim=384, depth=12, heads=6, taps=[2, 5, 8, 11]),
+    "vitl": dict(embed_dim=1024, depth=24, heads=16, taps=[4, 11, 17, 23]),
+}
+
+# video_depth.py:29-33 — "infer settings, do not change"
+INFER_LEN = 32
+OVERLAP = 10
+KEYFRAMES = [0, 12, 24, 25, 26, 27, 28, 29, 30, 31]
+INTERP_LEN = 8
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+# ======================================================================================================
+# encoder: DINOv2 get_intermediate_layers (dinov2.py:212-231, 271-321; block.py:82-107)
+# ======================================================================================================
+def encoder_forward(enc: dict, x: torch.Tensor) -> List[torch.Tensor]:
+    """x (Bf, 3, H, W) fp32 -> 4 x [Bf*ph*pw, C] 16-bit (final-norm'ed patch tokens of the tapped blocks, cls dropped)."""
+    Bf, _, H, W = x.shape
+    if H % 14 != 0 or W % 14 != 0:
+        raise RuntimeError(f"Input image height {H} / width {W} is not a multiple of patch size 14")  # patch_embed.py:73-74
+    dev, od = x.device, ops.operand_dtype()
+    C, heads = enc["C"], enc["heads"]
+    ph, pw = H // 14, W // 14
+    P, N = ph * pw, ph * pw + 1
+    rows = Bf * N
+    pos = packing.encoder_pos_embed(enc, ph, pw, dev)
+    patches = _empty((Bf * P, 592), od, dev)
+    ops.patch_im2col(x.contiguous(), patches, Bf, H, W, 592)
+    xs = _empty((rows, C), torch.float32, dev)  # fp32 residual stream
+    ops.gemm(patches, enc["patch_w"], xs, M=Bf * P, N=C, K=592, bias=enc["patch_b"], res=pos, row_map=ops.ROWMAP_PATCH_TOKENS, rm=(P, 0, 0, 0))
+    ops.write_cls(xs, enc["cls"], pos, Bf, N, C)
+    npad = (N + 7) // 8 * 8
+    xn = _empty((rows, C), od, dev)
+    qk = _empty((rows, 2 * C), od, dev)
+    vT = _empty((Bf * heads, 64, npad), od, dev)
+    ao = _empty((rows, C), od, dev)
+    hid = _empty((rows, 4 * C), od, dev)
+    feats = []
+    for i, blk in enumerate(enc["blocks"]):
+        ops.layernorm(xs, blk["ln1_w"], blk["ln1_b"], xn, 1e-6)
+        ops.gemm(xn, blk["qkv"]["w"], qk, M=rows, N=3 * C, K=C, bias=blk["qkv"]["b"], ldc=2 * C, out2=vT, row_map=ops.ROWMAP_QKV_SPLIT,
+                 rm=(N, npad, C, 0))
+        ops.flash_attn(qk, vT, ao, Bf, N, heads)
+        ops.gemm(ao, blk["proj"]["w"], xs, M=rows, N=C, K=C, bias=blk["proj"]["b"], gamma=blk["ls1"], res=xs)
+        ops.layernorm(xs, blk["ln2_w"], blk["ln2_b"], xn, 1e-6)
+        ops.gemm(xn, blk["fc1"]["w"], hid, M=rows, N=4 * C, K=C, bias=blk["fc1"]["b"], act=ops.ACT_GELU)
+        ops.gemm(hid, blk["fc2"]["w"], xs, M=rows, N=C, K=4 * C, bias=blk["fc2"]["b"], gamma=blk["ls2"], res=xs)
+        if i in enc["taps"]:
+            f = _empty((Bf * P, C), od, dev)
+            ops.layernorm(xs, enc["norm_w"], enc["norm_b"], f, 1e-6, drop_first=True, rows_per_batch=N)
+            feats.append(f)
+    return feats
+
+
+# ======================================================================================================
+# temporal motion module (motion_module.py:60-136, 174-192, 245-326)
+# ======================================================================================================
+def motion_module_forward(mm: dict, x: torch.Tensor, Bv: int, T: int, D: int, relu_copy: bool = False):
+    """x: [Bv*T, D, C] 16-bit frame-major NHWC -> same layout; optional ReLU'd copy for the next RCU."""
+    dev, od, C = x.device, ops.operand_dtype(), mm["C"]
+    rows = Bv * D * T
+    stats = _empty((Bv * T * 32 * 2,), torch.float32, dev)
+    ops.groupnorm_stats(x, stats, Bv * T, D, C, 32, 1e-6)
+    xt = _empty((rows, C), od, dev)
+    ops.groupnorm_apply_tc(x, stats, mm["gn_w"], mm["gn_b"], xt, Bv, T, D, C, 32)
+    h = _empty((rows, C), torch.float32, dev)  # fp32 hidden state, pixel-major rows (b*D+d)*T+f
+    ops.gemm(xt, mm["proj_in"]["w"], h, M=rows, N=C, K=C, bias=mm["proj_in"]["b"])
+    n16 = xt  # reuse
+    qkv = _empty((rows, 3 * C), od, dev)
+    ao = _empty((rows, C), od, dev)
+    for a in mm["attn"]:
+        ops.layernorm(h, a["ln_w"], a["ln_b"], n16, 1e-5, pe=a["pe"][:T])
+        ops.gemm(n16, a["qkv_w"], qkv, M=rows, N=3 * C, K=C)
+        ops.temporal_attn(qkv, ao, Bv * D, T, C, 8)
+        ops.gemm(ao, a["out"]["w"], h, M=rows, N=C, K=C, bias=a["out"]["b"], res=h)
+    ops.layernorm(h, mm["ffn_w"], mm["ffn_b"], n16, 1e-5)
+    g = _empty((rows, 4 * C), od, dev)
+    ops.gemm(n16, mm["ff1_w"], g, M=rows, N=8 * C, K=C, bias=mm["ff1_b"], geglu=True)
+    h16 = ao  # reuse
+    ops.gemm(g, mm["ff2"]["w"], h, M=rows, N=C, K=4 * C, bias=mm["ff2"]["b"], res=h, out2=h16)
+    y = _empty((Bv * T, D, C), od, dev)
+    y_relu = _empty((Bv * T, D, C), od, dev) if relu_copy else None
+    ops.gemm(h16, mm["proj_out"]["w"], y, M=rows, N=C, K=C, bias=mm["proj_out"]["b"], res=x, row_map=ops.ROWMAP_TEMPORAL, rm=(T, D, 0, 0),
+             out2=y_relu, out2_relu=True)
+    return (y, y_relu) if relu_copy else y
+
+
+# ======================================================================================================
+# DPT head (dpt.py:126-159, dpt_temporal.py:53-127, util/blocks.py:68-162)
+# ======================================================================================================
+def _conv3(x, cw, B, H, W, out=None, **kw):
+    dev, od = x.device, ops.operand_dtype()
+    co = cw["co"]
+    if out is None:
+        out = _empty((B, H, W, co), od, dev)
+    ops.gemm(x, cw["w"], out, M=B * H * W, N=co, K=cw["ci"], conv=(B, H, W), bias=cw.get("b"), **kw)
+    return out
+
+
+def _rcu(x, x_relu, rcu, B, H, W, res2=None, relu_copy=False):
+    """ResidualConvUnit: conv2(relu(conv1(relu(x)))) + x (+ res2).  x_relu = relu(x) precomputed by the producer."""
+    dev, od = x.device, ops.operand_dtype()
+    c1 = _conv3(x_relu, rcu[0], B, H, W, act=ops.ACT_RELU)
+    out2 = _empty(tuple(x.shape), od, dev) if relu_copy else None
+    o = _conv3(c1, rcu[1], B, H, W, res=x, res2=res2, out2=out2, out2_relu=True)
+    return (o, out2) if relu_copy else o
+
+
+def _fusion(rf, B, H, W, Ho, Wo, x0, x0_relu=None, x1=None, x1_relu=None, relu_copy=False):
+    """FeatureFusionBlock: out_conv(upsample(RCU2(x0 + RCU1(x1)))).  The 1x1 out_conv commutes exactly with the
+    align_corners bilinear upsample (interpolation weights sum to 1), so it runs at the low resolution."""
+    dev, od = x0.device, ops.operand_dtype()
+    Fe = x0.shape[-1]
+    if x1 is not None:
+        s, s_relu = _rcu(x1, x1_relu, rf["rcu1"], B, H, W, res2=x0, relu_copy=True)
+    else:
+        s, s_relu = x0, x0_relu
+    o = _rcu(s, s_relu, rf["rcu2"], B, H, W)
+    lo = _empty((B, H, W, Fe), od, dev)
+    ops.gemm(o, rf["out_conv"]["w"], lo, M=B * H * W, N=Fe, K=Fe, bias=rf["out_conv"]["b"])
+    up = _empty((B, Ho, Wo, Fe), od, dev)
+    ops.bilinear_nhwc(lo, up, B, H, W, Ho, Wo, Fe)
+    if relu_copy:
+        upr = _empty((B, Ho, Wo, Fe), od, dev)
+        ops.relu16(up, upr)
+        return up, upr
+    return up
+
+
+def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: int, T: Optional[int]) -> torch.Tensor:
+    """-> depth fp32 [Bf, 14*ph, 14*pw] (after output_conv2's ReLUs)."""
+    dev, od = feats[0].device, ops.operand_dtype()
+    C, Fe, oc = feats[0].shape[-1], head["features"], head["oc"]
+    P = ph * pw
+    M = Bf * P
+    # ---- reassemble (dpt_temporal.py:55-69)
+    pr = []
+    for i in range(4):
+        t = _empty((M, oc[i]), od, dev)
+        ops.gemm(feats[i], head["projects"][i]["w"], t, M=M, N=oc[i], K=C, bias=head["projects"][i]["b"])
+        pr.append(t)
+    H1, W1, H2, W2, H3, W3 = 4 * ph, 4 * pw, 2 * ph, 2 * pw, ph, pw
+    H4, W4 = (ph - 1) // 2 + 1, (pw - 1) // 2 + 1
+    layer1 = _empty((Bf, H1, W1, oc[0]), od, dev)
+    ops.gemm(pr[0], head["resize0"]["w"], layer1, M=M, N=16 * oc[0], K=oc[0], bias=head["resize0"]["b"], ldc=oc[0],
+             row_map=ops.ROWMAP_PIXEL_SHUFFLE, rm=(ph, pw, 4, oc[0]))
+    layer2 = _empty((Bf, H2, W2, oc[1]), od, dev)
+    ops.gemm(pr[1], head["resize1"]["w"], layer2, M=M, N=4 * oc[1], K=oc[1], bias=head["resize1"]["b"], ldc=oc[1],
+             row_map=ops.ROWMAP_PIXEL_SHUFFLE, rm=(ph, pw, 2, oc[1]))
+    layer3 = pr[2].view(Bf, P, oc[2])
+    col = _empty((Bf * H4 * W4, 9 * oc[3]), od, dev)
+    ops.im2col_3x3_s2(pr[3], col, Bf, ph, pw, oc[3])
+    layer4 = _empty((Bf, H4 * W4, oc[3]), od, dev)
+    ops.gemm(col, head["resize3"]["w"], layer4, M=Bf * H4 * W4, N=oc[3], K=9 * oc[3], bias=head["resize3"]["b"])
+    # ---- temporal mixing on layer_3 / layer_4 (dpt_temporal.py:81-84)
+    if T is not None:
+        Bv = Bf // T
+        layer3 = motion_module_forward(head["mm"][0], layer3, Bv, T, P)
+        layer4 = motion_module_forward(head["mm"][1], layer4, Bv, T, H4 * W4)
+    # ---- layerN_rn (3x3, no bias) with ReLU'd copies for the RCUs
+    def rn(i, x, H, W):
+        out2 = _empty((Bf, H, W, Fe), od, dev)
+        o = _conv3(x, head["rn"][i], Bf, H, W, out2=out2, out2_relu=True)
+        return o, out2
+    l1r, l1r_relu = rn(0, layer1, H1, W1)
+    l2r, l2r_relu = rn(1, layer2, H2, W2)
+    l3r, l3r_relu = rn(2, layer3, H3, W3)
+    l4r, l4r_relu = rn(3, layer4, H4, W4)
+    # ---- refinenets (dpt_temporal.py:91-101)
+    rf = head["refine"]
+    path4 = _fusion(rf[4], Bf, H4, W4, H3, W3, l4r, x0_relu=l4r_relu)
+    if T is not None:
+        path4 = motion_module_forward(head["mm"][2], path4.view(Bf, H3 * W3, Fe), Bv, T, H3 * W3)
+    path3 = _fusion(rf[3], Bf, H3, W3, H2, W2, path4, x1=l3r, x1_relu=l3r_relu)
+    if T is not None:
+        path3 = motion_module_forward(head["mm"][3], path3.view(Bf, H2 * W2, Fe), Bv, T, H2 * W2)
+    path2 = _fusion(rf[2], Bf, H2, W2, H1, W1, path3, x1=l2r, x1_relu=l2r_relu)
+    path1 = _fusion(rf[1], Bf, H1, W1, 2 * H1, 2 * W1, path2, x1=l1r, x1_relu=l1r_relu)
+    # ---- output convs (dpt_temporal.py:103-111): 3x3 F->F/2, bilinear to 14x, fused [3x3 -> ReLU -> 1x1 -> ReLU]
+    o1 = _conv3(path1, head["oc1"], Bf, 2 * H1, 2 * W1)
+    Ho, Wo = 14 * ph, 14 * pw
+    up = _empty((Bf, Ho, Wo, Fe // 2), od, dev)
+    ops.bilinear_nhwc(o1, up, Bf, 2 * H1, 2 * W1, Ho, Wo, Fe // 2)
+    depth = _empty((Bf, Ho, Wo), torch.float32, dev)
+    _conv3(up, head["oc2"], Bf, Ho, Wo, out=depth, head_w=head["oc2_head_w"], head_b=head["oc2_head_b"])
+    return depth
+
+
+# ======================================================================================================
+# modules
+# ======================================================================================================
+class _PackedModule(nn.Module):
+    """Holds the reference-format state_dict on the host and the packed kernel weights on the device."""
+
+    _kind = ""
+
+    def __init__(self):
+        super().__init__()
+        self._sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self._packed: Optional[dict] = None
+        self._packed_key = None
+        self._dev = torch.device("cpu")
+
+    # --- nn.Module surface the reference callers use -----------------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True):
+        expected = self._expected_shapes()
+        missing = [k for k in expected if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in expected]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing keys {missing[:8]}, unexpected keys {unexpected[:8]}")
+        for k, shp in expected.items():
+            if k in state_dict and tuple(state_dict[k].shape) != tuple(shp):
+                raise RuntimeError(f"size mismatch for {k}: copying a param with shape {tuple(state_dict[k].shape)}, expected {tuple(shp)}")
+        self._sd = OrderedDict((k, state_dict[k].detach().to("cpu", torch.float32).clone()) for k in expected if k in state_dict)
+        self._packed = None
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def state_dict(self, *args, **kwargs):
+        return OrderedDict(self._sd)
+
+    def _apply(self, fn, recurse=True):
+        probe = fn(torch.empty(0))
+        if probe.device != self._dev:
+            self._dev = probe.device
+            self._packed = None
+        return super()._apply(fn, recurse)
+
+    def _weights(self) -> dict:
+        if self._dev.type != "cuda":
+            raise RuntimeError("this model runs on CUDA only (sm_100a kernels, no CPU fallback): call .cuda() first")
+        key = (self._dev, ops.operand_dtype())
+        if self._packed is None or self._packed_key != key:
+            if not self._sd:
+                raise RuntimeError("no weights loaded: call load_state_dict() with a reference-format state_dict")
+            self._packed = self._pack(self._sd, self._dev, ops.operand_dtype())
+            self._packed_key = key
+        return self._packed
+
+    def _expected_shapes(self) -> Dict[str, tuple]:
+        raise NotImplementedError
+
+    def _pack(self, sd, dev, dt) -> dict:
+        raise NotImplementedError
+
+
+def _encoder_shapes(prefix: str, cfg: dict) -> Dict[str, tuple]:
+    C = cfg["embed_dim"]
+    s = OrderedDict()
+    s[prefix + "cls_token"] = (1, 1, C)
+    s[prefix + "pos_embed"] = (1, 1370, C)
+    s[prefix + "mask_token"] = (1, C)
+    s[prefix + "patch_embed.proj.weight"] = (C, 3, 14, 14)
+    s[prefix + "patch_embed.proj.bias"] = (C,)
+    for i in range(cfg["depth"]):
+        p = f"{prefix}blocks.{i}."
+        for n in ("norm1", "norm2"):
+            s[p + n + ".weight"] = (C,)
+            s[p + n + ".bias"] = (C,)
+        s[p + "attn.qkv.weight"], s[p + "attn.qkv.bias"] = (3 * C, C), (3 * C,)
+        s[p + "attn.proj.weight"], s[p + "attn.proj.bias"] = (C, C), (C,)
+        s[p + "ls1.gamma"] = s[p + "ls2.gamma"] = (C,)
+        s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"] = (4 * C, C), (4 * C,)
+        s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = (C, 4 * C), (C,)
+    s[prefix + "norm.weight"] = s[prefix + "norm.bias"] = (C,)
+    return s
+
+
+def _head_shapes(prefix: str, C: int, Fe: int, oc: List[int], temporal: bool) -> Dict[str, tuple]:
+    s = OrderedDict()
+    for i in range(4):
+        s[f"{prefix}projects.{i}.weight"], s[f"{prefix}projects.{i}.bias"] = (oc[i], C, 1, 1), (oc[i],)
+    s[prefix + "resize_layers.0.weight"], s[prefix + "resize_layers.0.bias"] = (oc[0], oc[0], 4, 4), (oc[0],)
+    s[prefix + "resize_layers.1.weight"], s[prefix + "resize_layers.1.bias"] = (oc[1], oc[1], 2, 2), (oc[1],)
+    s[prefix + "resize_layers.3.weight"], s[prefix + "resize_layers.3.bias"] = (oc[3], oc[3], 3, 3), (oc[3],)
+    sc = prefix + "scratch."
+    for i in range(4):
+        s[f"{sc}layer{i + 1}_rn.weight"] = (Fe, oc[i], 3, 3)
+    for r in (1, 2, 3, 4):
+        p = f"{sc}refinenet{r}."
+        s[p + "out_conv.weight"], s[p + "out_conv.bias"] = (Fe, Fe, 1, 1), (Fe,)
+        for u in (1, 2):
+            for c in (1, 2):
+                s[f"{p}resConfUnit{u}.conv{c}.weight"], s[f"{p}resConfUnit{u}.conv{c}.bias"] = (Fe, Fe, 3, 3), (Fe,)
+    s[sc + "output_conv1.weight"], s[sc + "output_conv1.bias"] = (Fe // 2, Fe, 3, 3), (Fe // 2,)
+    s[sc + "output_conv2.0.weight"], s[sc + "output_conv2.0.bias"] = (32, Fe // 2, 3, 3), (32,)
+    s[sc + "output_conv2.2.weight"], s[sc + "output_conv2.2.bias"] = (1, 32, 1, 1), (1,)
+    if temporal:
+        for m, Cm in enumerate([oc[2], oc[3], Fe, Fe]):
+            p = f"{prefix}motion_modules.{m}.temporal_transformer."
+            s[p + "norm.weight"] = s[p + "norm.bias"] = (Cm,)
+            s[p + "proj_in.weight"], s[p + "proj_in.bias"] = (Cm, Cm), (Cm,)
+            tb = p + "transformer_blocks.0."
+            for a in range(2):
+                ab = f"{tb}attention_blocks.{a}."
+                s[ab + "to_q.weight"] = s[ab + "to_k.weight"] = s[ab + "to_v.weight"] = (Cm, Cm)
+                s[ab + "to_out.0.weight"], s[ab + "to_out.0.bias"] = (Cm, Cm), (Cm,)
+                s[ab + "pos_encoder.pe"] = (1, 32, Cm)
+                s[f"{tb}norms.{a}.weight"] = s[f"{tb}norms.{a}.bias"] = (Cm,)
+            s[tb + "ff.net.0.proj.weight"], s[tb + "ff.net.0.proj.bias"] = (8 * Cm, Cm), (8 * Cm,)
+            s[tb + "ff.net.2.weight"], s[tb + "ff.net.2.bias"] = (Cm, 4 * Cm), (Cm,)
+            s[tb + "ff_norm.weight"] = s[tb + "ff_norm.bias"] = (Cm,)
+            s[p + "proj_out.weight"], s[p + "proj_out.bias"] = (Cm, Cm), (Cm,)
+    return s
+
+
+class VideoDepthAnything(_PackedModule):
+    """Drop-in for video_depth_anything/video_depth.py:35 ``VideoDepthAnything`` (vits / vitl, use_bn=False, use_clstoken=False, pe='ape')."""
+
+    def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False, use_clstoken=False, num_frames=32, pe="ape"):
+        super().__init__()
+        if encoder not in ENCODER_CONFIGS:
+            raise KeyError(encoder)  # the reference indexes intermediate_layer_idx[encoder] (video_depth.py:48-51)
+        if use_bn or use_clstoken:
+            raise NotImplementedError("use_bn / use_clstoken are never exercised by the reference (SURVEY.md §8b)")
+        if pe != "ape":
+            raise NotImplementedError("pe='rope' is on the roadmap (SURVEY.md §8f rank 3)")
+        assert num_frames > 0
+        self.encoder = encoder
+        self.num_frames = num_frames
+        self.cfg = dict(ENCODER_CONFIGS[encoder], features=features, out_channels=list(out_channels))
+        self.intermediate_layer_idx = {k: v["taps"] for k, v in ENCODER_CONFIGS.items()}
+
+    def _expected_shapes(self):
+        s = _encoder_shapes("pretrained.", self.cfg)
+        s.update(_head_shapes("head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], True))
+        return s
+
+    def _pack(self, sd, dev, dt):
+        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "head.", self.cfg, dev, dt, True)}
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B, T, 3, H, W) fp32 -> depth (B, T, H, W) fp32   (video_depth.py:58-65)."""
+        if x.dim() != 5 or x.shape[2] != 3:
+            raise RuntimeError(f"expected (B, T, 3, H, W), got {tuple(x.shape)}")
+        w = self._weights()
+        B, T, _, H, W = x.shape
+        if T > 32:
+            raise RuntimeError("temporal attention supports at most 32 frames per window")
+        x = x.to(device=self._dev, dtype=torch.float32)
+        ph, pw = H // 14, W // 14
+        feats = encoder_forward(w["enc"], x.reshape(B * T, 3, H, W))
+        depth = head_forward(w["head"], feats, B * T, ph, pw, T)
+        # F.interpolate(depth, (H, W), align_corners=True) is the identity here (H == 14*ph) and the head's output is already >= 0
+        return depth.view(B, T, H, W)
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def infer_video_depth(self, frames, target_fps, input_size=518, device="cuda", fp32=False):
+        """Drop-in for video_depth.py:67-156.  frames: np.uint8 (N, H, W, 3) RGB -> (np.float32 (N, H, W), target_fps)."""
+        from .video import infer_video_depth
+        return infer_video_depth(self, frames, target_fps, input_size=input_size, device=device, fp32=fp32)

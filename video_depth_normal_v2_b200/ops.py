@@ -1,0 +1,202 @@
+"""Thin torch-tensor wrappers over the C ABI (include/vdn_b200.h).  PyTorch supplies device memory and streams only;
+every op here launches a hand-written sm_100a kernel on the current CUDA stream.  No fallbacks: CPU tensors raise."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ROWMAP_IDENTITY, ROWMAP_PIXEL_SHUFFLE, ROWMAP_TEMPORAL, ROWMAP_PATCH_TOKENS, ROWMAP_QKV_SPLIT = 0, 1, 2, 3, 4
+
+_FMT_DTYPE = {0: torch.float16, 1: torch.bfloat16}
+
+
+def lib():
+    return _lib.load()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {lib().vdn_last_error().decode()}")
+
+
+def set_operand_dtype(dtype: torch.dtype):
+    """Library-wide 16-bit operand format: torch.float16 (default) or torch.bfloat16."""
+    fmt = {torch.float16: 0, torch.bfloat16: 1}[dtype]
+    _check(lib().vdn_set_operand_format(fmt), "vdn_set_operand_format")
+
+
+def operand_dtype() -> torch.dtype:
+    return _FMT_DTYPE[lib().vdn_get_operand_format()]
+
+
+def launch_count() -> int:
+    return int(lib().vdn_launch_count())
+
+
+def reset_launch_count():
+    lib().vdn_reset_launch_count()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (this path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: Optional[int] = None, ldw: Optional[int] = None,
+         ldc: Optional[int] = None, conv: Optional[Tuple[int, int, int]] = None, bias=None, gamma=None, res=None, ld_res=None, res2=None,
+         ld_res2=None, out2=None, out2_relu=False, ld_out2=None, act=ACT_NONE, geglu=False, row_map=ROWMAP_IDENTITY,
+         rm: Sequence[int] = (0, 0, 0, 0), head_w=None, head_b: float = 0.0):
+    """out = epilogue(A @ W^T) on tcgen05.  See vdn_gemm_desc in include/vdn_b200.h for the field meanings."""
+    od = operand_dtype()
+    d = GemmDesc()
+    d.a = _ptr(a, od, "a")
+    d.w = _ptr(w, od, "w")
+    d.M, d.N, d.K = M, N, K
+    d.lda = lda if lda is not None else K
+    d.ldw = ldw if ldw is not None else w.shape[-1]
+    if conv is not None:
+        d.conv, (d.B, d.H, d.W) = 1, conv
+    d.bias = _ptr(bias, torch.float32, "bias")
+    d.gamma = _ptr(gamma, torch.float32, "gamma")
+    n_out = N // 2 if geglu else N
+    if res is not None:
+        d.res = _ptr(res, None, "res")
+        d.res_f32 = 1 if res.dtype == torch.float32 else 0
+        if not d.res_f32 and res.dtype != od:
+            raise RuntimeError("res must be fp32 or the operand dtype")
+        d.ld_res = ld_res if ld_res is not None else n_out
+    if res2 is not None:
+        d.res2 = _ptr(res2, od, "res2")
+        d.ld_res2 = ld_res2 if ld_res2 is not None else n_out
+    d.out = _ptr(out, None, "out")
+    d.out_f32 = 1 if out.dtype == torch.float32 else 0
+    if not d.out_f32 and out.dtype != od:
+        raise RuntimeError("out must be fp32 or the operand dtype")
+    d.ldc = ldc if ldc is not None else n_out
+    if out2 is not None:
+        d.out2 = _ptr(out2, od, "out2")
+        d.out2_relu = 1 if out2_relu else 0
+        d.ld_out2 = ld_out2 if ld_out2 is not None else n_out
+    d.act, d.geglu, d.row_map = act, 1 if geglu else 0, row_map
+    d.rm0, d.rm1, d.rm2, d.rm3 = [int(v) for v in rm]
+    if head_w is not None:
+        d.head_w = _ptr(head_w, torch.float32, "head_w")
+        d.head_b = float(head_b)
+    _check(lib().vdn_gemm(C.byref(d), _stream()), "vdn_gemm")
+    return out
+
+
+def flash_attn(qk: torch.Tensor, vT: torch.Tensor, out: torch.Tensor, B: int, tokens: int, heads: int):
+    od = operand_dtype()
+    _check(lib().vdn_flash_attn(_ptr(qk, od, "qk"), qk.shape[-1], _ptr(vT, od, "vT"), vT.shape[-1], _ptr(out, od, "out"), B, tokens, heads, _stream()),
+           "vdn_flash_attn")
+    return out
+
+
+def temporal_attn(qkv: torch.Tensor, out: torch.Tensor, D: int, T: int, C_: int, heads: int):
+    od = operand_dtype()
+    _check(lib().vdn_temporal_attn(_ptr(qkv, od, "qkv"), _ptr(out, od, "out"), D, T, C_, heads, _stream()), "vdn_temporal_attn")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor, eps: float, drop_first: bool = False, rows_per_batch: int = 0,
+              pe: Optional[torch.Tensor] = None):
+    rows, C_ = x.shape[0], x.shape[1]
+    _check(lib().vdn_layernorm(_ptr(x, torch.float32, "x"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"), _ptr(out, operand_dtype(), "out"),
+                               rows, C_, eps, 1 if drop_first else 0, rows_per_batch, _ptr(pe, torch.float32, "pe"), pe.shape[0] if pe is not None else 0,
+                               _stream()), "vdn_layernorm")
+    return out
+
+
+def groupnorm_stats(x, stats, frames, D, C_, groups, eps):
+    _check(lib().vdn_groupnorm_stats(_ptr(x, operand_dtype(), "x"), _ptr(stats, torch.float32, "stats"), frames, D, C_, groups, eps, _stream()),
+           "vdn_groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply_tc(x, stats, w, b, out, Bv, T, D, C_, groups):
+    od = operand_dtype()
+    _check(lib().vdn_groupnorm_apply_tc(_ptr(x, od, "x"), _ptr(stats, torch.float32, "stats"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
+                                        _ptr(out, od, "out"), Bv, T, D, C_, groups, _stream()), "vdn_groupnorm_apply_tc")
+    return out
+
+
+def patch_im2col(img, out, B, H, W, Kp):
+    _check(lib().vdn_patch_im2col(_ptr(img, torch.float32, "img"), _ptr(out, operand_dtype(), "out"), B, H, W, Kp, _stream()), "vdn_patch_im2col")
+    return out
+
+
+def write_cls(x, cls, pos, B, tokens, C_):
+    _check(lib().vdn_write_cls(_ptr(x, torch.float32, "x"), _ptr(cls, torch.float32, "cls"), _ptr(pos, torch.float32, "pos"), B, tokens, C_, _stream()),
+           "vdn_write_cls")
+    return x
+
+
+def im2col_3x3_s2(x, out, B, H, W, C_):
+    od = operand_dtype()
+    _check(lib().vdn_im2col_3x3_s2(_ptr(x, od, "x"), _ptr(out, od, "out"), B, H, W, C_, _stream()), "vdn_im2col_3x3_s2")
+    return out
+
+
+def bilinear_nhwc(x, out, B, H, W, Ho, Wo, C_, relu_out=False):
+    od = operand_dtype()
+    _check(lib().vdn_bilinear_nhwc(_ptr(x, od, "x"), _ptr(out, od, "out"), B, H, W, Ho, Wo, C_, 1 if relu_out else 0, _stream()), "vdn_bilinear_nhwc")
+    return out
+
+
+def bilinear_f32(x, out, N, H, W, Ho, Wo, relu=False):
+    _check(lib().vdn_bilinear_f32(_ptr(x, torch.float32, "x"), _ptr(out, torch.float32, "out"), N, H, W, Ho, Wo, 1 if relu else 0, _stream()),
+           "vdn_bilinear_f32")
+    return out
+
+
+def relu16(x, out):
+    od = operand_dtype()
+    _check(lib().vdn_relu16(_ptr(x, od, "x"), _ptr(out, od, "out"), x.numel(), _stream()), "vdn_relu16")
+    return out
+
+
+def cast_f32_to_16(x, out):
+    _check(lib().vdn_cast_f32_to_16(_ptr(x, torch.float32, "x"), _ptr(out, operand_dtype(), "out"), x.numel(), _stream()), "vdn_cast_f32_to_16")
+    return out
+
+
+def lsq_sums(pred, target, sums5):
+    _check(lib().vdn_lsq_sums(_ptr(pred, torch.float32, "pred"), _ptr(target, torch.float32, "target"), pred.numel(), _ptr(sums5, torch.float64, "sums"),
+                              _stream()), "vdn_lsq_sums")
+    return sums5
+
+
+def affine_clamp(x, out, scale_shift):
+    _check(lib().vdn_affine_clamp(_ptr(x, torch.float32, "x"), _ptr(out, torch.float32, "out"), x.numel(), _ptr(scale_shift, torch.float32, "ss"),
+                                  _stream()), "vdn_affine_clamp")
+    return out
+
+
+def crossfade(pre, post, out, scale_shift, w: float):
+    _check(lib().vdn_crossfade(_ptr(pre, torch.float32, "pre"), _ptr(post, torch.float32, "post"), _ptr(out, torch.float32, "out"), pre.numel(),
+                               _ptr(scale_shift, torch.float32, "ss"), float(w), _stream()), "vdn_crossfade")
+    return out
+
+
+def sobel_normals(depth, normals, N, H, W, channels_out=3):
+    _check(lib().vdn_sobel_normals(_ptr(depth, torch.float32, "depth"), _ptr(normals, torch.float32, "normals"), N, H, W, channels_out, _stream()),
+           "vdn_sobel_normals")
+    return normals

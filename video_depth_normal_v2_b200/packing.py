@@ -1,0 +1,150 @@
+"""One-time, host-side conversion of the reference's ``state_dict`` (SURVEY.md §8b key names) into kernel layouts:
+K-major 16-bit GEMM weights, tap-major 3x3 conv filters padded to 64 input channels per tap, pixel-shuffle ConvTranspose
+weights, fused q|k|v temporal projections, (value, gate)-interleaved GEGLU weights, fp32 biases / norm affines.
+
+Pure data movement on weights (no activations touch this file); the bicubic pos-embed interpolation is the reference's
+own weights-only computation (dinov2.py:179-210) evaluated once per patch grid."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+def _f32(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _w16(t: torch.Tensor, dev, dt) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).to(dt).contiguous()
+
+
+def pack_linear(sd, name, dev, dt, bias=True):
+    d = {"w": _w16(sd[name + ".weight"], dev, dt)}
+    if bias and (name + ".bias") in sd:
+        d["b"] = _f32(sd[name + ".bias"], dev)
+    return d
+
+
+def pack_conv1x1(sd, name, dev, dt):
+    w = sd[name + ".weight"]
+    return {"w": _w16(w.reshape(w.shape[0], w.shape[1]), dev, dt), "b": _f32(sd[name + ".bias"], dev)}
+
+
+def pack_conv3x3(sd, name, dev, dt, bias=True):
+    """(Co, Ci, 3, 3) -> [Co, 9 * roundup(Ci, 64)], column = (r*3+s)*Cip + ci (implicit-GEMM tap-major order)."""
+    w = sd[name + ".weight"].detach().float()
+    co, ci = w.shape[:2]
+    cip = (ci + 63) // 64 * 64
+    p = torch.zeros(co, 9, cip)
+    p[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    d = {"w": _w16(p.reshape(co, 9 * cip), dev, dt), "ci": ci, "co": co}
+    if bias:
+        d["b"] = _f32(sd[name + ".bias"], dev)
+    return d
+
+
+def pack_conv3x3_im2col(sd, name, dev, dt):
+    """(Co, Ci, 3, 3) -> [Co, 9*Ci] matching vdn_im2col_3x3_s2's column order (tap-major, unpadded)."""
+    w = sd[name + ".weight"].detach().float()
+    co, ci = w.shape[:2]
+    return {"w": _w16(w.permute(0, 2, 3, 1).reshape(co, 9 * ci), dev, dt), "b": _f32(sd[name + ".bias"], dev)}
+
+
+def pack_conv_transpose(sd, name, dev, dt, s):
+    """ConvTranspose2d (Ci, Co, s, s), kernel == stride -> GEMM weight [(i*s+j)*Co + co, ci] + expanded bias."""
+    w = sd[name + ".weight"].detach().float()
+    ci, co = w.shape[:2]
+    return {"w": _w16(w.permute(2, 3, 1, 0).reshape(s * s * co, ci), dev, dt), "b": _f32(sd[name + ".bias"].detach().float().repeat(s * s), dev), "co": co}
+
+
+def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str, cfg: dict, dev, dt) -> dict:
+    C = cfg["embed_dim"]
+    enc = {"C": C, "heads": cfg["heads"], "depth": cfg["depth"], "taps": list(cfg["taps"])}
+    pw = sd[prefix + "patch_embed.proj.weight"].detach().float().reshape(C, 588)
+    enc["patch_w"] = _w16(F.pad(pw, (0, 4)), dev, dt)  # K 588 -> 592 (16-byte row pitch); pad columns are zero
+    enc["patch_b"] = _f32(sd[prefix + "patch_embed.proj.bias"], dev)
+    enc["cls"] = _f32(sd[prefix + "cls_token"].reshape(C), dev)
+    enc["pos_embed_raw"] = sd[prefix + "pos_embed"].detach().float().cpu()
+    enc["pos_cache"] = {}
+    blocks = []
+    for i in range(cfg["depth"]):
+        p = f"{prefix}blocks.{i}."
+        blocks.append({
+            "ln1_w": _f32(sd[p + "norm1.weight"], dev), "ln1_b": _f32(sd[p + "norm1.bias"], dev),
+            "qkv": pack_linear(sd, p + "attn.qkv", dev, dt), "proj": pack_linear(sd, p + "attn.proj", dev, dt),
+            "ls1": _f32(sd[p + "ls1.gamma"], dev),
+            "ln2_w": _f32(sd[p + "norm2.weight"], dev), "ln2_b": _f32(sd[p + "norm2.bias"], dev),
+            "fc1": pack_linear(sd, p + "mlp.fc1", dev, dt), "fc2": pack_linear(sd, p + "mlp.fc2", dev, dt),
+            "ls2": _f32(sd[p + "ls2.gamma"], dev),
+        })
+    enc["blocks"] = blocks
+    enc["norm_w"], enc["norm_b"] = _f32(sd[prefix + "norm.weight"], dev), _f32(sd[prefix + "norm.bias"], dev)
+    return enc
+
+
+def encoder_pos_embed(enc: dict, ph: int, pw: int, dev) -> torch.Tensor:
+    """fp32 [(1 + ph*pw), C] positional embedding for the requested grid (dinov2.py:179-210), cached."""
+    key = (ph, pw)
+    if key not in enc["pos_cache"]:
+        pe = enc["pos_embed_raw"]
+        N = pe.shape[1] - 1
+        if not (ph * pw == N and ph == pw):
+            s = math.sqrt(N)
+            C = pe.shape[-1]
+            sx, sy = float(ph + 0.1) / s, float(pw + 0.1) / s
+            patch = F.interpolate(pe[:, 1:].reshape(1, int(s), int(s), C).permute(0, 3, 1, 2), scale_factor=(sx, sy), mode="bicubic", antialias=False)
+            assert patch.shape[-2] == ph and patch.shape[-1] == pw
+            pe = torch.cat((pe[:, :1], patch.permute(0, 2, 3, 1).reshape(1, -1, C)), dim=1)
+        enc["pos_cache"][key] = pe[0].to(device=dev, dtype=torch.float32).contiguous()
+    return enc["pos_cache"][key]
+
+
+def pack_motion_module(sd, prefix: str, C: int, dev, dt) -> dict:
+    p = prefix + "temporal_transformer."
+    tb = p + "transformer_blocks.0."
+    mm = {"C": C, "gn_w": _f32(sd[p + "norm.weight"], dev), "gn_b": _f32(sd[p + "norm.bias"], dev),
+          "proj_in": pack_linear(sd, p + "proj_in", dev, dt), "proj_out": pack_linear(sd, p + "proj_out", dev, dt), "attn": []}
+    for a in range(2):
+        ab = f"{tb}attention_blocks.{a}."
+        qkv = torch.cat([sd[ab + "to_q.weight"], sd[ab + "to_k.weight"], sd[ab + "to_v.weight"]], dim=0)
+        mm["attn"].append({
+            "ln_w": _f32(sd[f"{tb}norms.{a}.weight"], dev), "ln_b": _f32(sd[f"{tb}norms.{a}.bias"], dev),
+            "qkv_w": _w16(qkv, dev, dt), "out": pack_linear(sd, ab + "to_out.0", dev, dt),
+            "pe": _f32(sd[ab + "pos_encoder.pe"][0], dev),  # (32, C)
+        })
+    w1, b1 = sd[tb + "ff.net.0.proj.weight"].detach().float(), sd[tb + "ff.net.0.proj.bias"].detach().float()
+    h = w1.shape[0] // 2  # rows [0,h) = value, [h,2h) = gate (GEGLU.chunk(2), motion_module/attention.py:382-384)
+    mm["ff1_w"] = _w16(torch.stack([w1[:h], w1[h:]], dim=1).reshape(2 * h, -1), dev, dt)
+    mm["ff1_b"] = _f32(torch.stack([b1[:h], b1[h:]], dim=1).reshape(2 * h), dev)
+    mm["ff2"] = pack_linear(sd, tb + "ff.net.2", dev, dt)
+    mm["ffn_w"], mm["ffn_b"] = _f32(sd[tb + "ff_norm.weight"], dev), _f32(sd[tb + "ff_norm.bias"], dev)
+    return mm
+
+
+def pack_head(sd, prefix: str, cfg: dict, dev, dt, temporal: bool) -> dict:
+    oc, Fe = cfg["out_channels"], cfg["features"]
+    s = prefix + "scratch."
+    head = {"features": Fe, "oc": list(oc)}
+    head["projects"] = [pack_conv1x1(sd, f"{prefix}projects.{i}", dev, dt) for i in range(4)]
+    head["resize0"] = pack_conv_transpose(sd, prefix + "resize_layers.0", dev, dt, 4)
+    head["resize1"] = pack_conv_transpose(sd, prefix + "resize_layers.1", dev, dt, 2)
+    head["resize3"] = pack_conv3x3_im2col(sd, prefix + "resize_layers.3", dev, dt)
+    head["rn"] = [pack_conv3x3(sd, f"{s}layer{i + 1}_rn", dev, dt, bias=False) for i in range(4)]
+    head["refine"] = {}
+    for r in (1, 2, 3, 4):
+        p = f"{s}refinenet{r}."
+        head["refine"][r] = {
+            "out_conv": pack_conv1x1(sd, p + "out_conv", dev, dt),
+            "rcu1": (pack_conv3x3(sd, p + "resConfUnit1.conv1", dev, dt), pack_conv3x3(sd, p + "resConfUnit1.conv2", dev, dt)),
+            "rcu2": (pack_conv3x3(sd, p + "resConfUnit2.conv1", dev, dt), pack_conv3x3(sd, p + "resConfUnit2.conv2", dev, dt)),
+        }
+    head["oc1"] = pack_conv3x3(sd, s + "output_conv1", dev, dt)
+    head["oc2"] = pack_conv3x3(sd, s + "output_conv2.0", dev, dt)
+    head["oc2_head_w"] = _f32(sd[s + "output_conv2.2.weight"].reshape(32), dev)
+    head["oc2_head_b"] = float(sd[s + "output_conv2.2.bias"].reshape(()).item())
+    if temporal:
+        head["mm"] = [pack_motion_module(sd, f"{prefix}motion_modules.{m}.", C, dev, dt) for m, C in enumerate([oc[2], oc[3], Fe, Fe])]
+    return head
