@@ -1,0 +1,134 @@
+"""`-m gpu`: end-to-end parity of the CUDA path (through the C ABI) with the reference goldens and the fp32 oracle.
+
+Tolerances are BASELINE.json's north_star: per-pixel relative depth error <= 1e-2, AbsRel <= 1e-3, normal angle <= 0.5 deg."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vdn_oracle as O
+from oracle.init_recipe import ENCODERS, make_input, make_state_dict
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MAX_REL, ABS_REL, MAX_ANGLE = 1e-2, 1e-3, 0.5
+
+
+@pytest.fixture(scope="module")
+def vdn():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import video_depth_normal_v2_b200 as pkg
+    pkg.ops.set_operand_dtype(torch.float16)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return pkg
+
+
+def _model(vdn, enc, seed):
+    cfg = ENCODERS[enc]
+    m = vdn.VideoDepthAnything(encoder=enc, features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
+    sd = make_state_dict("vda", enc, seed)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def _check(name, pred, ref):
+    e = O.depth_errors(pred.float().cpu(), ref.float().cpu())
+    ang = O.normal_angle_deg(O.normals_from_depth(pred.float().cpu().flatten(0, -3)), O.normals_from_depth(ref.float().cpu().flatten(0, -3)))
+    print(f"{name}: {e} normal_angle_deg={ang:.4f}")
+    assert e["max_rel"] <= MAX_REL and e["abs_rel"] <= ABS_REL, (name, e)
+    assert ang <= MAX_ANGLE, (name, ang)
+    return e
+
+
+@pytest.mark.parametrize("name,enc", [("vda_vits_t4_70x84", "vits"), ("vda_vits_t2_518x518", "vits"), ("vda_vitl_t2_56x70", "vitl")])
+def test_forward_matches_reference_golden(vdn, name, enc):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    T, H, W, seed, stride = [int(v) for v in g["meta"]]
+    m, sd = _model(vdn, enc, seed)
+    x = make_input("rgb", (1, T, 3, H, W), seed)
+    vdn.ops.reset_launch_count()
+    y = m(x.cuda())
+    torch.cuda.synchronize()
+    assert y.shape == (1, T, H, W) and y.dtype == torch.float32 and y.is_cuda
+    assert vdn.ops.launch_count() > 50
+    _check(name, y[:, :, ::stride, ::stride], torch.from_numpy(g["depth"]))
+
+
+def test_encoder_taps_match_oracle(vdn):
+    from video_depth_normal_v2_b200.models import encoder_forward
+    m, sd = _model(vdn, "vits", 5)
+    x = make_input("rgb", (3, 3, 70, 84), 5)
+    feats = encoder_forward(m._weights()["enc"], x.cuda())
+    ref = O.dinov2_intermediate(sd, x, "vits", O._Ops())
+    for i, (f, (tok, _)) in enumerate(zip(feats, ref)):
+        err = (f.float().cpu().reshape(tok.shape) - tok).abs().max() / tok.abs().max()
+        print(f"tap {i}: rel-to-max err {float(err):.3e}")
+        assert err < 5e-3
+
+
+def test_stagewise_head_matches_oracle(vdn):
+    """Per-stage check of the head on oracle features (isolates head/motion-module errors from encoder errors)."""
+    from video_depth_normal_v2_b200.models import head_forward
+    enc = "vits"
+    m, sd = _model(vdn, enc, 6)
+    T, ph, pw = 4, 5, 6
+    x = make_input("rgb", (1, T, 3, 14 * ph, 14 * pw), 6)
+    ops_ = O._Ops()
+    feats = O.dinov2_intermediate(sd, x.flatten(0, 1), enc, ops_)
+    ref = O.dpt_head(sd, "head.", feats, ph, pw, ops_, T=T)
+    f16 = [f[0].reshape(-1, f[0].shape[-1]).cuda().to(vdn.ops.operand_dtype()).contiguous() for f in feats]
+    d = head_forward(m._weights()["head"], f16, T, ph, pw, T)
+    torch.cuda.synchronize()
+    _check("head on oracle features", d.reshape(1, T, 14 * ph, 14 * pw), ref.reshape(1, T, 14 * ph, 14 * pw))
+
+
+def test_infer_video_depth_matches_reference_golden(vdn):
+    from tests.golden.gen_golden import video_frames
+    g = np.load(os.path.join(GOLD, "video_vits_n50_56x70.npz"))
+    N, H, W, seed = [int(v) for v in g["meta"]]
+    m, sd = _model(vdn, "vits", seed)
+    frames = video_frames(N, H, W, seed)
+    out, fps = m.infer_video_depth(frames, 30, input_size=min(H, W), device="cuda")
+    assert fps == 30 and out.shape == (N, H, W) and out.dtype == np.float32
+    _check("infer_video_depth", torch.from_numpy(out), torch.from_numpy(g["depths"]))
+
+
+def test_full_size_vitl_window_matches_oracle_on_gpu(vdn):
+    """BASELINE config size (ViT-L, 518x518); the oracle runs in strict fp32 on the same GPU as the checker."""
+    enc, T, H, W = "vitl", 8, 518, 518
+    m, sd = _model(vdn, enc, 7)
+    x = make_input("rgb", (1, T, 3, H, W), 7).cuda()
+    y = m(x)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    ref = O.vda_forward(sd_gpu, x, enc)
+    torch.cuda.synchronize()
+    _check("vitl 8x518x518", y, ref)
+
+
+def test_determinism_and_batch_independence(vdn):
+    """Size-independent properties: repeated runs are bit-identical; frames of different clips in a batch do not interact."""
+    m, sd = _model(vdn, "vits", 8)
+    x = make_input("rgb", (2, 4, 3, 56, 70), 8).cuda()
+    y1 = m(x)
+    y2 = m(x)
+    ya = m(x[:1])
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    assert torch.equal(y1[:1], ya)
+
+
+def test_api_errors(vdn):
+    m, sd = _model(vdn, "vits", 0)
+    with pytest.raises(RuntimeError, match="multiple of patch size"):
+        m(torch.zeros(1, 2, 3, 60, 70).cuda())
+    bad = dict(sd)
+    bad.pop("head.scratch.output_conv1.bias")
+    with pytest.raises(RuntimeError, match="missing keys"):
+        m.load_state_dict(bad)
+    cpu_model = vdn.VideoDepthAnything(encoder="vits", features=64, out_channels=[48, 96, 192, 384])
+    cpu_model.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        cpu_model(torch.zeros(1, 2, 3, 56, 70))
