@@ -108,6 +108,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       issue_s(0);
       for (int j = 0; j < nt; ++j) {
         const int buf = j & 1;
+        if (j + 1 < nt) {
+          // S(j+1) = Q K(j+1)^T goes to the tensor pipe as soon as the softmax warps have pulled S(j) out of TMEM,
+          // i.e. it runs underneath softmax(j) instead of after it
+          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(s_free, j & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         {
@@ -118,16 +126,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
             const uint32_t chunk = kk >> 2, sub = kk & 3;
             const uint64_t dp = make_sdesc_sw128(pbase + chunk * FA_TILE) + 2 * sub;
             const uint64_t dv = make_sdesc_sw128(vbase + chunk * (FA_TILE / 2)) + 2 * sub;
-            umma_f16(tmem_PV, dp, dv, idesc_pv, kk != 0 ? 1u : 0u);
+            umma_f16(tmem_PV, dp, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);  // O accumulates in TMEM across KV tiles
           }
           umma_commit(pv_full);
           umma_commit(&kv_empty[buf]);
-        }
-        if (j + 1 < nt) {
-          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          mbar_wait(s_free, j & 1);
-          tc_fence_after();
-          issue_s(j + 1);
         }
         if (j + 2 < nt) {
           mbar_wait(&kv_empty[buf], (j >> 1) & 1);
@@ -141,9 +143,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     const uint32_t lane_off = uint32_t(warp_idx * 32) << 16;
     const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     float m = -INFINITY, l = 0.0f;
-    float O[FA_D];
-#pragma unroll
-    for (int i = 0; i < FA_D; ++i) O[i] = 0.0f;
     uint8_t* p_row = sP + r * 128;
     const int sw = r & 7;
 
@@ -152,85 +151,105 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       const int nvalid = min(FA_BN, tokens - kv0);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
+      // the whole S row (128 fp32) in registers: four TMEM loads in flight, one wait
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld32(tmem_S + lane_off + 0, s0);
+      tmem_ld32(tmem_S + lane_off + 32, s1);
+      tmem_ld32(tmem_S + lane_off + 64, s2);
+      tmem_ld32(tmem_S + lane_off + 96, s3);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);  // S(j) is out of TMEM: the issuer may overwrite it with S(j+1)
+      if (nvalid < FA_BN) {  // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          if (i >= nvalid) s0[i] = 0xff800000u;
+          if (32 + i >= nvalid) s1[i] = 0xff800000u;
+          if (64 + i >= nvalid) s2[i] = 0xff800000u;
+          if (96 + i >= nvalid) s3[i] = 0xff800000u;
         }
       }
-      const float m_new = fmaxf(m, mx * sc);
-      const float alpha = exp2f(m - m_new);
-      // fold in the previous tile's P V, then rescale the running output
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+      // lazy rescaling: keep the stale running max unless it grows by more than 2^8 (p stays <= 256, exact after the final 1/l)
+      float m_new = m;
+      const bool grow = mx > m + 8.0f;
+      if (grow) m_new = mx;
+      const bool warp_rescale = __any_sync(0xffffffffu, grow);
+      // P(j) may only overwrite P(j-1) once PV(j-1) has consumed it; the same wait makes O safe to rescale
       if (j > 0) {
         mbar_wait(pv_full, (j - 1) & 1);
         tc_fence_after();
+        if (warp_rescale) {
+          const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move (ex2(-inf) = 0 on the first tile)
+          l *= alpha;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_PV + lane_off + c * 32, v);
-          tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_PV + lane_off + c * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < FA_D; ++i) O[i] *= alpha;
-      l *= alpha;
-      // pass 2: probabilities -> swizzled smem (A operand of the P V MMA)
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < nvalid) ? exp2f(__uint_as_float(v[i]) * sc - m_new) : 0.0f;
-          float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(__uint_as_float(v[i + 1]) * sc - m_new) : 0.0f;
-          l += p0 + p1;
-          pk[i >> 1] = pack16(p0, p1, fmt);
-        }
-        // 32 keys = 4 x 16-byte pieces; piece index within the 64-key chunk = (c & 1) * 4 + q
-        uint8_t* chunk_row = p_row + (c >> 1) * FA_TILE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int piece = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(chunk_row + ((piece ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_PV + lane_off + c * 32, o);
+          }
+          tmem_st_wait();
         }
       }
       m = m_new;
+      float sum0 = 0.0f, sum1 = 0.0f;
+      // probabilities -> 16-bit -> swizzled smem, 8 keys (one 16-byte piece) at a time to keep temporaries short-lived
+      auto emit = [&](const uint32_t (&sv)[32], int c) {
+        uint8_t* chunk_row = p_row + (c >> 1) * FA_TILE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = fmaf(__uint_as_float(sv[8 * q + i]), sc, -m_new);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(pv[i]);
+          sum0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+          sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+          const int piece = (c & 1) * 4 + q;  // 128B swizzle: 16-byte piece index ^= row & 7
+          *reinterpret_cast<uint4*>(chunk_row + ((piece ^ sw) << 4)) =
+              make_uint4(pack16(pv[0], pv[1], fmt), pack16(pv[2], pv[3], fmt), pack16(pv[4], pv[5], fmt), pack16(pv[6], pv[7], fmt));
+        }
+      };
+      emit(s0, 0);
+      emit(s1, 1);
+      emit(s2, 2);
+      emit(s3, 3);
+      l += sum0 + sum1;
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(s_free);
       mbar_arrive(p_full);
     }
     mbar_wait(pv_full, (nt - 1) & 1);
     tc_fence_after();
+    const bool ok = q0 + r < tokens;
+    const float inv = 1.0f / l;
+    uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q0 + r) * C + h * FA_D;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_PV + lane_off + c * 32, v);
       tmem_ld_wait();
+      if (ok) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
-    }
-    if (q0 + r < tokens) {
-      const float inv = 1.0f / l;
-      uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q0 + r) * C + h * FA_D;
-#pragma unroll
-      for (int i = 0; i < FA_D; i += 8) {
-        uint4 u;
-        u.x = pack16(O[i] * inv, O[i + 1] * inv, fmt);
-        u.y = pack16(O[i + 2] * inv, O[i + 3] * inv, fmt);
-        u.z = pack16(O[i + 4] * inv, O[i + 5] * inv, fmt);
-        u.w = pack16(O[i + 6] * inv, O[i + 7] * inv, fmt);
-        *reinterpret_cast<uint4*>(o + i) = u;
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, fmt);
+          u.y = pack16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, fmt);
+          u.z = pack16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, fmt);
+          u.w = pack16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, fmt);
+          *reinterpret_cast<uint4*>(o + c * 32 + i) = u;
+        }
       }
     }
   }

@@ -5,11 +5,16 @@
 //                 two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 2..9  : epilogue — tcgen05.ld TMEM -> registers, fused bias / GELU / ReLU / GEGLU / LayerScale / residual(s) /
 //                 row remaps (pixel-shuffle, temporal transpose, patch tokens, QKV split with transposed V) / 1x1 "head" dot,
-//                 direct vectorised global stores
+//                 direct vectorised global stores.  The kernel is templated on <BLOCK_N, epilogue mode, operand format> so each
+//                 instantiation carries one epilogue body (the all-modes-in-one version was instruction-fetch bound: ncu showed
+//                 28 % stall_no_inst); the chunk loop is rolled and software-pipelined: the next accumulator chunk's tcgen05.ld
+//                 and the fp32 residual two chunks ahead are in flight while the current chunk's math and stores run.
 //
 // Convolution mode: A is an NHWC activation tensor described by a 4-D tensor map (C, W, H, B); a 128-pixel output tile is a
 // TH x TW spatial box and each of the 9 taps is the same box shifted by (r-1, s-1) — TMA's out-of-bounds zero fill implements
 // the padding, so no im2col buffer ever exists.
+#include <stdlib.h>
+
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -24,7 +29,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
-constexpr int kSmemBudget = 227 * 1024 - 2048;
+constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - 2 * 256 * 4 /*bias+gamma*/;
+
+// EPI_PLAIN: bias / act / out (+out2), no residual operands (keeps registers free so the GELU chains interleave);
+// EPI_RES  : additionally LayerScale gamma + residual(s), with register prefetch buffers.
+enum { EPI_PLAIN = 0, EPI_QKV = 1, EPI_GEGLU = 2, EPI_PIXSHUF = 3, EPI_HEAD = 4, EPI_RES = 5 };
 
 struct GemmKParams {
   int M, N;
@@ -46,10 +55,9 @@ struct GemmKParams {
   void* out2;
   int out2_relu;
   long long ld_out2;
-  int act, geglu, row_map, rm0, rm1, rm2, rm3;
+  int act, row_map, rm0, rm1, rm2, rm3;
   const float* head_w;
   float head_b;
-  int fmt;
 };
 
 template <int BLOCK_N>
@@ -60,7 +68,8 @@ struct GemmCfg {
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kParamBytes = 2 * BLOCK_N * 4;  // this tile's bias and gamma slices
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + kParamBytes;
 };
 
 // Per-thread output-row context, computed once per tile.
@@ -71,119 +80,209 @@ struct RowCtx {
   int b, y, x;        // PIXEL_SHUFFLE: image, input row, input col.  QKV_SPLIT: b = frame, x = token
 };
 
-__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (FMT == 1) return T16<__nv_bfloat16>::pack(a, b);
+  else return T16<__half>::pack(a, b);
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if constexpr (FMT == 1) return T16<__nv_bfloat16>::unpack(u);
+  else return T16<__half>::unpack(u);
+}
+__device__ __forceinline__ void store8_f32(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-__device__ __forceinline__ void store8_16(void* base, long long idx, const float (&v)[8], int fmt) {
+template <int FMT>
+__device__ __forceinline__ void store8_16(void* base, long long idx, const float* v) {
   uint4 u;
-  u.x = pack16(v[0], v[1], fmt);
-  u.y = pack16(v[2], v[3], fmt);
-  u.z = pack16(v[4], v[5], fmt);
-  u.w = pack16(v[6], v[7], fmt);
+  u.x = pack2<FMT>(v[0], v[1]);
+  u.y = pack2<FMT>(v[2], v[3]);
+  u.z = pack2<FMT>(v[4], v[5]);
+  u.w = pack2<FMT>(v[6], v[7]);
   *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + idx) = u;
 }
+template <int FMT>
+__device__ __forceinline__ void add16x8(float* v, const uint4& u) {
+  float2 f;
+  f = unpack2<FMT>(u.x); v[0] += f.x; v[1] += f.y;
+  f = unpack2<FMT>(u.y); v[2] += f.x; v[3] += f.y;
+  f = unpack2<FMT>(u.z); v[4] += f.x; v[5] += f.y;
+  f = unpack2<FMT>(u.w); v[6] += f.x; v[7] += f.y;
+}
 
-// Epilogue for one group of 8 consecutive accumulator columns [n, n+8) of one row.
-__device__ __forceinline__ void epilogue_group8(const GemmKParams& p, const RowCtx& rc, int n, float (&v)[8]) {
-  if (p.bias != nullptr) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  if (p.geglu) {
-    // interleaved (value, gate) pairs -> 4 outputs at column n/2
-    uint2 u;
-    u.x = pack16(v[0] * gelu_erf(v[1]), v[2] * gelu_erf(v[3]), p.fmt);
-    u.y = pack16(v[4] * gelu_erf(v[5]), v[6] * gelu_erf(v[7]), p.fmt);
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + rc.out_row * p.ldc + (n >> 1)) = u;
-    return;
-  }
-  if (p.act == VDN_ACT_GELU) {
+// Raw residual vectors of one 32-column chunk of one row (fp32: 8 x 16 B; 16-bit: r[0..3]).
+struct ResBuf {
+  uint4 r[8];
+};
+
+__device__ __forceinline__ void prefetch_res(const GemmKParams& p, const RowCtx& rc, int n0, ResBuf& rb) {
+  if (p.res == nullptr || !rc.valid || n0 >= p.N) return;
+  if (p.res_f32) {
+    const float* r = reinterpret_cast<const float*>(p.res) + rc.res_row * p.ld_res + n0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 8; ++i)
+      if (n0 + i * 4 < p.N) rb.r[i] = *reinterpret_cast<const uint4*>(r + i * 4);
+  } else {
+    const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + rc.res_row * p.ld_res + n0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n0 + i * 8 < p.N) rb.r[i] = *reinterpret_cast<const uint4*>(r + i * 8);
+  }
+}
+__device__ __forceinline__ void prefetch_res2(const GemmKParams& p, const RowCtx& rc, int n0, uint4 (&r2)[4]) {
+  if (p.res2 == nullptr || !rc.valid || n0 >= p.N) return;
+  const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res2) + rc.out_row * p.ld_res2 + n0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (n0 + i * 8 < p.N) r2[i] = *reinterpret_cast<const uint4*>(r + i * 8);
+}
+
+// ---- epilogue bodies: v[32] already holds acc (+bias) for columns [n0, n0+32) of this thread's row ----------------------------
+template <int FMT>
+__device__ __forceinline__ void store_plain(const GemmKParams& p, const RowCtx& rc, int n0, float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n0 + g * 8;
+    if (n < p.N) {
+      const long long o_idx = rc.out_row * p.ldc + n;
+      if (p.out_f32) store8_f32(reinterpret_cast<float*>(p.out) + o_idx, v + g * 8);
+      else store8_16<FMT>(p.out, o_idx, v + g * 8);
+    }
+  }
+  if (p.out2 != nullptr) {
+    if (p.out2_relu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (n0 + g * 8 < p.N) store8_16<FMT>(p.out2, rc.out_row * p.ld_out2 + n0 + g * 8, v + g * 8);
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ void epi_noresidual(const GemmKParams& p, const RowCtx& rc, int n0, float (&v)[32]) {
+  if (p.act == VDN_ACT_GELU) {
+    gelu_fast_batch<8>(v);
+    gelu_fast_batch<8>(v + 8);
+    gelu_fast_batch<8>(v + 16);
+    gelu_fast_batch<8>(v + 24);
   } else if (p.act == VDN_ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+  store_plain<FMT>(p, rc, n0, v);
+}
+
+template <int FMT>
+__device__ __forceinline__ void epi_plain(const GemmKParams& p, const RowCtx& rc, int n0, int col_in_tile, float (&v)[32], ResBuf& rb,
+                                          uint4 (&r2)[4], int n_res_next, int n_res2_next, const float* sgamma) {
+  if (p.act == VDN_ACT_GELU) {
+    gelu_fast_batch<8>(v);
+    gelu_fast_batch<8>(v + 8);
+    gelu_fast_batch<8>(v + 16);
+    gelu_fast_batch<8>(v + 24);
+  } else if (p.act == VDN_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
   }
   if (p.gamma != nullptr) {
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + n));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + n + 4));
-    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= sgamma[col_in_tile + i];
   }
-  if (p.row_map == VDN_ROWMAP_QKV_SPLIT) {
-    const int twoC = 2 * p.rm2;
+  if (p.res != nullptr) {
+    if (p.res_f32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (n0 + i * 4 < p.N) {
+          v[4 * i] += __uint_as_float(rb.r[i].x); v[4 * i + 1] += __uint_as_float(rb.r[i].y);
+          v[4 * i + 2] += __uint_as_float(rb.r[i].z); v[4 * i + 3] += __uint_as_float(rb.r[i].w);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n0 + i * 8 < p.N) add16x8<FMT>(v + 8 * i, rb.r[i]);
+    }
+    if (n_res_next >= 0) prefetch_res(p, rc, n_res_next, rb);  // two chunks ahead, different columns than the stores below
+  }
+  if (p.res2 != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n0 + i * 8 < p.N) add16x8<FMT>(v + 8 * i, r2[i]);
+    if (n_res2_next >= 0) prefetch_res2(p, rc, n_res2_next, r2);
+  }
+  store_plain<FMT>(p, rc, n0, v);
+}
+
+template <int FMT>
+__device__ __forceinline__ void epi_qkv(const GemmKParams& p, const RowCtx& rc, int n0, float (&v)[32]) {
+  const int twoC = 2 * p.rm2;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n0 + g * 8;
+    if (n >= p.N) break;
     if (n < twoC) {
-      store8_16(p.out, rc.out_row * p.ldc + n, v, p.fmt);
+      store8_16<FMT>(p.out, rc.out_row * p.ldc + n, v + g * 8);
     } else {
       const int c = n - twoC;  // h*64 + d
       const int heads = p.rm2 >> 6;
       uint16_t* vt = reinterpret_cast<uint16_t*>(p.out2) + ((long long)(rc.b * heads + (c >> 6)) * 64 + (c & 63)) * p.rm1 + rc.x;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t pk = pack16(v[i], 0.0f, p.fmt);
-        vt[(long long)i * p.rm1] = static_cast<uint16_t>(pk & 0xFFFFu);
-      }
+      for (int i = 0; i < 8; ++i) vt[(long long)i * p.rm1] = static_cast<uint16_t>(pack2<FMT>(v[g * 8 + i], 0.0f) & 0xFFFFu);
     }
-    return;
-  }
-  long long o_idx;
-  if (p.row_map == VDN_ROWMAP_PIXEL_SHUFFLE) {
-    const int s = p.rm2, Co = p.rm3;
-    const int ij = n / Co, co = n - ij * Co;
-    const int i = ij / s, j = ij - i * s;
-    o_idx = (((long long)rc.b * (p.rm0 * s) + rc.y * s + i) * (p.rm1 * s) + rc.x * s + j) * p.ldc + co;
-  } else {
-    o_idx = rc.out_row * p.ldc + n;
-  }
-  if (p.res != nullptr) {
-    if (p.res_f32) {
-      const float* r = reinterpret_cast<const float*>(p.res) + rc.res_row * p.ld_res + n;
-      const float4 r0 = *reinterpret_cast<const float4*>(r);
-      const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-    } else {
-      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res) + rc.res_row * p.ld_res + n);
-      float2 f;
-      f = unpack16(u.x, p.fmt); v[0] += f.x; v[1] += f.y;
-      f = unpack16(u.y, p.fmt); v[2] += f.x; v[3] += f.y;
-      f = unpack16(u.z, p.fmt); v[4] += f.x; v[5] += f.y;
-      f = unpack16(u.w, p.fmt); v[6] += f.x; v[7] += f.y;
-    }
-  }
-  if (p.res2 != nullptr) {
-    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + rc.out_row * p.ld_res2 + n);
-    float2 f;
-    f = unpack16(u.x, p.fmt); v[0] += f.x; v[1] += f.y;
-    f = unpack16(u.y, p.fmt); v[2] += f.x; v[3] += f.y;
-    f = unpack16(u.z, p.fmt); v[4] += f.x; v[5] += f.y;
-    f = unpack16(u.w, p.fmt); v[6] += f.x; v[7] += f.y;
-  }
-  if (p.out_f32) {
-    store8_f32(reinterpret_cast<float*>(p.out) + o_idx, v);
-  } else {
-    store8_16(p.out, o_idx, v, p.fmt);
-  }
-  if (p.out2 != nullptr) {
-    if (p.out2_relu) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
-    }
-    store8_16(p.out2, rc.out_row * p.ld_out2 + n, v, p.fmt);
   }
 }
 
-template <int BLOCK_N>
+template <int FMT>
+__device__ __forceinline__ void epi_geglu(const GemmKParams& p, const RowCtx& rc, int n0, float (&v)[32]) {
+  // interleaved (value, gate) pairs -> 16 outputs at column n0/2
+  uint32_t o[8];
+  float gt[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gt[i] = v[2 * i + 1];
+  gelu_fast_batch<16>(gt);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = pack2<FMT>(v[4 * i] * gt[2 * i], v[4 * i + 2] * gt[2 * i + 1]);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + rc.out_row * p.ldc + (n0 >> 1);
+  if (n0 + 16 <= p.N) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+  else if (n0 + 8 <= p.N) *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
+  if (n0 + 32 <= p.N) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+  else if (n0 + 24 <= p.N) *reinterpret_cast<uint2*>(dst + 8) = make_uint2(o[4], o[5]);
+}
+
+template <int FMT>
+__device__ __forceinline__ void epi_pixshuf(const GemmKParams& p, const RowCtx& rc, int n0, float (&v)[32]) {
+  const int s = p.rm2, Co = p.rm3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n0 + g * 8;
+    if (n >= p.N) break;
+    const int ij = n / Co, co = n - ij * Co;
+    const int i = ij / s, j = ij - i * s;
+    const long long o_idx = (((long long)rc.b * (p.rm0 * s) + rc.y * s + i) * (p.rm1 * s) + rc.x * s + j) * p.ldc + co;
+    store8_16<FMT>(p.out, o_idx, v + g * 8);
+  }
+}
+
+__device__ __forceinline__ void epi_head(const GemmKParams& p, const RowCtx& rc, float (&v)[32]) {
+  // fused output_conv2: ReLU(conv3x3) -> 1x1 conv -> ReLU  (dpt.py:118-124); N <= 32 so one chunk per row
+  float s = p.head_b;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < p.N) s = fmaf(fmaxf(v[j], 0.0f), __ldg(p.head_w + j), s);
+  reinterpret_cast<float*>(p.out)[rc.out_row] = fmaxf(s, 0.0f);
+}
+
+template <int BLOCK_N, int EPI, int FMT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
@@ -192,6 +291,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* sbias = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
+  float* sgamma = sbias + BLOCK_N;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -256,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.fmt ? 1u : 0u, BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(FMT ? 1u : 0u, BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -292,6 +393,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = e >> 2;           // column half handled by this warp
     constexpr int kChunks = BLOCK_N / 32;
     constexpr int kChunksPerHalf = (kChunks + 1) / 2;
+    const int c_begin = half * kChunksPerHalf;
+    const int c_end = (c_begin + kChunksPerHalf < kChunks) ? c_begin + kChunksPerHalf : kChunks;
     const int row_in_tile = quarter * 32 + lane;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
@@ -318,65 +421,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       rc.out_row = row;
       rc.res_row = row;
       rc.b = rc.y = rc.x = 0;
-      if (p.row_map == VDN_ROWMAP_PIXEL_SHUFFLE) {
+      if constexpr (EPI == EPI_PIXSHUF) {
         const int hw = p.rm0 * p.rm1;
         rc.b = int(row / hw);
         const int rem = int(row - (long long)rc.b * hw);
         rc.y = rem / p.rm1;
         rc.x = rem - rc.y * p.rm1;
-      } else if (p.row_map == VDN_ROWMAP_TEMPORAL) {
-        const int T = p.rm0, D = p.rm1;
-        const long long bd = row / T;
-        const int f = int(row - bd * T);
-        const long long bb = bd / D;
-        const int d = int(bd - bb * D);
-        rc.out_row = (bb * T + f) * D + d;
-        rc.res_row = rc.out_row;
-      } else if (p.row_map == VDN_ROWMAP_PATCH_TOKENS) {
-        const int P = p.rm0;
-        const long long bb = row / P;
-        const int pp = int(row - bb * P);
-        rc.out_row = bb * (P + 1) + 1 + pp;
-        rc.res_row = 1 + pp;
-      } else if (p.row_map == VDN_ROWMAP_QKV_SPLIT) {
+      } else if constexpr (EPI == EPI_QKV) {
         rc.b = int(row / p.rm0);
         rc.x = int(row - (long long)rc.b * p.rm0);
+      } else if constexpr (EPI == EPI_PLAIN || EPI == EPI_RES) {
+        if (p.row_map == VDN_ROWMAP_TEMPORAL) {
+          const int T = p.rm0, D = p.rm1;
+          const long long bd = row / T;
+          const int f = int(row - bd * T);
+          const long long bb = bd / D;
+          const int d = int(bd - bb * D);
+          rc.out_row = (bb * T + f) * D + d;
+          rc.res_row = rc.out_row;
+        } else if (p.row_map == VDN_ROWMAP_PATCH_TOKENS) {
+          const int P = p.rm0;
+          const long long bb = row / P;
+          const int pp = int(row - bb * P);
+          rc.out_row = bb * (P + 1) + 1 + pp;
+          rc.res_row = 1 + pp;
+        }
       }
 
+      // stage this tile's bias / gamma slices in shared memory (all epilogue warps; named barrier 1)
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      {
+        const int t = threadIdx.x - 64;
+        if (t < BLOCK_N) {
+          const int n = n_blk * BLOCK_N + t;
+          if (p.bias != nullptr) sbias[t] = n < p.N ? __ldg(p.bias + n) : 0.0f;
+          if (p.gamma != nullptr) sgamma[t] = n < p.N ? __ldg(p.gamma + n) : 0.0f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+
+      const int nb = n_blk * BLOCK_N;
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
+      uint32_t accr[32];
+      ResBuf rb0, rb1;  // only live in the EPI_RES instantiation
+      uint4 r2[4];
+      if constexpr (EPI == EPI_RES) {
+        // residual operands of the first two chunks are requested before the accumulator is even ready
+        if (c_begin < c_end) {
+          prefetch_res(p, rc, nb + c_begin * 32, rb0);
+          prefetch_res2(p, rc, nb + c_begin * 32, r2);
+        }
+        if (c_begin + 1 < c_end) prefetch_res(p, rc, nb + (c_begin + 1) * 32, rb1);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = half * kChunksPerHalf; c < kChunks && c < (half + 1) * kChunksPerHalf; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
+      if (c_begin < c_end) tmem_ld32(t_row + c_begin * 32, accr);
+
+      auto chunk = [&](int c, ResBuf& rb) {
         tmem_ld_wait();
-        const int n0 = n_blk * BLOCK_N + c * 32;
-        if (rc.valid) {
-          if (p.head_w != nullptr) {
-            // fused output_conv2: ReLU(conv3x3) -> 1x1 conv -> ReLU  (dpt.py:118-124), N <= 32 so one chunk per row
-            float s = p.head_b;
+        const int n0 = nb + c * 32;
+        float v[32];
+        if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < p.N) {
-                const float a = fmaxf(__uint_as_float(r[j]) + __ldg(p.bias + j), 0.0f);
-                s = fmaf(a, __ldg(p.head_w + j), s);
-              }
-            }
-            reinterpret_cast<float*>(p.out)[rc.out_row] = fmaxf(s, 0.0f);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]) + sbias[c * 32 + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]);
+        }
+        // the accumulator registers are free again: next chunk's TMEM load runs under this chunk's math and stores
+        if (c + 1 < c_end) tmem_ld32(t_row + (c + 1) * 32, accr);
+        if (rc.valid && n0 < p.N) {
+          if constexpr (EPI == EPI_RES) {
+            epi_plain<FMT>(p, rc, n0, c * 32, v, rb, r2, (c + 2 < c_end) ? nb + (c + 2) * 32 : -1, (c + 1 < c_end) ? nb + (c + 1) * 32 : -1, sgamma);
+          } else if constexpr (EPI == EPI_PLAIN) {
+            epi_noresidual<FMT>(p, rc, n0, v);
+          } else if constexpr (EPI == EPI_QKV) {
+            epi_qkv<FMT>(p, rc, n0, v);
+          } else if constexpr (EPI == EPI_GEGLU) {
+            epi_geglu<FMT>(p, rc, n0, v);
+          } else if constexpr (EPI == EPI_PIXSHUF) {
+            epi_pixshuf<FMT>(p, rc, n0, v);
           } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = n0 + g * 8;
-              if (n < p.N) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                epilogue_group8(p, rc, n, v);
-              }
-            }
+            epi_head(p, rc, v);
           }
         }
+      };
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 2) {
+        chunk(c, rb0);
+        if (c + 1 < c_end) chunk(c + 1, rb1);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -394,20 +527,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI, int FMT>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
     configured = true;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_blocks;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BLOCK_N, EPI, FMT><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
+}
+
+template <int EPI, int FMT>
+static int launch_gemm_bn(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, cudaStream_t stream) {
+  if constexpr (EPI == EPI_HEAD) {
+    return launch_gemm<32, EPI, FMT>(tmA, tmB, p, stream);
+  } else if constexpr (EPI == EPI_PLAIN || EPI == EPI_RES) {
+    switch (block_n) {
+      case 256: return launch_gemm<256, EPI, FMT>(tmA, tmB, p, stream);
+      case 128: return launch_gemm<128, EPI, FMT>(tmA, tmB, p, stream);
+      case 64: return launch_gemm<64, EPI, FMT>(tmA, tmB, p, stream);
+      default: return launch_gemm<32, EPI, FMT>(tmA, tmB, p, stream);
+    }
+  } else {
+    // QKV / GEGLU / pixel-shuffle outputs are always wide (N >= 256): two tile widths suffice
+    if (block_n == 256) return launch_gemm<256, EPI, FMT>(tmA, tmB, p, stream);
+    return launch_gemm<128, EPI, FMT>(tmA, tmB, p, stream);
+  }
+}
+
+template <int FMT>
+static int launch_gemm_epi(int epi, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_QKV: return launch_gemm_bn<EPI_QKV, FMT>(block_n, tmA, tmB, p, stream);
+    case EPI_GEGLU: return launch_gemm_bn<EPI_GEGLU, FMT>(block_n, tmA, tmB, p, stream);
+    case EPI_PIXSHUF: return launch_gemm_bn<EPI_PIXSHUF, FMT>(block_n, tmA, tmB, p, stream);
+    case EPI_HEAD: return launch_gemm_bn<EPI_HEAD, FMT>(block_n, tmA, tmB, p, stream);
+    case EPI_RES: return launch_gemm_bn<EPI_RES, FMT>(block_n, tmA, tmB, p, stream);
+    default: return launch_gemm_bn<EPI_PLAIN, FMT>(block_n, tmA, tmB, p, stream);
+  }
 }
 
 static void pick_spatial_tile(int H, int W, int* th, int* tw) {
@@ -447,11 +610,20 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
   p.res2 = d->res2; p.ld_res2 = d->ld_res2;
   p.out = d->out; p.out_f32 = d->out_f32; p.ldc = d->ldc;
   p.out2 = d->out2; p.out2_relu = d->out2_relu; p.ld_out2 = d->ld_out2;
-  p.act = d->act; p.geglu = d->geglu;
+  p.act = d->act;
   p.row_map = d->row_map; p.rm0 = d->rm0; p.rm1 = d->rm1; p.rm2 = d->rm2; p.rm3 = d->rm3;
   p.head_w = d->head_w; p.head_b = d->head_b;
-  p.fmt = fmt;
   p.conv = d->conv;
+  int epi = EPI_PLAIN;
+  if (d->head_w != nullptr) epi = EPI_HEAD;
+  else if (d->geglu) epi = EPI_GEGLU;
+  else if (d->row_map == VDN_ROWMAP_QKV_SPLIT) epi = EPI_QKV;
+  else if (d->row_map == VDN_ROWMAP_PIXEL_SHUFFLE) epi = EPI_PIXSHUF;
+  else if (d->res != nullptr || d->res2 != nullptr || d->gamma != nullptr) epi = EPI_RES;
+  if (epi == EPI_QKV && (d->out_f32 || d->out2 == nullptr || d->res || d->gamma || d->act)) return set_error("vdn_gemm: QKV split takes bias only, 16-bit out and out2 = V^T");
+  if (epi == EPI_PIXSHUF && (d->out_f32 || d->res || d->res2 || d->gamma || d->act || d->out2)) return set_error("vdn_gemm: pixel-shuffle takes bias only and a 16-bit output");
+  if (epi == EPI_GEGLU && (d->gamma || d->act || d->out2 || d->res2)) return set_error("vdn_gemm: geglu takes bias only");
+  if (epi != EPI_PLAIN && epi != EPI_RES && epi != EPI_HEAD && d->N < 256) return set_error("vdn_gemm: QKV / GEGLU / pixel-shuffle epilogues need N >= 256");
 
   // BLOCK_N: largest tile that does not waste more than necessary
   int block_n;
@@ -461,6 +633,14 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
   else block_n = 32;
   // prefer 128-wide tiles when 256 would leave most of the last tile empty (e.g. N = 384)
   if (block_n == 256 && (d->N % 256) != 0 && (d->N % 256) <= 128) block_n = 128;
+  // fp32 read-modify-write outputs with a short K loop are HBM/latency bound in the epilogue: with 128-wide tiles each epilogue
+  // warp owns two 32-column chunks and both residual chunks are requested a whole tile ahead of their use
+  {
+    static const char* env = getenv("VDN_RMW_BN");
+    const int rmw_bn = env ? atoi(env) : 256;
+    const long long k_total = (long long)d->K * (d->conv ? 9 : 1);
+    if (block_n == 256 && epi == EPI_RES && d->out_f32 && d->res != nullptr && k_total <= 1024 && rmw_bn == 128) block_n = 128;
+  }
   p.num_n_blocks = (int)((d->N + block_n - 1) / block_n);
 
   CUtensorMap tmA, tmB;
@@ -495,10 +675,5 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)block_n};
     if (make_tensor_map(&tmB, d->w, fmt, 2, dims, strides, box)) return 1;
   }
-  switch (block_n) {
-    case 256: return launch_gemm<256>(tmA, tmB, p, stream);
-    case 128: return launch_gemm<128>(tmA, tmB, p, stream);
-    case 64: return launch_gemm<64>(tmA, tmB, p, stream);
-    default: return launch_gemm<32>(tmA, tmB, p, stream);
-  }
+  return fmt ? launch_gemm_epi<1>(epi, block_n, tmA, tmB, p, stream) : launch_gemm_epi<0>(epi, block_n, tmA, tmB, p, stream);
 }

@@ -43,6 +43,44 @@ def reset_launch_count():
     lib().vdn_reset_launch_count()
 
 
+class KernelProfiler:
+    """Optional CUDA-event timing of every op launch on the current stream (used by bench.py for the live roofline).
+    work = algorithmic FLOPs (kind 'tensor') or algorithmic bytes (kind 'hbm') of the launch."""
+
+    def __init__(self, by_shape: bool = False):
+        self.by_shape = by_shape
+        self.records = []  # (name, kind, work, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, kind, work, e0, e1 in self.records:
+            a = agg.setdefault(name, {"kind": kind, "launches": 0, "ms": 0.0, "work": 0.0})
+            a["launches"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["work"] += work
+        return agg
+
+
+_profiler: Optional[KernelProfiler] = None
+
+
+def set_profiler(p: Optional[KernelProfiler]):
+    global _profiler
+    _profiler = p
+
+
+def _run(name: str, kind: str, work: float, fn, *args):
+    if _profiler is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    _profiler.records.append((name, kind, work, e0, e1))
+    return rc
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -99,47 +137,54 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     if head_w is not None:
         d.head_w = _ptr(head_w, torch.float32, "head_w")
         d.head_b = float(head_b)
-    _check(lib().vdn_gemm(C.byref(d), _stream()), "vdn_gemm")
+    flops = 2.0 * M * N * K * (9 if conv is not None else 1)
+    name = "gemm_conv3x3" if conv is not None else "gemm"
+    if _profiler is not None and _profiler.by_shape:
+        name = f"{name}[{M}x{N}x{K}{',f32out' if d.out_f32 else ''}{',act' + str(act) if act else ''}{',geglu' if geglu else ''}{',map' + str(row_map) if row_map else ''}]"
+    _check(_run(name, "tensor", flops, lib().vdn_gemm, C.byref(d), _stream()), "vdn_gemm")
     return out
 
 
 def flash_attn(qk: torch.Tensor, vT: torch.Tensor, out: torch.Tensor, B: int, tokens: int, heads: int):
     od = operand_dtype()
-    _check(lib().vdn_flash_attn(_ptr(qk, od, "qk"), qk.shape[-1], _ptr(vT, od, "vT"), vT.shape[-1], _ptr(out, od, "out"), B, tokens, heads, _stream()),
-           "vdn_flash_attn")
+    _check(_run("flash_attn", "tensor", 4.0 * B * heads * tokens * tokens * 64, lib().vdn_flash_attn, _ptr(qk, od, "qk"), qk.shape[-1],
+                _ptr(vT, od, "vT"), vT.shape[-1], _ptr(out, od, "out"), B, tokens, heads, _stream()), "vdn_flash_attn")
     return out
 
 
 def temporal_attn(qkv: torch.Tensor, out: torch.Tensor, D: int, T: int, C_: int, heads: int):
     od = operand_dtype()
-    _check(lib().vdn_temporal_attn(_ptr(qkv, od, "qkv"), _ptr(out, od, "out"), D, T, C_, heads, _stream()), "vdn_temporal_attn")
+    _check(_run("temporal_attn", "hbm", 8.0 * D * T * C_, lib().vdn_temporal_attn, _ptr(qkv, od, "qkv"), _ptr(out, od, "out"), D, T, C_, heads,
+                _stream()), "vdn_temporal_attn")
     return out
 
 
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor, eps: float, drop_first: bool = False, rows_per_batch: int = 0,
               pe: Optional[torch.Tensor] = None):
     rows, C_ = x.shape[0], x.shape[1]
-    _check(lib().vdn_layernorm(_ptr(x, torch.float32, "x"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"), _ptr(out, operand_dtype(), "out"),
-                               rows, C_, eps, 1 if drop_first else 0, rows_per_batch, _ptr(pe, torch.float32, "pe"), pe.shape[0] if pe is not None else 0,
-                               _stream()), "vdn_layernorm")
+    _check(_run("layernorm", "hbm", 6.0 * rows * C_, lib().vdn_layernorm, _ptr(x, torch.float32, "x"), _ptr(w, torch.float32, "w"),
+                _ptr(b, torch.float32, "b"), _ptr(out, operand_dtype(), "out"), rows, C_, eps, 1 if drop_first else 0, rows_per_batch,
+                _ptr(pe, torch.float32, "pe"), pe.shape[0] if pe is not None else 0, _stream()), "vdn_layernorm")
     return out
 
 
 def groupnorm_stats(x, stats, frames, D, C_, groups, eps):
-    _check(lib().vdn_groupnorm_stats(_ptr(x, operand_dtype(), "x"), _ptr(stats, torch.float32, "stats"), frames, D, C_, groups, eps, _stream()),
-           "vdn_groupnorm_stats")
+    _check(_run("groupnorm_stats", "hbm", 2.0 * frames * D * C_, lib().vdn_groupnorm_stats, _ptr(x, operand_dtype(), "x"),
+                _ptr(stats, torch.float32, "stats"), frames, D, C_, groups, eps, _stream()), "vdn_groupnorm_stats")
     return stats
 
 
 def groupnorm_apply_tc(x, stats, w, b, out, Bv, T, D, C_, groups):
     od = operand_dtype()
-    _check(lib().vdn_groupnorm_apply_tc(_ptr(x, od, "x"), _ptr(stats, torch.float32, "stats"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
-                                        _ptr(out, od, "out"), Bv, T, D, C_, groups, _stream()), "vdn_groupnorm_apply_tc")
+    _check(_run("groupnorm_apply_tc", "hbm", 4.0 * Bv * T * D * C_, lib().vdn_groupnorm_apply_tc, _ptr(x, od, "x"), _ptr(stats, torch.float32, "stats"),
+                _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"), _ptr(out, od, "out"), Bv, T, D, C_, groups, _stream()),
+           "vdn_groupnorm_apply_tc")
     return out
 
 
 def patch_im2col(img, out, B, H, W, Kp):
-    _check(lib().vdn_patch_im2col(_ptr(img, torch.float32, "img"), _ptr(out, operand_dtype(), "out"), B, H, W, Kp, _stream()), "vdn_patch_im2col")
+    _check(_run("patch_im2col", "hbm", B * 3.0 * H * W * 4 + B * (H // 14) * (W // 14) * Kp * 2.0, lib().vdn_patch_im2col, _ptr(img, torch.float32, "img"),
+                _ptr(out, operand_dtype(), "out"), B, H, W, Kp, _stream()), "vdn_patch_im2col")
     return out
 
 
@@ -151,25 +196,27 @@ def write_cls(x, cls, pos, B, tokens, C_):
 
 def im2col_3x3_s2(x, out, B, H, W, C_):
     od = operand_dtype()
-    _check(lib().vdn_im2col_3x3_s2(_ptr(x, od, "x"), _ptr(out, od, "out"), B, H, W, C_, _stream()), "vdn_im2col_3x3_s2")
+    _check(_run("im2col_3x3_s2", "hbm", 2.0 * B * H * W * C_ + 2.0 * out.numel(), lib().vdn_im2col_3x3_s2, _ptr(x, od, "x"), _ptr(out, od, "out"), B, H, W,
+                C_, _stream()), "vdn_im2col_3x3_s2")
     return out
 
 
 def bilinear_nhwc(x, out, B, H, W, Ho, Wo, C_, relu_out=False):
     od = operand_dtype()
-    _check(lib().vdn_bilinear_nhwc(_ptr(x, od, "x"), _ptr(out, od, "out"), B, H, W, Ho, Wo, C_, 1 if relu_out else 0, _stream()), "vdn_bilinear_nhwc")
+    _check(_run("bilinear_nhwc", "hbm", 2.0 * B * C_ * (H * W + Ho * Wo), lib().vdn_bilinear_nhwc, _ptr(x, od, "x"), _ptr(out, od, "out"), B, H, W, Ho, Wo,
+                C_, 1 if relu_out else 0, _stream()), "vdn_bilinear_nhwc")
     return out
 
 
 def bilinear_f32(x, out, N, H, W, Ho, Wo, relu=False):
-    _check(lib().vdn_bilinear_f32(_ptr(x, torch.float32, "x"), _ptr(out, torch.float32, "out"), N, H, W, Ho, Wo, 1 if relu else 0, _stream()),
-           "vdn_bilinear_f32")
+    _check(_run("bilinear_f32", "hbm", 4.0 * N * (H * W + Ho * Wo), lib().vdn_bilinear_f32, _ptr(x, torch.float32, "x"), _ptr(out, torch.float32, "out"),
+                N, H, W, Ho, Wo, 1 if relu else 0, _stream()), "vdn_bilinear_f32")
     return out
 
 
 def relu16(x, out):
     od = operand_dtype()
-    _check(lib().vdn_relu16(_ptr(x, od, "x"), _ptr(out, od, "out"), x.numel(), _stream()), "vdn_relu16")
+    _check(_run("relu16", "hbm", 4.0 * x.numel(), lib().vdn_relu16, _ptr(x, od, "x"), _ptr(out, od, "out"), x.numel(), _stream()), "vdn_relu16")
     return out
 
 
