@@ -1,11 +1,12 @@
 #!/bin/bash
-# quick iteration: op tests (gemm/conv/attention groups) + model parity + bench
+# quick iteration: selected op tests + model parity + bench. usage: gpu_iter.sh "<pytest -k expr for ops>"
 mkdir -p gpurun_out
-timeout -k 10 600 python -m pytest tests/test_ops_gpu.py -q -m gpu -p no:cacheprovider -x -k "gemm or conv3x3 or qkv_split or pixel or temporal_rowmap or patch_tokens" > gpurun_out/iter_ops.log 2>&1
+K="${1:-flash or gemm or conv3x3}"
+timeout -k 10 600 python -m pytest tests/test_ops_gpu.py -q -m gpu -p no:cacheprovider -x -k "$K" > gpurun_out/iter_ops.log 2>&1
 echo "ops exit $?"; tail -n 4 gpurun_out/iter_ops.log
 timeout -k 10 600 python -m pytest tests/test_model_gpu.py -q -m gpu -p no:cacheprovider -s > gpurun_out/iter_model.log 2>&1
 echo "model exit $?"; grep -E "passed|failed|: \{" gpurun_out/iter_model.log | tail -12
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/iter_bench.json 2> gpurun_out/iter_bench.err
+timeout -k 10 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/iter_bench.json 2> gpurun_out/iter_bench.err
 echo "bench exit $?"
 python - <<'PY'
 import json

@@ -19,54 +19,71 @@ namespace vdn {
 // ------------------------------------------------------------------------------------------------
 // flash attention
 // ------------------------------------------------------------------------------------------------
-constexpr int FA_BM = 128;     // queries per CTA
+constexpr int FA_BM = 128;     // queries per softmax group (one TMEM lane per query row)
 constexpr int FA_BN = 128;     // keys per tile
 constexpr int FA_D = 64;       // head dim
-constexpr int FA_THREADS = 160;
-constexpr int FA_TILE = FA_BM * FA_D * 2;  // 16 KB : Q tile, K tile, V^T tile (2 x 8 KB chunks), P chunk
-constexpr int FA_SMEM = FA_TILE /*Q*/ + 2 * FA_TILE /*K*/ + 2 * FA_TILE /*V^T*/ + 2 * FA_TILE /*P, two 64-key chunks*/ + 256;
-constexpr int FA_TMEM_COLS = 256;  // S: cols [0,128), PV: cols [128,192)
+constexpr int FA_GROUPS = 2;   // query tiles per CTA, processed ping-pong by two softmax warpgroups
+constexpr int FA_THREADS = FA_GROUPS * 128 + 128;  // + one control warpgroup: MMA issuer warp, TMA producer warp, 2 idle warps
+constexpr int FA_TILE = FA_BM * FA_D * 2;         // 16 KB : one Q / K / V^T tile, one 64-key chunk of P
+constexpr int FA_SMEM = 2 * FA_TILE /*Q*/ + 2 * FA_TILE /*K x2*/ + 2 * FA_TILE /*V^T x2*/ + 4 * FA_TILE /*P: 2 groups x 2 chunks*/ + 256;
+constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+// The softmax of a head_dim-64 attention is bound by the XU pipe: one ex2 per score at 8 cycles per warp instruction per SM
+// sub-partition (measured, scripts/microbench/pipes.cu), i.e. 1024 cycles per 128x128 score tile per SM, twice the tensor-pipe
+// time of the two MMAs.  The kernel is therefore organised around keeping the XU pipe busy:
+//   * one CTA per SM owns TWO 128-query tiles of the same (frame, head); softmax warpgroups A and B (one query row per thread,
+//     the whole 128-key score row in registers) alternate strictly — a named-barrier token lets exactly one group run its
+//     exp phase while the other does everything that needs no MUFU (wait for S, TMEM loads, masking, row max, O rescale);
+//   * S tiles are issued two KV tiles ahead into per-group TMEM buffers, K and V^T have independent 2-stage TMA rings,
+//     O accumulates in TMEM across KV tiles (lazy rescale: only when the running max grows by more than 2^8).
+// Two independent CTAs per SM (the previous design) drifted into phase and left the XU pipe 47 % busy (ncu, profiles/).
+template <int FMT>
+__global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT, void* __restrict__ out, int tokens,
-                  int heads, int C, int fmt) {
+                  int heads, int C) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + FA_TILE;            // 2 buffers
-  uint8_t* sV = smem + 3 * FA_TILE;        // 2 buffers, each = 2 chunks [64 d rows x 64 keys]
-  uint8_t* sP = smem + 5 * FA_TILE;        // 2 chunks [128 rows x 64 keys]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * FA_TILE);
+  uint8_t* sQ = smem;                      // [group]
+  uint8_t* sK = smem + 2 * FA_TILE;        // [stage]
+  uint8_t* sV = smem + 4 * FA_TILE;        // [stage], each = 2 chunks [64 d rows x 64 keys]
+  uint8_t* sP = smem + 6 * FA_TILE;        // [group][2 chunks of 128 rows x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * FA_TILE);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* pv_full = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [group]
+  uint64_t* s_free = bars + 11;   // [group]
+  uint64_t* p_full = bars + 13;   // [group]
+  uint64_t* pv_done = bars + 15;  // [group]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * FA_BM;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int nt = (tokens + FA_BN - 1) / FA_BN;
+  const int q_tile0 = blockIdx.x * FA_GROUPS;
+  const bool two = (q_tile0 + 1) * FA_BM < tokens;  // the second query tile exists
+  const int ngroups = two ? 2 : 1;
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1024-byte alignment
 
-  if (warp_idx == 4) {
+  if (warp_idx == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQK);
       tma_prefetch_desc(&tmVT);
       mbar_init(q_full, 1);
-      mbar_init(&kv_full[0], 1);
-      mbar_init(&kv_full[1], 1);
-      mbar_init(&kv_empty[0], 1);
-      mbar_init(&kv_empty[1], 1);
-      mbar_init(s_full, 1);
-      mbar_init(s_free, 128);
-      mbar_init(p_full, 128);
-      mbar_init(pv_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_free[i], 128);
+        mbar_init(&p_full[i], 128);
+        mbar_init(&pv_done[i], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -76,91 +93,107 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_PV = tmem_base + 128;
 
-  if (warp_idx == 4) {
+  // Registers are allocated per warpgroup: the control warpgroup gives most of its share to the two softmax warpgroups,
+  // whose threads each hold a whole 128-key score row (12 warps x 168 = 8 x 232 + 4 x 40 registers per lane).
+  if (warp_idx >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+  if (warp_idx == 9) {
+    // ---------------- TMA producer ----------------
     if (lane == 0) {
-      // ---------------- TMA producer + MMA issuer (one thread) ----------------
-      auto load_kv = [&](int j) {
-        const int buf = j & 1;
-        mbar_arrive_expect_tx(&kv_full[buf], 2 * FA_TILE);
-        tma_load_5d(sK + buf * FA_TILE, &tmQK, &kv_full[buf], 0, h, 1, j * FA_BN, b);
-        tma_load_3d(sV + buf * FA_TILE, &tmVT, &kv_full[buf], j * FA_BN, 0, b * heads + h);
-        tma_load_3d(sV + buf * FA_TILE + FA_TILE / 2, &tmVT, &kv_full[buf], j * FA_BN + 64, 0, b * heads + h);
-      };
-      const uint32_t idesc_s = make_idesc(fmt ? 1u : 0u, 128, 128);
-      const uint32_t idesc_pv = make_idesc(fmt ? 1u : 0u, 128, 64);
-      auto issue_s = [&](int j) {
-        const uint64_t dq = make_sdesc_sw128(smem_u32(sQ));
+      mbar_arrive_expect_tx(q_full, ngroups * FA_TILE);
+      for (int g = 0; g < ngroups; ++g) tma_load_5d(sQ + g * FA_TILE, &tmQK, q_full, 0, h, 0, (q_tile0 + g) * FA_BM, b);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], FA_TILE);
+        tma_load_5d(sK + st * FA_TILE, &tmQK, &k_full[st], 0, h, 1, j * FA_BN, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], FA_TILE);
+        tma_load_3d(sV + st * FA_TILE, &tmVT, &v_full[st], j * FA_BN, 0, b * heads + h);
+        tma_load_3d(sV + st * FA_TILE + FA_TILE / 2, &tmVT, &v_full[st], j * FA_BN + 64, 0, b * heads + h);
+      }
+    }
+  } else if (warp_idx == 8) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, 128);
+      constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, 64);
+      auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T
+        const uint64_t dq = make_sdesc_sw128(smem_u32(sQ + g * FA_TILE));
         const uint64_t dk = make_sdesc_sw128(smem_u32(sK + (j & 1) * FA_TILE));
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tmem_S, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(s_full);
+        for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tmem_base + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+        if (g == ngroups - 1) umma_commit(&k_empty[j & 1]);
       };
-      mbar_arrive_expect_tx(q_full, FA_TILE);
-      tma_load_5d(sQ, &tmQK, q_full, 0, h, 0, q0, b);
-      load_kv(0);
-      if (nt > 1) load_kv(1);
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nt; ++j) {
-        const int buf = j & 1;
-        if (j + 1 < nt) {
-          // S(j+1) = Q K(j+1)^T goes to the tensor pipe as soon as the softmax warps have pulled S(j) out of TMEM,
-          // i.e. it runs underneath softmax(j) instead of after it
-          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          mbar_wait(s_free, j & 1);
+      // prologue: S(0) and S(1) of both groups (each group's S buffer is refilled as soon as the group has pulled it into registers)
+      for (int j = 0; j < 2 && j < nt; ++j) {
+        mbar_wait(&k_full[j], 0);
+        for (int g = 0; g < ngroups; ++g) {
+          if (j > 0) mbar_wait(&s_free[g], 0);
           tc_fence_after();
-          issue_s(j + 1);
+          issue_s(g, j);
         }
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        {
-          const uint32_t pbase = smem_u32(sP);
-          const uint32_t vbase = smem_u32(sV + buf * FA_TILE);
+      }
+      for (int j = 0; j < nt; ++j) {
+        const int st = j & 1;
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&p_full[g], j & 1);
+          if (g == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t pbase = smem_u32(sP + g * 2 * FA_TILE);
+          const uint32_t vbase = smem_u32(sV + st * FA_TILE);
 #pragma unroll
           for (int kk = 0; kk < FA_BN / 16; ++kk) {
             const uint32_t chunk = kk >> 2, sub = kk & 3;
             const uint64_t dp = make_sdesc_sw128(pbase + chunk * FA_TILE) + 2 * sub;
             const uint64_t dv = make_sdesc_sw128(vbase + chunk * (FA_TILE / 2)) + 2 * sub;
-            umma_f16(tmem_PV, dp, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);  // O accumulates in TMEM across KV tiles
+            umma_f16(tmem_base + 256 + g * 64, dp, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);  // O accumulates in TMEM across KV tiles
           }
-          umma_commit(pv_full);
-          umma_commit(&kv_empty[buf]);
-        }
-        if (j + 2 < nt) {
-          mbar_wait(&kv_empty[buf], (j >> 1) & 1);
-          load_kv(j + 2);
+          umma_commit(&pv_done[g]);
+          if (g == ngroups - 1) umma_commit(&v_empty[st]);
+          if (j + 2 < nt) {
+            mbar_wait(&s_free[g], (j + 1) & 1);
+            if (g == 0) mbar_wait(&k_full[st], ((j + 2) >> 1) & 1);
+            tc_fence_after();
+            issue_s(g, j + 2);
+          }
         }
       }
     }
+  }
   } else {
-    // ---------------- softmax / output warps: one query row per thread ----------------
-    const int r = threadIdx.x;  // 0..127 == TMEM lane
-    const uint32_t lane_off = uint32_t(warp_idx * 32) << 16;
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+  if (warp_idx < 4 * ngroups) {
+    // ---------------- softmax / output warpgroups: one query row per thread ----------------
+    const int g = warp_idx >> 2;
+    const int r = threadIdx.x & 127;  // row in the query tile == TMEM lane
+    const uint32_t lane_off = uint32_t((warp_idx & 3) * 32) << 16;
+    const uint32_t tmem_S = tmem_base + g * 128 + lane_off;
+    const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
     const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     float m = -INFINITY, l = 0.0f;
-    uint8_t* p_row = sP + r * 128;
+    uint8_t* p_row = sP + g * 2 * FA_TILE + r * 128;
     const int sw = r & 7;
+    // XU token: barrier 1 admits group A to its exp phase, barrier 2 group B.  B primes A's first turn.
+    if (two && g == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
 
     for (int j = 0; j < nt; ++j) {
-      const int kv0 = j * FA_BN;
-      const int nvalid = min(FA_BN, tokens - kv0);
-      mbar_wait(s_full, j & 1);
+      const int nvalid = min(FA_BN, tokens - j * FA_BN);
+      mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
-      // the whole S row (128 fp32) in registers: four TMEM loads in flight, one wait
       uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld32(tmem_S + lane_off + 0, s0);
-      tmem_ld32(tmem_S + lane_off + 32, s1);
-      tmem_ld32(tmem_S + lane_off + 64, s2);
-      tmem_ld32(tmem_S + lane_off + 96, s3);
+      tmem_ld32(tmem_S + 0, s0);
+      tmem_ld32(tmem_S + 32, s1);
+      tmem_ld32(tmem_S + 64, s2);
+      tmem_ld32(tmem_S + 96, s3);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_free);  // S(j) is out of TMEM: the issuer may overwrite it with S(j+1)
-      if (nvalid < FA_BN) {  // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
+      mbar_arrive(&s_free[g]);  // S(j) is out of TMEM: the issuer may overwrite it with S(j+2)
+      if (nvalid < FA_BN) {     // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= nvalid) s0[i] = 0xff800000u;
@@ -185,26 +218,30 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       const bool warp_rescale = __any_sync(0xffffffffu, grow);
       // P(j) may only overwrite P(j-1) once PV(j-1) has consumed it; the same wait makes O safe to rescale
       if (j > 0) {
-        mbar_wait(pv_full, (j - 1) & 1);
+        mbar_wait(&pv_done[g], (j - 1) & 1);
         tc_fence_after();
         if (warp_rescale) {
-          const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move (ex2(-inf) = 0 on the first tile)
+          const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move
           l *= alpha;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
-            tmem_ld32(tmem_PV + lane_off + c * 32, o);
+            tmem_ld32(tmem_O + c * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_PV + lane_off + c * 32, o);
+            tmem_st32(tmem_O + c * 32, o);
           }
           tmem_st_wait();
         }
       }
       m = m_new;
+      // ---- exp phase: owns the XU pipe ----
+      if (two) {
+        if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
       float sum0 = 0.0f, sum1 = 0.0f;
-      // probabilities -> 16-bit -> swizzled smem, 8 keys (one 16-byte piece) at a time to keep temporaries short-lived
       auto emit = [&](const uint32_t (&sv)[32], int c) {
         uint8_t* chunk_row = p_row + (c >> 1) * FA_TILE;
 #pragma unroll
@@ -218,44 +255,50 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
           const int piece = (c & 1) * 4 + q;  // 128B swizzle: 16-byte piece index ^= row & 7
           *reinterpret_cast<uint4*>(chunk_row + ((piece ^ sw) << 4)) =
-              make_uint4(pack16(pv[0], pv[1], fmt), pack16(pv[2], pv[3], fmt), pack16(pv[4], pv[5], fmt), pack16(pv[6], pv[7], fmt));
+              make_uint4(T16f<FMT>::pack(pv[0], pv[1]), T16f<FMT>::pack(pv[2], pv[3]), T16f<FMT>::pack(pv[4], pv[5]), T16f<FMT>::pack(pv[6], pv[7]));
         }
       };
       emit(s0, 0);
       emit(s1, 1);
       emit(s2, 2);
       emit(s3, 3);
+      if (two) {  // hand the XU pipe to the other group (B's last turn has no successor)
+        if (g == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        else if (j + 1 < nt) asm volatile("bar.arrive 1, 256;" ::: "memory");
+      }
       l += sum0 + sum1;
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[g]);
     }
-    mbar_wait(pv_full, (nt - 1) & 1);
+    mbar_wait(&pv_done[g], (nt - 1) & 1);
     tc_fence_after();
-    const bool ok = q0 + r < tokens;
+    const int q_row = (q_tile0 + g) * FA_BM + r;
+    const bool ok = q_row < tokens;
     const float inv = 1.0f / l;
-    uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q0 + r) * C + h * FA_D;
+    uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q_row) * C + h * FA_D;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem_PV + lane_off + c * 32, v);
+      tmem_ld32(tmem_O + c * 32, v);
       tmem_ld_wait();
       if (ok) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 u;
-          u.x = pack16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, fmt);
-          u.y = pack16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, fmt);
-          u.z = pack16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, fmt);
-          u.w = pack16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, fmt);
+          u.x = T16f<FMT>::pack(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+          u.y = T16f<FMT>::pack(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          u.z = T16f<FMT>::pack(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+          u.w = T16f<FMT>::pack(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
           *reinterpret_cast<uint4*>(o + c * 32 + i) = u;
         }
       }
     }
   }
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 4) {
+  if (warp_idx == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, FA_TMEM_COLS);
   }
@@ -380,12 +423,14 @@ extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(flash_attn): ") + cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid((tokens + FA_BM - 1) / FA_BM, heads, B);
-  flash_attn_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQK, tmVT, out, tokens, heads, C, fmt);
+  dim3 grid((tokens + FA_GROUPS * FA_BM - 1) / (FA_GROUPS * FA_BM), heads, B);
+  if (fmt) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQK, tmVT, out, tokens, heads, C);
+  else flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQK, tmVT, out, tokens, heads, C);
   count_launch();
   return check_launch("flash_attn_kernel");
 }

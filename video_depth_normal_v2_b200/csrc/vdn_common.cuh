@@ -42,6 +42,10 @@ template <> struct T16<__half> {
   static constexpr uint32_t kUmmaFormat = 0;  // F16F32Format::F16
 };
 
+// compile-time format index (0 = fp16, 1 = bf16)
+template <int FMT> struct T16f : T16<__half> {};
+template <> struct T16f<1> : T16<__nv_bfloat16> {};
+
 // runtime-format versions (fmt: 0 = fp16, 1 = bf16), for kernels that are not templated on T
 __device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
   return fmt ? T16<__nv_bfloat16>::pack(a, b) : T16<__half>::pack(a, b);
