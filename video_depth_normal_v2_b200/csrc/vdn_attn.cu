@@ -24,9 +24,9 @@ constexpr int FA_BN = 128;     // keys per tile
 constexpr int FA_D = 64;       // head dim
 constexpr int FA_GROUPS = 2;   // query tiles per CTA, processed ping-pong by two softmax warpgroups
 constexpr int FA_THREADS = FA_GROUPS * 128 + 128;  // + one control warpgroup: MMA issuer warp, TMA producer warp, 2 idle warps
-constexpr int FA_TILE = FA_BM * FA_D * 2;         // 16 KB : one Q / K / V^T tile, one 64-key chunk of P
-constexpr int FA_SMEM = 2 * FA_TILE /*Q*/ + 2 * FA_TILE /*K x2*/ + 2 * FA_TILE /*V^T x2*/ + 4 * FA_TILE /*P: 2 groups x 2 chunks*/ + 256;
-constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+constexpr int FA_TILE = FA_BM * FA_D * 2;         // 16 KB : one Q / K / V^T tile
+constexpr int FA_SMEM = 2 * FA_TILE /*Q*/ + 2 * FA_TILE /*K x2*/ + 2 * FA_TILE /*V^T x2*/ + 256;
+constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
 
 // The softmax of a head_dim-64 attention is bound by the XU pipe: one ex2 per score at 8 cycles per warp instruction per SM
 // sub-partition (measured, scripts/microbench/pipes.cu), i.e. 1024 cycles per 128x128 score tile per SM, twice the tensor-pipe
@@ -34,6 +34,9 @@ constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_
 //   * one CTA per SM owns TWO 128-query tiles of the same (frame, head); softmax warpgroups A and B (one query row per thread,
 //     the whole 128-key score row in registers) alternate strictly — a named-barrier token lets exactly one group run its
 //     exp phase while the other does everything that needs no MUFU (wait for S, TMEM loads, masking, row max, O rescale);
+//   * P never touches shared memory: the probabilities are packed to 16 bits and written to TMEM (tcgen05.st), and O += P V
+//     reads its A operand from TMEM.  With P in shared memory the operand fetches of the two MMAs plus the P stores came to
+//     ~112 KB per tile per group against a 128 B/clk shared-memory pipe — as long as the exp phase itself;
 //   * S tiles are issued two KV tiles ahead into per-group TMEM buffers, K and V^T have independent 2-stage TMA rings,
 //     O accumulates in TMEM across KV tiles (lazy rescale: only when the running max grows by more than 2^8).
 // Two independent CTAs per SM (the previous design) drifted into phase and left the XU pipe 47 % busy (ncu, profiles/).
@@ -45,8 +48,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   uint8_t* sQ = smem;                      // [group]
   uint8_t* sK = smem + 2 * FA_TILE;        // [stage]
   uint8_t* sV = smem + 4 * FA_TILE;        // [stage], each = 2 chunks [64 d rows x 64 keys]
-  uint8_t* sP = smem + 6 * FA_TILE;        // [group][2 chunks of 128 rows x 64 keys]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * FA_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * FA_TILE);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
@@ -144,14 +146,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           mbar_wait(&p_full[g], j & 1);
           if (g == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
           tc_fence_after();
-          const uint32_t pbase = smem_u32(sP + g * 2 * FA_TILE);
           const uint32_t vbase = smem_u32(sV + st * FA_TILE);
 #pragma unroll
           for (int kk = 0; kk < FA_BN / 16; ++kk) {
             const uint32_t chunk = kk >> 2, sub = kk & 3;
-            const uint64_t dp = make_sdesc_sw128(pbase + chunk * FA_TILE) + 2 * sub;
             const uint64_t dv = make_sdesc_sw128(vbase + chunk * (FA_TILE / 2)) + 2 * sub;
-            umma_f16(tmem_base + 256 + g * 64, dp, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);  // O accumulates in TMEM across KV tiles
+            // A = P_g from TMEM (16 keys = 8 packed columns per MMA); O accumulates in TMEM across KV tiles
+            umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&pv_done[g]);
           if (g == ngroups - 1) umma_commit(&v_empty[st]);
@@ -176,8 +177,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
     const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     float m = -INFINITY, l = 0.0f;
-    uint8_t* p_row = sP + g * 2 * FA_TILE + r * 128;
-    const int sw = r & 7;
+    const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_off;
     // XU token: barrier 1 admits group A to its exp phase, barrier 2 group B.  B primes A's first turn.
     if (two && g == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
 
@@ -242,8 +242,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
         else asm volatile("bar.sync 2, 256;" ::: "memory");
       }
       float sum0 = 0.0f, sum1 = 0.0f;
+      uint32_t pk[32];  // 64 probabilities packed to 16 bits = 32 TMEM columns
       auto emit = [&](const uint32_t (&sv)[32], int c) {
-        uint8_t* chunk_row = p_row + (c >> 1) * FA_TILE;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float pv[8];
@@ -253,10 +253,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(pv[i]);
           sum0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
           sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-          const int piece = (c & 1) * 4 + q;  // 128B swizzle: 16-byte piece index ^= row & 7
-          *reinterpret_cast<uint4*>(chunk_row + ((piece ^ sw) << 4)) =
-              make_uint4(T16f<FMT>::pack(pv[0], pv[1]), T16f<FMT>::pack(pv[2], pv[3]), T16f<FMT>::pack(pv[4], pv[5]), T16f<FMT>::pack(pv[6], pv[7]));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pk[(c & 1) * 16 + q * 4 + i] = T16f<FMT>::pack(pv[2 * i], pv[2 * i + 1]);
         }
+        if (c & 1) tmem_st32(tmem_P + (c >> 1) * 32, pk);
       };
       emit(s0, 0);
       emit(s1, 1);
@@ -267,8 +267,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
         else if (j + 1 < nt) asm volatile("bar.arrive 1, 256;" ::: "memory");
       }
       l += sum0 + sum1;
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
       mbar_arrive(&p_full[g]);
     }
     mbar_wait(&pv_done[g], (nt - 1) & 1);

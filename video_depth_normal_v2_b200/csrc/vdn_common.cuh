@@ -235,6 +235,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       : "memory");
 }
 
+// Same with the A operand read from TMEM (128 lanes x K/2 packed 32-bit columns): no shared-memory traffic for A.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate (cute/arch/mma_sm100_desc.hpp InstrDescriptor bit layout):
 //   [4,6) c_format=1 (F32) | [7,10) a_format | [10,13) b_format | bit15 a_major | bit16 b_major | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
