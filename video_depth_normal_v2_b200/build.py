@@ -12,8 +12,8 @@ LIB = os.path.join(HERE, "libvdn_b200.so")
 SOURCES = ["vdn_host.cu", "vdn_gemm.cu", "vdn_attn.cu", "vdn_elem.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas=-v",
-]
+    "-Xcompiler", "-fPIC", "-Xptxas=-v",
+] + os.environ.get("VDN_EXTRA_NVCC_FLAGS", "").split()  # debug builds only, e.g. -DVDN_FA_TIMELINE
 
 
 def _nvcc() -> str:

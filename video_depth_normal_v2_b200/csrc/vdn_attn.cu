@@ -31,9 +31,11 @@ constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_
 // The softmax of a head_dim-64 attention is bound by the XU pipe: one ex2 per score at 8 cycles per warp instruction per SM
 // sub-partition (measured, scripts/microbench/pipes.cu), i.e. 1024 cycles per 128x128 score tile per SM, twice the tensor-pipe
 // time of the two MMAs.  The kernel is therefore organised around keeping the XU pipe busy:
-//   * one CTA per SM owns TWO 128-query tiles of the same (frame, head); softmax warpgroups A and B (one query row per thread,
-//     the whole 128-key score row in registers) alternate strictly — a named-barrier token lets exactly one group run its
-//     exp phase while the other does everything that needs no MUFU (wait for S, TMEM loads, masking, row max, O rescale);
+//   * one CTA per SM owns TWO 128-query tiles of the same (frame, head), one softmax warpgroup each (one query row per thread,
+//     the whole 128-key score row in registers), so that one group's MUFU stream overlaps the other's non-MUFU work (wait for
+//     S, TMEM loads, masking, row max, O rescale).  A warp's own instruction costs add up (MUFU 8 + FFMA 1 + FADD 1 + F2FP 0.5
+//     cycles per score, measured in scripts/microbench/exp_phase.cu): one warp alone reaches 10.5 cycles per score, two
+//     overlapping warps 8.5 — which is why the groups are NOT serialised by a token (tried: slower);
 //   * P never touches shared memory: the probabilities are packed to 16 bits and written to TMEM (tcgen05.st), and O += P V
 //     reads its A operand from TMEM.  With P in shared memory the operand fetches of the two MMAs plus the P stores came to
 //     ~112 KB per tile per group against a 128 B/clk shared-memory pipe — as long as the exp phase itself;
@@ -101,67 +103,82 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   if (warp_idx >= 8) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
   if (warp_idx == 9) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    // ---------------- TMA producer (warp-uniform control flow, one elected lane issues) ----------------
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ngroups * FA_TILE);
       for (int g = 0; g < ngroups; ++g) tma_load_5d(sQ + g * FA_TILE, &tmQK, q_full, 0, h, 0, (q_tile0 + g) * FA_BM, b);
-      for (int j = 0; j < nt; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nt; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[st], FA_TILE);
         tma_load_5d(sK + st * FA_TILE, &tmQK, &k_full[st], 0, h, 1, j * FA_BN, b);
-        mbar_wait(&v_empty[st], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[st], FA_TILE);
         tma_load_3d(sV + st * FA_TILE, &tmVT, &v_full[st], j * FA_BN, 0, b * heads + h);
         tma_load_3d(sV + st * FA_TILE + FA_TILE / 2, &tmVT, &v_full[st], j * FA_BN + 64, 0, b * heads + h);
       }
+      __syncwarp();
     }
   } else if (warp_idx == 8) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, 128);
-      constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, 64);
-      auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T
-        const uint64_t dq = make_sdesc_sw128(smem_u32(sQ + g * FA_TILE));
-        const uint64_t dk = make_sdesc_sw128(smem_u32(sK + (j & 1) * FA_TILE));
+    // The whole warp runs the (warp-uniform) control flow and one elected lane issues: with the loops under `if (lane == 0)`
+    // the compiler cannot prove the descriptors uniform and wraps every tcgen05.mma in an R2UR / ELECT / BRA.U.ANY waterfall.
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, 128);
+    constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, 64);
+    const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T
+      if (elect_one()) {
+        const uint64_t dq = make_sdesc_sw128(q_addr + g * FA_TILE);
+        const uint64_t dk = make_sdesc_sw128(k_addr + (j & 1) * FA_TILE);
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tmem_base + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+        for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tb + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
         umma_commit(&s_full[g]);
         if (g == ngroups - 1) umma_commit(&k_empty[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      // prologue: S(0) and S(1) of both groups (each group's S buffer is refilled as soon as the group has pulled it into registers)
-      for (int j = 0; j < 2 && j < nt; ++j) {
-        mbar_wait(&k_full[j], 0);
-        for (int g = 0; g < ngroups; ++g) {
-          if (j > 0) mbar_wait(&s_free[g], 0);
-          tc_fence_after();
-          issue_s(g, j);
-        }
       }
-      for (int j = 0; j < nt; ++j) {
-        const int st = j & 1;
-        for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(&p_full[g], j & 1);
-          if (g == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
-          tc_fence_after();
-          const uint32_t vbase = smem_u32(sV + st * FA_TILE);
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    // prologue: S(0) and S(1) of both groups (each group's S buffer is refilled as soon as the group has pulled it into registers)
+    for (int j = 0; j < 2 && j < nt; ++j) {
+      mbar_wait(&k_full[j], 0);
+      for (int g = 0; g < ngroups; ++g) {
+        if (j > 0) mbar_wait(&s_free[g], 0);
+        tc_fence_after();
+        issue_s(g, j);
+      }
+    }
+    for (int j = 0; j < nt; ++j) {
+      const int st = j & 1;
+      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(&p_full[g], j & 1);
+        if (g == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dv0 = make_sdesc_sw128(v_addr + st * FA_TILE);
 #pragma unroll
           for (int kk = 0; kk < FA_BN / 16; ++kk) {
-            const uint32_t chunk = kk >> 2, sub = kk & 3;
-            const uint64_t dv = make_sdesc_sw128(vbase + chunk * (FA_TILE / 2)) + 2 * sub;
-            // A = P_g from TMEM (16 keys = 8 packed columns per MMA); O accumulates in TMEM across KV tiles
-            umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            // B = V^T chunk (kk >> 2), 16 keys further per MMA; A = P_g from TMEM (16 keys = 8 packed columns per MMA);
+            // O accumulates in TMEM across KV tiles
+            const uint64_t dv = dv0 + uint64_t(((kk >> 2) * (FA_TILE / 2)) >> 4) + 2 * (kk & 3);
+            umma_f16_ts(tb + 256 + g * 64, tb + 384 + g * 64 + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&pv_done[g]);
           if (g == ngroups - 1) umma_commit(&v_empty[st]);
-          if (j + 2 < nt) {
-            mbar_wait(&s_free[g], (j + 1) & 1);
-            if (g == 0) mbar_wait(&k_full[st], ((j + 2) >> 1) & 1);
-            tc_fence_after();
-            issue_s(g, j + 2);
-          }
+        }
+        __syncwarp();
+        if (j + 2 < nt) {
+          mbar_wait(&s_free[g], (j + 1) & 1);
+          if (g == 0) mbar_wait(&k_full[st], ((j + 2) >> 1) & 1);
+          tc_fence_after();
+          issue_s(g, j + 2);
         }
       }
     }
@@ -178,8 +195,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     float m = -INFINITY, l = 0.0f;
     const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_off;
-    // XU token: barrier 1 admits group A to its exp phase, barrier 2 group B.  B primes A's first turn.
-    if (two && g == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
 
     for (int j = 0; j < nt; ++j) {
       const int nvalid = min(FA_BN, tokens - j * FA_BN);
@@ -236,11 +251,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
         }
       }
       m = m_new;
-      // ---- exp phase: owns the XU pipe ----
-      if (two) {
-        if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-        else asm volatile("bar.sync 2, 256;" ::: "memory");
-      }
       float sum0 = 0.0f, sum1 = 0.0f;
       uint32_t pk[32];  // 64 probabilities packed to 16 bits = 32 TMEM columns
       auto emit = [&](const uint32_t (&sv)[32], int c) {
@@ -262,10 +272,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       emit(s1, 1);
       emit(s2, 2);
       emit(s3, 3);
-      if (two) {  // hand the XU pipe to the other group (B's last turn has no successor)
-        if (g == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-        else if (j + 1 < nt) asm volatile("bar.arrive 1, 256;" ::: "memory");
-      }
       l += sum0 + sum1;
       tmem_st_wait();
       tc_fence_before();
