@@ -113,6 +113,8 @@ int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H, int32_t W,
  * optional second input added before interpolation is NOT supported; relu_out writes max(x,0). */
 int vdn_bilinear_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, int32_t relu_out,
                       void* stream);
+/* same, additionally writing relu(out) to out_relu (the ReLU'd copy the next ResidualConvUnit consumes, util/blocks.py:77) */
+int vdn_bilinear_nhwc2(const void* x, void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream);
 /* bilinear resize of fp32 planes [N,H,W] -> [N,Ho,Wo], align_corners=True, optional ReLU (video_depth.py:63-64,110) */
 int vdn_bilinear_f32(const float* x, float* out, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t relu, void* stream);
 /* out = relu(x), 16-bit, n elements (util/blocks.py:78) */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "vdn_write_cls": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdn_im2col_3x3_s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_bilinear_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vdn_bilinear_nhwc2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_bilinear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_relu16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vdn_cast_f32_to_16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -87,6 +87,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics: one block per (frame, group); two passes over an L2-resident slice
 // ------------------------------------------------------------------------------------------------
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, int D, int C, int groups, float eps, int fmt) {
   const int f = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -94,13 +95,23 @@ groupnorm_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, in
   const uint16_t* base = reinterpret_cast<const uint16_t*>(x) + (long long)f * D * C + g * cg;
   __shared__ double red[8];
   __shared__ float s_mean;
-  const long long n = (long long)D * cg;
+  const int n = D * cg;
+  const int vpr = cg >> 3;  // 16-byte vectors per pixel row of this group (VEC path: cg % 8 == 0)
+  const int nvec = D * vpr;
   // pass 1: mean
   float s = 0.0f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long d = i / cg;
-    const int c = int(i - d * cg);
-    s += load16(base, d * C + c, fmt);
+  if (VEC) {
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const int d = i / vpr, v = i - d * vpr;
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)d * C + v * 8);
+      const float2 a = unpack16(u.x, fmt), b2 = unpack16(u.y, fmt), c2 = unpack16(u.z, fmt), d2 = unpack16(u.w, fmt);
+      s += ((a.x + a.y) + (b2.x + b2.y)) + ((c2.x + c2.y) + (d2.x + d2.y));
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int d = i / cg, c = i - d * cg;
+      s += load16(base, (long long)d * C + c, fmt);
+    }
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (double)s;
@@ -112,12 +123,26 @@ groupnorm_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, in
   }
   __syncthreads();
   const float mean = s_mean;
+  // pass 2 (the slice is L2-resident): centred sum of squares
   float q = 0.0f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long d = i / cg;
-    const int c = int(i - d * cg);
-    const float v = load16(base, d * C + c, fmt) - mean;
-    q += v * v;
+  if (VEC) {
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const int d = i / vpr, v = i - d * vpr;
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)d * C + v * 8);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack16(w4[k], fmt);
+        q = fmaf(a.x - mean, a.x - mean, q);
+        q = fmaf(a.y - mean, a.y - mean, q);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int d = i / cg, c = i - d * cg;
+      const float v = load16(base, (long long)d * C + c, fmt) - mean;
+      q += v * v;
+    }
   }
   q = warp_sum(q);
   __syncthreads();
@@ -240,42 +265,50 @@ __device__ __forceinline__ void ac_coords(int dst, float scale, int in_size, int
   l1 = src - (float)i0;
 }
 
+// grid (x-chunks of one output row, Ho, B): row coordinates are block-uniform, only 32-bit index arithmetic per thread
+// (the flat 64-bit div/mod version was instruction-bound at ~30 % of HBM bandwidth).  Each thread produces 8 channels of one
+// output pixel from four 16-byte loads (neighbouring pixels hit L1/L2) and writes one or two 16-byte results.
+template <int FMT>
 __global__ void __launch_bounds__(256)
-bilinear_nhwc_kernel(const void* __restrict__ x, void* __restrict__ out, int B, int H, int W, int Ho, int Wo, int C, int relu_out, int fmt) {
-  const int cv = C >> 3;
-  const long long total = (long long)B * Ho * Wo * cv;
+bilinear_nhwc_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4* __restrict__ o_relu, int H, int W, int Ho, int Wo, int cv,
+                     int relu_out) {
+  const int ho = blockIdx.y;
+  const long long bimg = blockIdx.z;
   const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.0f;
   const float sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.0f;
-  const uint4* xin = reinterpret_cast<const uint4*>(x);
-  uint4* o = reinterpret_cast<uint4*>(out);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = int(idx % cv);
-    long long t = idx / cv;
-    const int wo = int(t % Wo);
-    t /= Wo;
-    const int ho = int(t % Ho);
-    const long long bimg = t / Ho;
-    int h0, h1, w0, w1;
-    float lh, lw;
-    ac_coords(ho, sh, H, h0, h1, lh);
+  int h0, h1;
+  float lh;
+  ac_coords(ho, sh, H, h0, h1, lh);
+  const uint4* row0 = xin + (bimg * H + h0) * (long long)W * cv;
+  const uint4* row1 = xin + (bimg * H + h1) * (long long)W * cv;
+  const long long obase = (bimg * Ho + ho) * (long long)Wo * cv;
+  const int per_row = Wo * cv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+    const int wo = i / cv;
+    const int c8 = i - wo * cv;
+    int w0, w1;
+    float lw;
     ac_coords(wo, sw, W, w0, w1, lw);
-    const uint4 a = xin[((bimg * H + h0) * W + w0) * cv + c8];
-    const uint4 b = xin[((bimg * H + h0) * W + w1) * cv + c8];
-    const uint4 c = xin[((bimg * H + h1) * W + w0) * cv + c8];
-    const uint4 d = xin[((bimg * H + h1) * W + w1) * cv + c8];
+    const uint4 a = __ldg(row0 + w0 * cv + c8);
+    const uint4 b = __ldg(row0 + w1 * cv + c8);
+    const uint4 c = __ldg(row1 + w0 * cv + c8);
+    const uint4 d = __ldg(row1 + w1 * cv + c8);
     const float w00 = (1.0f - lh) * (1.0f - lw), w01 = (1.0f - lh) * lw, w10 = lh * (1.0f - lw), w11 = lh * lw;
     const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
-    uint4 r;
+    uint4 r, rr;
     uint32_t* pr = &r.x;
+    uint32_t* prr = &rr.x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 fa = unpack16(pa[i], fmt), fb = unpack16(pb[i], fmt), fc = unpack16(pc[i], fmt), fd = unpack16(pd[i], fmt);
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = T16f<FMT>::unpack(pa[k]), fb = T16f<FMT>::unpack(pb[k]), fc = T16f<FMT>::unpack(pc[k]), fd = T16f<FMT>::unpack(pd[k]);
       float y0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
       float y1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
       if (relu_out) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
-      pr[i] = pack16(y0, y1, fmt);
+      pr[k] = T16f<FMT>::pack(y0, y1);
+      prr[k] = T16f<FMT>::pack(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f));
     }
-    o[idx] = r;
+    o[obase + i] = r;
+    if (o_relu != nullptr) o_relu[obase + i] = rr;
   }
 }
 
@@ -423,7 +456,9 @@ extern "C" int vdn_groupnorm_stats(const void* x, float* stats, int32_t frames, 
   VDN_STREAM;
   if (!x || !stats) return set_error("vdn_groupnorm_stats: null pointer");
   if (groups <= 0 || C % groups != 0) return set_error("vdn_groupnorm_stats: C must be divisible by groups");
-  groupnorm_stats_kernel<<<frames * groups, 256, 0, stream>>>(x, stats, D, C, groups, eps, get_operand_format());
+  if ((long long)D * C > 0x7fffffffLL) return set_error("vdn_groupnorm_stats: frame too large");
+  if ((C / groups) % 8 == 0 && C % 8 == 0) groupnorm_stats_kernel<true><<<frames * groups, 256, 0, stream>>>(x, stats, D, C, groups, eps, get_operand_format());
+  else groupnorm_stats_kernel<false><<<frames * groups, 256, 0, stream>>>(x, stats, D, C, groups, eps, get_operand_format());
   count_launch();
   return check_launch("groupnorm_stats_kernel");
 }
@@ -466,15 +501,36 @@ extern "C" int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H,
   return check_launch("im2col_3x3_s2_kernel");
 }
 
+static int launch_bilinear_nhwc(const void* x, void* out, void* out_relu, int B, int H, int W, int Ho, int Wo, int C, int relu_out, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return set_error("vdn_bilinear_nhwc: bad shape");
+  if (Ho > 65535 || B > 65535) return set_error("vdn_bilinear_nhwc: Ho and B must fit a grid dimension");
+  const int cv = C / 8;
+  const int per_row = Wo * cv;
+  dim3 grid((per_row + 255) / 256, Ho, B);
+  if (grid.x > 8) grid.x = 8;
+  const uint4* xi = reinterpret_cast<const uint4*>(x);
+  uint4* o = reinterpret_cast<uint4*>(out);
+  uint4* orl = reinterpret_cast<uint4*>(out_relu);
+  if (get_operand_format()) bilinear_nhwc_kernel<1><<<grid, 256, 0, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, relu_out);
+  else bilinear_nhwc_kernel<0><<<grid, 256, 0, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, relu_out);
+  count_launch();
+  return check_launch("bilinear_nhwc_kernel");
+}
+
 extern "C" int vdn_bilinear_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, int32_t relu_out,
                                  void* stream_v) {
   VDN_STREAM;
   if (!x || !out) return set_error("vdn_bilinear_nhwc: null pointer");
   if (C % 8 != 0) return set_error("vdn_bilinear_nhwc: C must be a multiple of 8");
-  bilinear_nhwc_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256, 32), 256, 0, stream>>>(x, out, B, H, W, Ho, Wo, C, relu_out,
-                                                                                             get_operand_format());
-  count_launch();
-  return check_launch("bilinear_nhwc_kernel");
+  return launch_bilinear_nhwc(x, out, nullptr, B, H, W, Ho, Wo, C, relu_out, stream);
+}
+
+extern "C" int vdn_bilinear_nhwc2(const void* x, void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C,
+                                  void* stream_v) {
+  VDN_STREAM;
+  if (!x || !out || !out_relu) return set_error("vdn_bilinear_nhwc2: null pointer");
+  if (C % 8 != 0) return set_error("vdn_bilinear_nhwc2: C must be a multiple of 8");
+  return launch_bilinear_nhwc(x, out, out_relu, B, H, W, Ho, Wo, C, 0, stream);
 }
 
 extern "C" int vdn_bilinear_f32(const float* x, float* out, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t relu, void* stream_v) {

@@ -33,7 +33,12 @@ constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - 2 * 256 * 4 /*bias+g
 
 // EPI_PLAIN: bias / act / out (+out2), no residual operands (keeps registers free so the GELU chains interleave);
 // EPI_RES  : additionally LayerScale gamma + residual(s), with register prefetch buffers.
-enum { EPI_PLAIN = 0, EPI_QKV = 1, EPI_GEGLU = 2, EPI_PIXSHUF = 3, EPI_HEAD = 4, EPI_RES = 5 };
+// EPI_TMA  : bias / act / gamma, identity row map; the tile leaves through swizzled shared-memory staging and TMA: a plain tensor
+//            store, or an fp32 reduce-add when the output is accumulated in place (x += gamma * (A W^T + b)) — the old value is
+//            never loaded into the SM.  Row-per-thread global accesses (32 rows x 16 B per warp instruction) cost 32 LSU
+//            wavefronts each and made the epilogue, not the MMA, the bound of the K=1024 residual GEMMs (tensor pipe 29 % busy).
+enum { EPI_PLAIN = 0, EPI_QKV = 1, EPI_GEGLU = 2, EPI_PIXSHUF = 3, EPI_HEAD = 4, EPI_RES = 5, EPI_TMA = 6 };
+constexpr int kStagingBytesPerWarp = 4096;  // one 32 x 32 fp32 chunk, or two 32 x 32 16-bit chunks
 
 struct GemmKParams {
   int M, N;
@@ -60,16 +65,17 @@ struct GemmKParams {
   float head_b;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = EPI_PLAIN>
 struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStagingBytes = EPI == EPI_TMA ? kNumEpiWarps * kStagingBytesPerWarp : 0;
+  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kParamBytes = 2 * BLOCK_N * 4;  // this tile's bias and gamma slices
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + kParamBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + kParamBytes;
 };
 
 // Per-thread output-row context, computed once per tile.
@@ -278,20 +284,22 @@ __device__ __forceinline__ void epi_head(const GemmKParams& p, const RowCtx& rc,
 
 template <int BLOCK_N, int EPI, int FMT>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const GemmKParams p) {
+  using Cfg = GemmCfg<BLOCK_N, EPI>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;  // EPI_TMA staging (1024-byte aligned: stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* sbias = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
+  float* sbias = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes + 256);
   float* sgamma = sbias + BLOCK_N;
 
   const int warp_idx = threadIdx.x >> 5;
@@ -301,6 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI == EPI_TMA) tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -320,23 +329,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.num_n_blocks;
-        const int m_tile = tile / p.num_n_blocks;
-        int img = 0, h0 = 0, w0 = 0;
-        if (p.conv) {
-          const int tw_i = m_tile % p.tiles_w;
-          const int t2 = m_tile / p.tiles_w;
-          const int th_i = t2 % p.tiles_h;
-          img = t2 / p.tiles_h;
-          h0 = th_i * p.TH;
-          w0 = tw_i * p.TW;
-        }
-        for (int k = 0; k < p.num_k_blocks; ++k) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // Producer and issuer warps run their (warp-uniform) loops with all lanes and elect one lane per issue: under a plain
+    // `if (lane == 0)` the compiler cannot prove descriptors / coordinates uniform and wraps every tcgen05.mma and TMA in an
+    // R2UR + ELECT + BRA.U.ANY waterfall (~80 cycles per MMA, longer than a 128x64x16 MMA itself).
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.num_n_blocks;
+      const int m_tile = tile / p.num_n_blocks;
+      int img = 0, h0 = 0, w0 = 0;
+      if (p.conv) {
+        const int tw_i = m_tile % p.tiles_w;
+        const int t2 = m_tile / p.tiles_w;
+        const int th_i = t2 % p.tiles_h;
+        img = t2 / p.tiles_h;
+        h0 = th_i * p.TH;
+        w0 = tw_i * p.TW;
+      }
+      for (int k = 0; k < p.num_k_blocks; ++k) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (p.conv) {
             const int tap = k / p.cin_blocks;
@@ -347,43 +359,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], k * BLOCK_K, m_tile * BLOCK_M);
           }
           tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], k * BLOCK_K, n_blk * BLOCK_N);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT ? 1u : 0u, BLOCK_M, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = make_idesc(FMT ? 1u : 0u, BLOCK_M, BLOCK_N);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tb + acc * BLOCK_N;
+      for (int k = 0; k < p.num_k_blocks; ++k) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int k = 0; k < p.num_k_blocks; ++k) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t da = make_sdesc_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
-          const uint64_t db = make_sdesc_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
+        if (elect_one()) {
+          const uint64_t da = make_sdesc_sw128(a_addr + stage * Cfg::kStageBytesA);
+          const uint64_t db = make_sdesc_sw128(b_addr + stage * Cfg::kStageBytesB);
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
             umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (k == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
@@ -462,6 +478,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       const int nb = n_blk * BLOCK_N;
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
+      if constexpr (EPI == EPI_TMA) {
+        uint8_t* stg = smem_stg + e * kStagingBytesPerWarp;
+        const int row0 = m_tile * BLOCK_M + quarter * 32;
+        uint32_t accr[32];
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        if (c_begin < c_end) tmem_ld32(t_row + c_begin * 32, accr);
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          tmem_ld_wait();
+          const int n0 = nb + c * 32;
+          float v[32];
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]) + sbias[c * 32 + i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]);
+          }
+          if (c + 1 < c_end) tmem_ld32(t_row + (c + 1) * 32, accr);
+          if (n0 < p.N) {  // warp-uniform
+            if (p.act == VDN_ACT_GELU) {
+              gelu_fast_batch<8>(v);
+              gelu_fast_batch<8>(v + 8);
+              gelu_fast_batch<8>(v + 16);
+              gelu_fast_batch<8>(v + 24);
+            } else if (p.act == VDN_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+            if (p.gamma != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= sgamma[c * 32 + i];
+            }
+            if (p.out_f32) {
+              // one 4 KB buffer: [32 rows][128 B], 128B swizzle (16-byte piece ^= row & 7) -> conflict-free 16-byte stores
+              if (elect_one()) tma_store_wait_read<0>();
+              __syncwarp();
+              uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(rowp + ((k ^ (lane & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (elect_one()) {
+                if (p.res != nullptr) tma_reduce_add_2d(&tmC, stg, n0, row0);
+                else tma_store_2d(&tmC, stg, n0, row0);
+                tma_store_commit();
+              }
+            } else {
+              // two 2 KB buffers: [32 rows][64 B], 64B swizzle (16-byte piece ^= (row >> 1) & 3)
+              uint8_t* buf = stg + (c & 1) * 2048;
+              if (elect_one()) tma_store_wait_read<1>();
+              __syncwarp();
+              uint8_t* rowp = buf + lane * 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(rowp + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(pack2<FMT>(v[8 * k], v[8 * k + 1]), pack2<FMT>(v[8 * k + 2], v[8 * k + 3]), pack2<FMT>(v[8 * k + 4], v[8 * k + 5]),
+                               pack2<FMT>(v[8 * k + 6], v[8 * k + 7]));
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (elect_one()) {
+                tma_store_2d(&tmC, buf, n0, row0);
+                tma_store_commit();
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
       uint32_t accr[32];
       ResBuf rb0, rb1;  // only live in the EPI_RES instantiation
       uint4 r2[4];
@@ -514,6 +603,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if constexpr (EPI == EPI_TMA) {
+      if (elect_one()) tma_store_wait_all();  // staging memory and the global writes must outlive the bulk copies
+      __syncwarp();
+    }
   }
 
   tc_fence_before();
@@ -528,8 +621,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int EPI, int FMT>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, EPI>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -538,38 +631,41 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int num_tiles = p.num_m_tiles * p.num_n_blocks;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N, EPI, FMT><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BLOCK_N, EPI, FMT><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }
 
 template <int EPI, int FMT>
-static int launch_gemm_bn(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, cudaStream_t stream) {
+static int launch_gemm_bn(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p,
+                          cudaStream_t stream) {
   if constexpr (EPI == EPI_HEAD) {
-    return launch_gemm<32, EPI, FMT>(tmA, tmB, p, stream);
-  } else if constexpr (EPI == EPI_PLAIN || EPI == EPI_RES) {
+    return launch_gemm<32, EPI, FMT>(tmA, tmB, tmC, p, stream);
+  } else if constexpr (EPI == EPI_PLAIN || EPI == EPI_RES || EPI == EPI_TMA) {
     switch (block_n) {
-      case 256: return launch_gemm<256, EPI, FMT>(tmA, tmB, p, stream);
-      case 128: return launch_gemm<128, EPI, FMT>(tmA, tmB, p, stream);
-      case 64: return launch_gemm<64, EPI, FMT>(tmA, tmB, p, stream);
-      default: return launch_gemm<32, EPI, FMT>(tmA, tmB, p, stream);
+      case 256: return launch_gemm<256, EPI, FMT>(tmA, tmB, tmC, p, stream);
+      case 128: return launch_gemm<128, EPI, FMT>(tmA, tmB, tmC, p, stream);
+      case 64: return launch_gemm<64, EPI, FMT>(tmA, tmB, tmC, p, stream);
+      default: return launch_gemm<32, EPI, FMT>(tmA, tmB, tmC, p, stream);
     }
   } else {
     // QKV / GEGLU / pixel-shuffle outputs are always wide (N >= 256): two tile widths suffice
-    if (block_n == 256) return launch_gemm<256, EPI, FMT>(tmA, tmB, p, stream);
-    return launch_gemm<128, EPI, FMT>(tmA, tmB, p, stream);
+    if (block_n == 256) return launch_gemm<256, EPI, FMT>(tmA, tmB, tmC, p, stream);
+    return launch_gemm<128, EPI, FMT>(tmA, tmB, tmC, p, stream);
   }
 }
 
 template <int FMT>
-static int launch_gemm_epi(int epi, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, cudaStream_t stream) {
+static int launch_gemm_epi(int epi, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p,
+                           cudaStream_t stream) {
   switch (epi) {
-    case EPI_QKV: return launch_gemm_bn<EPI_QKV, FMT>(block_n, tmA, tmB, p, stream);
-    case EPI_GEGLU: return launch_gemm_bn<EPI_GEGLU, FMT>(block_n, tmA, tmB, p, stream);
-    case EPI_PIXSHUF: return launch_gemm_bn<EPI_PIXSHUF, FMT>(block_n, tmA, tmB, p, stream);
-    case EPI_HEAD: return launch_gemm_bn<EPI_HEAD, FMT>(block_n, tmA, tmB, p, stream);
-    case EPI_RES: return launch_gemm_bn<EPI_RES, FMT>(block_n, tmA, tmB, p, stream);
-    default: return launch_gemm_bn<EPI_PLAIN, FMT>(block_n, tmA, tmB, p, stream);
+    case EPI_QKV: return launch_gemm_bn<EPI_QKV, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    case EPI_GEGLU: return launch_gemm_bn<EPI_GEGLU, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    case EPI_PIXSHUF: return launch_gemm_bn<EPI_PIXSHUF, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    case EPI_HEAD: return launch_gemm_bn<EPI_HEAD, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    case EPI_RES: return launch_gemm_bn<EPI_RES, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    case EPI_TMA: return launch_gemm_bn<EPI_TMA, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    default: return launch_gemm_bn<EPI_PLAIN, FMT>(block_n, tmA, tmB, tmC, p, stream);
   }
 }
 
@@ -620,10 +716,19 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
   else if (d->row_map == VDN_ROWMAP_QKV_SPLIT) epi = EPI_QKV;
   else if (d->row_map == VDN_ROWMAP_PIXEL_SHUFFLE) epi = EPI_PIXSHUF;
   else if (d->res != nullptr || d->res2 != nullptr || d->gamma != nullptr) epi = EPI_RES;
+  // TMA-store epilogue: plain tiles, or in-place fp32 accumulation (out += ...) as an L2 reduce-add
+  {
+    static const char* env = getenv("VDN_NO_TMA_EPI");
+    const int es = d->out_f32 ? 4 : 2;
+    const bool inplace_f32 = d->res != nullptr && d->res == d->out && d->res_f32 && d->out_f32 && d->ld_res == d->ldc;
+    if ((epi == EPI_PLAIN || epi == EPI_RES) && env == nullptr && !d->conv && d->row_map == VDN_ROWMAP_IDENTITY && d->out2 == nullptr &&
+        d->res2 == nullptr && (d->res == nullptr || inplace_f32) && (d->ldc * es) % 16 == 0)
+      epi = EPI_TMA;
+  }
   if (epi == EPI_QKV && (d->out_f32 || d->out2 == nullptr || d->res || d->gamma || d->act)) return set_error("vdn_gemm: QKV split takes bias only, 16-bit out and out2 = V^T");
   if (epi == EPI_PIXSHUF && (d->out_f32 || d->res || d->res2 || d->gamma || d->act || d->out2)) return set_error("vdn_gemm: pixel-shuffle takes bias only and a 16-bit output");
   if (epi == EPI_GEGLU && (d->gamma || d->act || d->out2 || d->res2)) return set_error("vdn_gemm: geglu takes bias only");
-  if (epi != EPI_PLAIN && epi != EPI_RES && epi != EPI_HEAD && d->N < 256) return set_error("vdn_gemm: QKV / GEGLU / pixel-shuffle epilogues need N >= 256");
+  if (epi != EPI_PLAIN && epi != EPI_RES && epi != EPI_HEAD && epi != EPI_TMA && d->N < 256) return set_error("vdn_gemm: QKV / GEGLU / pixel-shuffle epilogues need N >= 256");
 
   // BLOCK_N: largest tile that does not waste more than necessary
   int block_n;
@@ -675,5 +780,13 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)block_n};
     if (make_tensor_map(&tmB, d->w, fmt, 2, dims, strides, box)) return 1;
   }
-  return fmt ? launch_gemm_epi<1>(epi, block_n, tmA, tmB, p, stream) : launch_gemm_epi<0>(epi, block_n, tmA, tmB, p, stream);
+  CUtensorMap tmC = tmB;  // placeholder unless the TMA epilogue is used
+  if (epi == EPI_TMA) {
+    const int es = d->out_f32 ? 4 : 2;
+    const uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+    const uint64_t strides[1] = {(uint64_t)d->ldc * es};
+    const uint32_t box[2] = {32u, 32u};
+    if (make_tensor_map_ex(&tmC, d->out, d->out_f32 ? 2 : fmt, d->out_f32 ? 128 : 64, 2, dims, strides, box)) return 1;
+  }
+  return fmt ? launch_gemm_epi<1>(epi, block_n, tmA, tmB, tmC, p, stream) : launch_gemm_epi<0>(epi, block_n, tmA, tmB, tmC, p, stream);
 }

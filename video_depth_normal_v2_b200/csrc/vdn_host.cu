@@ -51,6 +51,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tensor_map(CUtensorMap* out, const void* base, int fmt, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box) {
+  return make_tensor_map_ex(out, base, fmt, 128, rank, dims, strides_bytes, box);
+}
+
+int make_tensor_map_ex(CUtensorMap* out, const void* base, int dtype, int swizzle_bytes, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error("cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdims[5];
@@ -68,9 +73,11 @@ int make_tensor_map(CUtensorMap* out, const void* base, int fmt, int rank, const
     if (strides_bytes[i] % 16 != 0) return set_error("tensor map: global stride not a multiple of 16 bytes");
   }
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_error("tensor map: base not 16-byte aligned");
-  CUresult r = fn(out, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims,
-                  gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return 0;
 }

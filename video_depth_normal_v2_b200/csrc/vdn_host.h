@@ -15,4 +15,7 @@ int get_operand_format();
 // Encode a tiled, 128B-swizzled tensor map for a 16-bit tensor. dims/box innermost first; strides (bytes) for dims 1..rank-1.
 int make_tensor_map(CUtensorMap* out, const void* base, int fmt, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
+// General form: dtype 0 = fp16, 1 = bf16, 2 = fp32; swizzle_bytes 0 / 32 / 64 / 128.
+int make_tensor_map_ex(CUtensorMap* out, const void* base, int dtype, int swizzle_bytes, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box);
 }  // namespace vdn

@@ -145,11 +145,11 @@ def _fusion(rf, B, H, W, Ho, Wo, x0, x0_relu=None, x1=None, x1_relu=None, relu_c
     lo = _empty((B, H, W, Fe), od, dev)
     ops.gemm(o, rf["out_conv"]["w"], lo, M=B * H * W, N=Fe, K=Fe, bias=rf["out_conv"]["b"])
     up = _empty((B, Ho, Wo, Fe), od, dev)
-    ops.bilinear_nhwc(lo, up, B, H, W, Ho, Wo, Fe)
     if relu_copy:
         upr = _empty((B, Ho, Wo, Fe), od, dev)
-        ops.relu16(up, upr)
+        ops.bilinear_nhwc2(lo, up, upr, B, H, W, Ho, Wo, Fe)
         return up, upr
+    ops.bilinear_nhwc(lo, up, B, H, W, Ho, Wo, Fe)
     return up
 
 

@@ -208,6 +208,14 @@ def bilinear_nhwc(x, out, B, H, W, Ho, Wo, C_, relu_out=False):
     return out
 
 
+def bilinear_nhwc2(x, out, out_relu, B, H, W, Ho, Wo, C_):
+    """out = bilinear(x), out_relu = relu(out) in one pass."""
+    od = operand_dtype()
+    _check(_run("bilinear_nhwc", "hbm", 2.0 * B * C_ * (H * W + 2 * Ho * Wo), lib().vdn_bilinear_nhwc2, _ptr(x, od, "x"), _ptr(out, od, "out"),
+                _ptr(out_relu, od, "out_relu"), B, H, W, Ho, Wo, C_, _stream()), "vdn_bilinear_nhwc2")
+    return out, out_relu
+
+
 def bilinear_f32(x, out, N, H, W, Ho, Wo, relu=False):
     _check(_run("bilinear_f32", "hbm", 4.0 * N * (H * W + Ho * Wo), lib().vdn_bilinear_f32, _ptr(x, torch.float32, "x"), _ptr(out, torch.float32, "out"),
                 N, H, W, Ho, Wo, 1 if relu else 0, _stream()), "vdn_bilinear_f32")
