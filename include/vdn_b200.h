@@ -125,6 +125,8 @@ int vdn_cast_f32_to_16(const float* x, void* out, int64_t n, void* stream);
 /* ---- window alignment (video_depth.py:118-154, utils/util.py:40-74) ------------------------------- */
 /* sums[0..4] = (sum p*p, sum p, n, sum p*t, sum t) over n elements, accumulated in fp64 on device */
 int vdn_lsq_sums(const float* pred, const float* target, int64_t n, double* sums5, void* stream);
+/* scale_shift[0..1] = solution of the 2x2 normal equations built from sums5 (identity (1, 0) when singular; utils/util.py:54-60) */
+int vdn_lsq_solve(const double* sums5, float* scale_shift, void* stream);
 /* out = max(x*scale + shift, 0) */
 int vdn_affine_clamp(const float* x, float* out, int64_t n, const float* scale_shift, void* stream);
 /* out = pre*(1-w) + max(post*scale+shift,0)*w */

@@ -1,0 +1,52 @@
+"""`-m gpu`, needs >= 2 GPUs (skipped otherwise): the NCCL window-sharded infer_video_depth against the single-GPU result."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    from oracle.init_recipe import make_state_dict
+    from video_depth_normal_v2_b200 import VideoDepthAnything
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        m = VideoDepthAnything(encoder="vits", features=64, out_channels=[48, 96, 192, 384]).cuda().eval()
+        m.load_state_dict(make_state_dict("vda", "vits", 0))
+        rng = np.random.RandomState(3)
+        frames = rng.randint(0, 255, (120, 56, 70, 3), dtype=np.uint8)
+        out, _ = m.infer_video_depth(frames, 30, input_size=56, device="cuda", gather="all")
+        np.save(f"{out_path}.{rank}.npy", out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_infer_video_depth_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle.init_recipe import make_state_dict
+    from video_depth_normal_v2_b200 import VideoDepthAnything
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "o")
+        mp.spawn(_worker, args=(2, port, path), nprocs=2, join=True)
+        a, b = np.load(f"{path}.0.npy"), np.load(f"{path}.1.npy")
+    assert np.array_equal(a, b)
+    m = VideoDepthAnything(encoder="vits", features=64, out_channels=[48, 96, 192, 384]).cuda().eval()
+    m.load_state_dict(make_state_dict("vda", "vits", 0))
+    frames = np.random.RandomState(3).randint(0, 255, (120, 56, 70, 3), dtype=np.uint8)
+    ref, _ = m.infer_video_depth(frames, 30, input_size=56, device="cuda")
+    no_reuse, _ = m.infer_video_depth(frames, 30, input_size=56, device="cuda", reuse_features=False)
+    # same kernels on the same inputs: only the fp64 atomics of the five LSQ sums may reorder
+    assert np.abs(a - ref).max() <= 1e-5 * max(1.0, float(np.abs(ref).max())), float(np.abs(a - ref).max())
+    assert np.abs(no_reuse - ref).max() <= 1e-5 * max(1.0, float(np.abs(ref).max()))

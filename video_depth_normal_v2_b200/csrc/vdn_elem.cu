@@ -391,6 +391,19 @@ __global__ void __launch_bounds__(256) lsq_sums_kernel(const float* __restrict__
   if (blockIdx.x == 0 && threadIdx.x == 4) atomicAdd(&sums[2], (double)n);
 }
 
+// 2x2 normal equations of the scale/shift fit (utils/util.py:40-62) solved on the device: no host round trip per window
+__global__ void lsq_solve_kernel(const double* __restrict__ sums, float* __restrict__ ss) {
+  const double a00 = sums[0], a01 = sums[1], a11 = sums[2], b0 = sums[3], b1 = sums[4];
+  const double det = a00 * a11 - a01 * a01;
+  double x0 = 1.0, x1 = 0.0;
+  if (det != 0.0) {
+    x0 = (a11 * b0 - a01 * b1) / det;
+    x1 = (-a01 * b0 + a00 * b1) / det;
+  }
+  ss[0] = (float)x0;
+  ss[1] = (float)x1;
+}
+
 __global__ void __launch_bounds__(256) affine_clamp_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, const float* __restrict__ ss) {
   const float sc = ss[0], sh = ss[1];
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
@@ -568,6 +581,14 @@ extern "C" int vdn_lsq_sums(const float* pred, const float* target, int64_t n, d
   lsq_sums_kernel<<<grid_for(n, 256 * 8, 4), 256, 0, stream>>>(pred, target, n, sums5);
   count_launch();
   return check_launch("lsq_sums_kernel");
+}
+
+extern "C" int vdn_lsq_solve(const double* sums5, float* scale_shift, void* stream_v) {
+  VDN_STREAM;
+  if (!sums5 || !scale_shift) return set_error("vdn_lsq_solve: null pointer");
+  lsq_solve_kernel<<<1, 1, 0, stream>>>(sums5, scale_shift);
+  count_launch();
+  return check_launch("lsq_solve_kernel");
 }
 
 extern "C" int vdn_affine_clamp(const float* x, float* out, int64_t n, const float* scale_shift, void* stream_v) {

@@ -370,9 +370,26 @@ class VideoDepthAnything(_PackedModule):
         # F.interpolate(depth, (H, W), align_corners=True) is the identity here (H == 14*ph) and the head's output is already >= 0
         return depth.view(B, T, H, W)
 
+    # --- the two halves of forward(), exposed for the long-video driver: the encoder is per-frame (dinov2.py:212-321 has no
+    # cross-frame op), so the features of the 10 key frames a window shares with its predecessor are computed once.
+    @torch.no_grad()
+    def encode_frames(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """x (F, 3, H, W) fp32 -> 4 x [F*ph*pw, C] tapped, final-norm'ed patch tokens (frame-major)."""
+        w = self._weights()
+        return encoder_forward(w["enc"], x.to(device=self._dev, dtype=torch.float32))
+
+    @torch.no_grad()
+    def head_from_features(self, feats: List[torch.Tensor], T: int, ph: int, pw: int) -> torch.Tensor:
+        """4 x [T*ph*pw, C] -> depth (T, 14*ph, 14*pw) fp32 (one video, T <= 32 frames)."""
+        w = self._weights()
+        if T > 32:
+            raise RuntimeError("temporal attention supports at most 32 frames per window")
+        return head_forward(w["head"], feats, T, ph, pw, T)
+
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def infer_video_depth(self, frames, target_fps, input_size=518, device="cuda", fp32=False):
-        """Drop-in for video_depth.py:67-156.  frames: np.uint8 (N, H, W, 3) RGB -> (np.float32 (N, H, W), target_fps)."""
+    def infer_video_depth(self, frames, target_fps, input_size=518, device="cuda", fp32=False, **kw):
+        """Drop-in for video_depth.py:67-156.  frames: np.uint8 (N, H, W, 3) RGB -> (np.float32 (N, H, W), target_fps).
+        Extra keyword arguments (``reuse_features``, ``group``, ``gather``, ``preprocessed``) go to video.infer_video_depth."""
         from .video import infer_video_depth
-        return infer_video_depth(self, frames, target_fps, input_size=input_size, device=device, fp32=fp32)
+        return infer_video_depth(self, frames, target_fps, input_size=input_size, device=device, fp32=fp32, **kw)

@@ -239,6 +239,11 @@ def lsq_sums(pred, target, sums5):
     return sums5
 
 
+def lsq_solve(sums5, scale_shift):
+    _check(lib().vdn_lsq_solve(_ptr(sums5, torch.float64, "sums"), _ptr(scale_shift, torch.float32, "ss"), _stream()), "vdn_lsq_solve")
+    return scale_shift
+
+
 def affine_clamp(x, out, scale_shift):
     _check(lib().vdn_affine_clamp(_ptr(x, torch.float32, "x"), _ptr(out, torch.float32, "out"), x.numel(), _ptr(scale_shift, torch.float32, "ss"),
                                   _stream()), "vdn_affine_clamp")
