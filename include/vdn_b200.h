@@ -135,6 +135,16 @@ int vdn_crossfade(const float* pre, const float* post, float* out, int64_t n, co
 /* ---- depth -> normals (utils/normal_utils.py:4-52): reflect-pad Sobel/8, n = normalize(-Ix,-Iy,1) ------- */
 int vdn_sobel_normals(const float* depth, float* normals, int32_t N, int32_t H, int32_t W, int32_t channels_out, void* stream);
 
+/* ---- v5 depth-refinement model, full-resolution pieces (models/video_depth_model_v5.py:160-192) -------------- */
+/* per frame: median (torch.quantile 0.5 semantics; optional output) and scale = exp(tanh(median * inv_max * w + b))
+   = GlobalScaleHead (:63-87) of the frame divided by max_depth */
+int vdn_frame_median_scale(const float* x, float* median, float* scale, int32_t N, int64_t n_per_frame, float inv_max, float w, float b, void* stream);
+/* r [N,h,w] (raw depth resized) -> x [N,3,h,w] = (r*scale/max, normal_x, normal_y) (:169-178, utils/normal_utils.py:4-52) */
+int vdn_v5_net_input(const float* r, const float* scale, float* x, int32_t N, int32_t h, int32_t w, float inv_max, void* stream);
+/* out = (din/max*scale + relu(bilinear(o [N,h,w] -> [N,H,W])) * ws + bs) * max   (:183-192) */
+int vdn_v5_residual(const float* din, const float* o, const float* scale, float* out, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, float ws,
+                    float bs, float max_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

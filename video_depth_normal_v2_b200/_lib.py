@@ -55,6 +55,9 @@ SIGNATURES = {
     "vdn_affine_clamp": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "vdn_crossfade": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p]),
     "vdn_sobel_normals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vdn_frame_median_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_float, c_void_p]),
+    "vdn_v5_net_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "vdn_v5_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
 }
 
 _lib = None

@@ -393,3 +393,63 @@ class VideoDepthAnything(_PackedModule):
         Extra keyword arguments (``reuse_features``, ``group``, ``gather``, ``preprocessed``) go to video.infer_video_depth."""
         from .video import infer_video_depth
         return infer_video_depth(self, frames, target_fps, input_size=input_size, device=device, fp32=fp32, **kw)
+
+
+class VideoDepthRefinerV5(_PackedModule):
+    """Drop-in for models/video_depth_model_v5.py:128 ``VideoDepthAnything`` (the depth-sequence refinement model):
+    forward(input_depth (B, S, H, W) in [0, max_depth]) -> refined depth (B, S, H, W).  use_residual=True, input_normal=True
+    (the reference defaults) are the supported configuration.  The dense part (DINOv2 + temporal DPT head at 224x224) runs on
+    the same kernels as VideoDepthAnything; the full-resolution part is three bandwidth-bound kernels (csrc/vdn_v5.cu)."""
+
+    NET_SIZE = 224  # models/video_depth_model_v5.py:169
+
+    def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False, use_clstoken=False, num_frames=32,
+                 max_depth=65535, pe="ape", use_residual=True, input_normal=True):
+        super().__init__()
+        if encoder not in ENCODER_CONFIGS:
+            raise KeyError(encoder)
+        if use_bn or use_clstoken:
+            raise NotImplementedError("use_bn / use_clstoken are never exercised by the reference (SURVEY.md §8b)")
+        if pe != "ape":
+            raise NotImplementedError("pe='rope' is on the roadmap (SURVEY.md §8f rank 3)")
+        if not use_residual or not input_normal:
+            raise NotImplementedError("only use_residual=True, input_normal=True (the reference defaults) are built")
+        self.encoder, self.num_frames, self.max_depth = encoder, num_frames, float(max_depth)
+        self.use_residual, self.input_normal = use_residual, input_normal
+        self.cfg = dict(ENCODER_CONFIGS[encoder], features=features, out_channels=list(out_channels))
+        self.intermediate_layer_idx = {k: v["taps"] for k, v in ENCODER_CONFIGS.items()}
+
+    def _expected_shapes(self):
+        s = _encoder_shapes("pretrained.", self.cfg)
+        s["scale_head.feat.1.weight"], s["scale_head.feat.1.bias"] = (1, 1, 1, 1), (1,)
+        s.update(_head_shapes("temporal_head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], True))
+        s["shift_head.0.weight"], s["shift_head.0.bias"] = (1, 1, 1, 1), (1,)
+        return s
+
+    def _pack(self, sd, dev, dt):
+        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "temporal_head.", self.cfg, dev, dt, True),
+                "scale_w": float(sd["scale_head.feat.1.weight"].reshape(())), "scale_b": float(sd["scale_head.feat.1.bias"].reshape(())),
+                "shift_w": float(sd["shift_head.0.weight"].reshape(())), "shift_b": float(sd["shift_head.0.bias"].reshape(()))}
+
+    @torch.no_grad()
+    def forward(self, input_depth: torch.Tensor) -> torch.Tensor:
+        if input_depth.dim() != 4:
+            raise RuntimeError(f"expected (B, S, H, W), got {tuple(input_depth.shape)}")
+        w = self._weights()
+        B, S, H, W = input_depth.shape
+        if S > 32:
+            raise RuntimeError("temporal attention supports at most 32 frames per window")
+        dev, n, hw = self._dev, B * S, self.NET_SIZE
+        din = input_depth.to(device=dev, dtype=torch.float32).contiguous()
+        inv_max = 1.0 / self.max_depth
+        scale = _empty((n,), torch.float32, dev)
+        ops.frame_median_scale(din, scale, H * W, inv_max, w["scale_w"], w["scale_b"])          # :164-167
+        r = _empty((n, hw, hw), torch.float32, dev)
+        ops.bilinear_f32(din.view(n, H, W), r, n, H, W, hw, hw)                                  # :169 (scale commutes with the resize)
+        x = _empty((n, 3, hw, hw), torch.float32, dev)
+        ops.v5_net_input(r, scale, x, n, hw, hw, inv_max)                                        # :173-178
+        feats = encoder_forward(w["enc"], x)
+        o = head_forward(w["head"], feats, n, hw // 14, hw // 14, S)  # temporal modules mix the S frames of each of the B sequences
+        out = _empty((B, S, H, W), torch.float32, dev)
+        ops.v5_residual(din, o, scale, out, n, H, W, hw, hw, w["shift_w"], w["shift_b"], self.max_depth)  # :183-192
+        return out

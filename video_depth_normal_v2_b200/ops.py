@@ -260,3 +260,23 @@ def sobel_normals(depth, normals, N, H, W, channels_out=3):
     _check(lib().vdn_sobel_normals(_ptr(depth, torch.float32, "depth"), _ptr(normals, torch.float32, "normals"), N, H, W, channels_out, _stream()),
            "vdn_sobel_normals")
     return normals
+
+
+def frame_median_scale(x, scale, n_per_frame: int, inv_max: float, w: float, b: float, median=None):
+    N = x.numel() // n_per_frame
+    _check(_run("frame_median_scale", "hbm", 4.0 * x.numel(), lib().vdn_frame_median_scale, _ptr(x, torch.float32, "x"), _ptr(median, torch.float32, "median"),
+                _ptr(scale, torch.float32, "scale"), N, n_per_frame, float(inv_max), float(w), float(b), _stream()), "vdn_frame_median_scale")
+    return scale
+
+
+def v5_net_input(r, scale, x, N, h, w, inv_max: float):
+    _check(_run("v5_net_input", "hbm", 16.0 * N * h * w, lib().vdn_v5_net_input, _ptr(r, torch.float32, "r"), _ptr(scale, torch.float32, "scale"),
+                _ptr(x, torch.float32, "x"), N, h, w, float(inv_max), _stream()), "vdn_v5_net_input")
+    return x
+
+
+def v5_residual(din, o, scale, out, N, H, W, h, w, ws: float, bs: float, max_depth: float):
+    _check(_run("v5_residual", "hbm", 8.0 * N * H * W + 4.0 * N * h * w, lib().vdn_v5_residual, _ptr(din, torch.float32, "din"), _ptr(o, torch.float32, "o"),
+                _ptr(scale, torch.float32, "scale"), _ptr(out, torch.float32, "out"), N, H, W, h, w, float(ws), float(bs), float(max_depth), _stream()),
+           "vdn_v5_residual")
+    return out
