@@ -18,6 +18,9 @@ Recipe (stated, applied identically to every side of a comparison):
   * last 1x1 conv (``output_conv2.2``): |w|, bias 0.05 -> strictly positive depth, so relative
     errors are well defined.
   * v5 ``ZeroConv``s: normal(0, 0.5) (reference zero, models/video_depth_model_v5.py:55-61).
+  * DA2 memory block: attention / MLP linears default-linear init, embeddings trunc-normal(0.02) as the reference
+    (memory_block.py:52-61), ConvNeXt layer scale ``gamma`` U(0.5, 1.0) (reference 1e-6, which would make the
+    fuser an identity map, sam2/modeling/memory_encoder.py:86-90).
 """
 from __future__ import annotations
 
@@ -153,15 +156,51 @@ def _motion_modules(sd, g, prefix, cfg):
         _default_linear(sd, g, p + "proj_out", C, C)  # de-zeroed
 
 
+def _memory_block(sd, g, prefix, cfg, max_len=6, layers=4):
+    """depth_anything_v2/memory_block.py:13-82 (MemoryAttention x4, MemoryEncoder with two MaskDownSamplers and a 2-layer fuser)."""
+    C = cfg["embed_dim"]
+    sd[prefix + "curr_pos_enc"] = g.trunc_normal((1, 1, C), 0.02)
+    sd[prefix + "maskmem_tpos_enc"] = g.trunc_normal((1, max_len, C), 0.02)
+    sd[prefix + "no_mem_embed"] = g.trunc_normal((1, 1, C), 0.02)
+    for l in range(layers):
+        p = f"{prefix}memory_attention.layers.{l}."
+        for att in ("self_attn", "cross_attn_image"):
+            for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                _default_linear(sd, g, f"{p}{att}.{proj}", C, C)
+        _default_linear(sd, g, p + "linear1", 2 * C, C)
+        _default_linear(sd, g, p + "linear2", C, 2 * C)
+        for n in ("norm1", "norm2", "norm3"):
+            _norm_affine(sd, g, p + n, C)
+    _norm_affine(sd, g, prefix + "memory_attention.norm", C)
+    me = prefix + "memory_encoder."
+    _conv(sd, g, me + "mask_downsampler.0.encoder.0", 4, 1, 3)
+    _norm_affine(sd, g, me + "mask_downsampler.0.encoder.1", 4)
+    _conv(sd, g, me + "mask_downsampler.0.encoder.3", 1, 4, 1)
+    _conv(sd, g, me + "mask_downsampler.1.encoder.0", 49, 1, 7)
+    _norm_affine(sd, g, me + "mask_downsampler.1.encoder.1", 49)
+    _conv(sd, g, me + "mask_downsampler.1.encoder.3", 1, 49, 1)
+    _conv(sd, g, me + "pix_feat_proj", C, C, 1)
+    for l in range(2):
+        p = f"{me}fuser.layers.{l}."
+        sd[p + "gamma"] = g.uniform((C,), 0.5, 1.0)
+        b = 1.0 / math.sqrt(49)
+        sd[p + "dwconv.weight"] = g.uniform((C, 1, 7, 7), -b, b)
+        sd[p + "dwconv.bias"] = g.uniform((C,), -b, b)
+        _norm_affine(sd, g, p + "norm", C)
+        _default_linear(sd, g, p + "pwconv1", 4 * C, C)
+        _default_linear(sd, g, p + "pwconv2", C, 4 * C)
+
+
 def make_state_dict(model: str, encoder: str, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
-    """model in {'vda', 'v5'}; returns fp32 CPU tensors under the reference's key names.
+    """model in {'vda', 'v5', 'da2'}; returns fp32 CPU tensors under the reference's key names.
 
     'vda' = video_depth_anything/video_depth.py:35-56 (prefixes ``pretrained.`` / ``head.``)
     'v5'  = models/video_depth_model_v5.py:128-158 (``pretrained.`` / ``temporal_head.`` /
             ``scale_head.feat.1.`` / ``shift_head.0.``)
+    'da2' = depth_anything_v2/depth_anything_v2.py:12-43 (``pretrained.`` / ``memory_block.`` / ``depth_head.``)
     """
     cfg = ENCODERS[encoder]
-    g = _Gen(seed * 7919 + {"vda": 1, "v5": 2}[model])
+    g = _Gen(seed * 7919 + {"vda": 1, "v5": 2, "da2": 3}[model])
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     _encoder(sd, g, "pretrained.", cfg)
     if model == "vda":
@@ -174,6 +213,9 @@ def make_state_dict(model: str, encoder: str, seed: int = 0) -> "OrderedDict[str
         _motion_modules(sd, g, "temporal_head.", cfg)
         sd["shift_head.0.weight"] = g.normal((1, 1, 1, 1), 0.5)
         sd["shift_head.0.bias"] = g.normal((1,), 0.5)
+    elif model == "da2":
+        _memory_block(sd, g, "memory_block.", cfg)
+        _dpt_head(sd, g, "depth_head.", cfg)
     else:
         raise ValueError(model)
     return sd

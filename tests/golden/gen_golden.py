@@ -30,6 +30,8 @@ VDA_CASES = [
     ("vda_vitl_t2_56x70", "vitl", 2, 56, 70, 2, 1),
 ]
 V5_CASES = [("v5_vits_s4_60x80", "vits", 4, 60, 80, 3)]
+# (name, encoder, batch, H(=W), calls, seed, stride): DepthAnythingV2 is stateful -> a sequence of forward() calls on one model
+DA2_CASES = [("da2_vits_b2_70_calls8", "vits", 2, 70, 8, 5, 1), ("da2_vits_b1_518_calls2", "vits", 1, 518, 2, 6, 4), ("da2_vitl_b1_70_calls3", "vitl", 1, 70, 3, 7, 1)]
 VIDEO_CASES = [("video_vits_n50_56x70", "vits", 50, 56, 70, 4)]
 SCHEDULE_NS = [1, 5, 21, 22, 23, 32, 44, 45, 50, 60, 100]
 
@@ -45,9 +47,30 @@ def video_frames(n, h, w, seed):
     return np.stack(frames)
 
 
+def da2_inputs(B, H, calls, seed):
+    """The i-th call's input: seeded N(0,1) frames (post-normalisation), a different seed per call."""
+    return [make_input("rgb", (B, 1, 3, H, H), seed * 100 + i)[:, 0] for i in range(calls)]
+
+
+def gen_da2():
+    for name, enc, B, H, calls, seed, stride in DA2_CASES:
+        sd = make_state_dict("da2", enc, seed)
+        m = RL.load_da2(enc, sd)
+        outs = [m(x)[:, ::stride, ::stride].numpy() for x in da2_inputs(B, H, calls, seed)]
+        m.clear_memory()
+        again = m(da2_inputs(B, H, calls, seed)[0])[:, ::stride, ::stride].numpy()  # clear_memory() really resets the state
+        assert np.array_equal(again, outs[0])
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), depth=np.stack(outs), meta=np.array([B, H, calls, seed, stride]))
+        print(name, np.stack(outs).shape, float(np.stack(outs).mean()), "memory effect", float(np.abs(outs[-1] - outs[0]).mean()))
+        del m
+
+
 def main():
     assert RL.available(), "reference not present"
     torch.set_grad_enabled(False)
+    if len(sys.argv) > 1 and sys.argv[1] == "da2":
+        return gen_da2()
+    gen_da2()
     for name, enc, T, H, W, seed, stride in VDA_CASES:
         sd = make_state_dict("vda", enc, seed)
         m = RL.load_vda(enc, sd)

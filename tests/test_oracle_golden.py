@@ -82,3 +82,33 @@ def test_operand_rounding_budget():
     assert e16["abs_rel"] < 1e-3 and e16["max_rel"] < 1e-2, e16
     assert ebf["abs_rel"] > e16["abs_rel"]
     print("fp16", e16, "bf16", ebf)
+
+
+# ------------------------------------------------------------------------------------------ a11: DepthAnythingV2 + memory block
+def _da2_inputs(B, H, calls, seed):
+    return [make_input("rgb", (B, 1, 3, H, H), seed * 100 + i)[:, 0] for i in range(calls)]
+
+
+@pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl")])
+def test_da2_stateful_forward_matches_reference(name, enc):
+    """A sequence of forward() calls on one model (memory bank filling up, then wrapping at 6 entries)."""
+    g = _load(name)
+    B, H, calls, seed, stride = [int(v) for v in g["meta"]]
+    sd = make_state_dict("da2", enc, seed)
+    bank = []
+    for i, x in enumerate(_da2_inputs(B, H, calls, seed)):
+        y = O.da2_forward(sd, x, enc, bank)
+        ref = torch.from_numpy(g["depth"][i])
+        assert (y[:, ::stride, ::stride] - ref).abs().max() / ref.abs().max() < 2e-4, (name, i)
+        assert len(bank) == min(i + 1, 6)
+
+
+def test_da2_memory_changes_the_output():
+    """Teeth for the parity tests: the same frame with an empty and with a filled bank gives measurably different depth."""
+    sd = make_state_dict("da2", "vits", 5)
+    xs = _da2_inputs(1, 70, 3, 5)
+    bank = []
+    first = O.da2_forward(sd, xs[0], "vits", bank)
+    O.da2_forward(sd, xs[1], "vits", bank)
+    with_mem = O.da2_forward(sd, xs[0], "vits", bank)
+    assert float((with_mem - first).abs().mean() / first.abs().mean()) > 2e-3  # twice the AbsRel parity tolerance
