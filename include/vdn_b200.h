@@ -40,7 +40,9 @@ enum {
   VDN_ROWMAP_PIXEL_SHUFFLE = 1, /* ConvTranspose k==stride: rm0=H_in rm1=W_in rm2=stride rm3=C_out; N = stride^2*C_out, col=(i*s+j)*C_out+co */
   VDN_ROWMAP_TEMPORAL = 2,      /* rows (b*D+d)*T+f -> (b*T+f)*D+d : rm0=T rm1=D (applies to out, res, res2, out2) */
   VDN_ROWMAP_PATCH_TOKENS = 3,  /* rows b*P+p -> b*(P+1)+1+p, residual row 1+p (pos_embed) : rm0=P */
-  VDN_ROWMAP_QKV_SPLIT = 4      /* cols [0,2C) -> out[row, col]; cols [2C,3C) -> out2 = V^T[(b*heads+h)*64+d][t] : rm0=tokens rm1=ld of V^T rm2=C */
+  VDN_ROWMAP_QKV_SPLIT = 4      /* cols [0,split) -> out[row', col]; cols [split,N) -> out2 = V^T[(b*heads+h)*64+d][t'] : rm0=tokens per batch of the
+                                   rows, rm1=ld of V^T, rm2=C; split = qkv_split (0 -> 2C).  row' = b*qkv_tokens_out + t', t' = qkv_token_offset + t
+                                   (qkv_tokens_out 0 -> rm0): lets a [k|v] projection of new memory tokens land in slot s of a per-layer KV cache */
 };
 
 typedef struct vdn_gemm_desc {
@@ -70,6 +72,7 @@ typedef struct vdn_gemm_desc {
   int32_t rm0, rm1, rm2, rm3;
   const float* head_w; /* if non-NULL (N <= 32): out_f32[row] = relu(sum_j relu(acc_j+bias_j) * head_w[j] + head_b) */
   float head_b;
+  int32_t qkv_split, qkv_tokens_out, qkv_token_offset; /* VDN_ROWMAP_QKV_SPLIT extensions (0 = defaults) */
 } vdn_gemm_desc;
 
 int vdn_gemm(const vdn_gemm_desc* d, void* stream);
@@ -82,6 +85,10 @@ int vdn_gemm(const vdn_gemm_desc* d, void* stream);
  * out: [B*tokens, C] 16-bit                                                                              */
 int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens,
                    int32_t heads, void* stream);
+/* general form: separate q [B, tokens_q, ld_q] and k [B, tokens_kv, ld_k] buffers (element strides), V^T [B*heads, 64, ld_vT];
+   cross-attention to a memory bank (sam2/modeling/sam/transformer.py:275-311 after the projections and RoPE) */
+int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_stride, const void* k, int64_t ld_k, int64_t k_batch_stride, const void* vT,
+                      int64_t ld_vT, void* out, int32_t B, int32_t tokens_q, int32_t tokens_kv, int32_t heads, void* stream);
 
 /* ---- temporal attention over T frames per (pixel, head) ----------------------------------------
  * Replaces CrossAttention._attention (motion_module/attention.py:182-211) as called from
@@ -144,6 +151,25 @@ int vdn_v5_net_input(const float* r, const float* scale, float* x, int32_t N, in
 /* out = (din/max*scale + relu(bilinear(o [N,h,w] -> [N,H,W])) * ws + bs) * max   (:183-192) */
 int vdn_v5_residual(const float* din, const float* o, const float* scale, float* out, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, float ws,
                     float bs, float max_depth, void* stream);
+
+/* ---- DepthAnythingV2 memory block, bandwidth-bound pieces (depth_anything_v2/memory_block.py, sam2/modeling/*) ---- */
+/* axial RoPE in place on `heads` 64-wide heads starting at column col0 of 16-bit rows [rows, ld]; row r sits at grid position r % P;
+   cos_sin [P, 64] fp32 = cos[32] | sin[32] per position (sam2/modeling/position_encoding.py:186-239) */
+int vdn_rope2d(void* x, int64_t rows, int64_t ld, int32_t col0, int32_t heads, const float* cos_sin, int32_t P, int64_t rows_per_batch,
+               int64_t batch_pitch, void* stream); /* rows_per_batch consecutive rows per batch, batches batch_pitch rows apart (0 -> dense) */
+/* out_f32[r, c] = x[r, c] + alpha * vec[c]   (x fp32 or 16-bit; in place allowed for fp32) */
+int vdn_add_rowvec(const void* x, int32_t x_f32, const float* vec, float alpha, float* out, int64_t rows, int32_t C, void* stream);
+/* x[r, :] += m[r] */
+int vdn_add_rowscalar(float* x, const float* m, int64_t rows, int32_t C, void* stream);
+/* ConvNeXt front half: depthwise 7x7 (pad 3, w [49, C] tap-major) + LayerNorm2d over channels; NHWC fp32 -> 16-bit [B*H*W, C]
+   (sam2/modeling/memory_encoder.py:96-99) */
+int vdn_dwconv7_ln(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out, int32_t B, int32_t H, int32_t W,
+                   int32_t C, float eps, void* stream);
+/* MaskDownSampler stages on the 1-channel map (memory_encoder.py:17-60 as configured at memory_block.py:68-71):
+   1: sigmoid -> conv3x3/s2/p1 (1->4) -> LN2d -> GELU -> 1x1; params = w0[4][9] b0[4] lnw[4] lnb[4] w1[4] b1      out [B, ceil(H/2), ceil(W/2)]
+   2: conv7x7/s7 (1->49) -> LN2d -> GELU -> 1x1;             params = w0[49][49] b0[49] lnw[49] lnb[49] w1[49] b1 out [B, Hi/7, Wi/7] */
+int vdn_mask_down1(const float* depth, const float* params, float* out, int32_t B, int32_t H, int32_t W, void* stream);
+int vdn_mask_down2(const float* in, const float* params, float* out, int32_t B, int32_t Hi, int32_t Wi, void* stream);
 
 #ifdef __cplusplus
 }

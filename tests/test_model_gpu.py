@@ -169,3 +169,55 @@ def test_frame_median_matches_torch_quantile(vdn):
         ref = torch.quantile(x.cpu(), 0.5, dim=-1)
         assert torch.equal(med.cpu(), ref) or float((med.cpu() - ref).abs().max()) <= 1e-6 * float(ref.abs().max()), (n, med, ref)
         assert torch.allclose(sc.cpu(), torch.exp(torch.tanh(ref * 0.3 - 0.1)), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ a11: DepthAnythingV2 + memory block
+def _da2_inputs(B, H, calls, seed):
+    return [make_input("rgb", (B, 1, 3, H, H), seed * 100 + i)[:, 0] for i in range(calls)]
+
+
+@pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl")])
+def test_da2_stateful_forward_matches_reference_golden(vdn, name, enc):
+    """A sequence of forward() calls on one model against the live reference's outputs: empty bank (constant cross-attention
+    term), filling bank (cross-attention over 1..6 cached entries) and the ring wrap after 6 entries."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    B, H, calls, seed, stride = [int(v) for v in g["meta"]]
+    cfg = ENCODERS[enc]
+    m = vdn.DepthAnythingV2(encoder=enc, features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
+    m.load_state_dict(make_state_dict("da2", enc, seed))
+    xs = _da2_inputs(B, H, calls, seed)
+    for i, x in enumerate(xs):
+        y = m(x.cuda())
+        assert y.shape == (B, H, H) and y.dtype == torch.float32
+        _check(f"{name} call {i}", y[:, ::stride, ::stride], torch.from_numpy(g["depth"][i]))
+    m.clear_memory()
+    y0 = m(xs[0].cuda())
+    _check(f"{name} after clear_memory", y0[:, ::stride, ::stride], torch.from_numpy(g["depth"][0]))
+
+
+def test_da2_batch16_vitl_518_matches_oracle(vdn):
+    """BASELINE configs[1] shape (ViT-L, 518x518), batch reduced to 2 for the fp32 oracle on the GPU; two calls (empty / one entry)."""
+    enc = "vitl"
+    cfg = ENCODERS[enc]
+    sd = make_state_dict("da2", enc, 11)
+    m = vdn.DepthAnythingV2(encoder=enc, features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
+    m.load_state_dict(sd)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    bank = []
+    for i, x in enumerate(_da2_inputs(2, 518, 2, 11)):
+        y = m(x.cuda())
+        ref = O.da2_forward(sd_gpu, x.cuda(), enc, bank)
+        _check(f"da2 vitl 2x518 call {i}", y, ref)
+
+
+def test_da2_infer_image_shape_and_state(vdn):
+    cfg = ENCODERS["vits"]
+    m = vdn.DepthAnythingV2(encoder="vits", features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
+    m.load_state_dict(make_state_dict("da2", "vits", 5))
+    img = np.random.RandomState(0).randint(0, 255, (90, 90, 3), dtype=np.uint8)
+    d = m.infer_image(img, input_size=70)
+    assert d.shape == (90, 90) and d.dtype == np.float32 and np.isfinite(d).all()
+    with pytest.raises(RuntimeError, match="clear_memory"):
+        m(torch.zeros(2, 3, 70, 70).cuda())  # batch size changed while the bank holds an entry
+    m.clear_memory()
+    m(torch.zeros(2, 3, 70, 70).cuda())

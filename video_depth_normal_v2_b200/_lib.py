@@ -25,6 +25,7 @@ class GemmDesc(C.Structure):
         ("act", c_int), ("geglu", c_int), ("row_map", c_int),
         ("rm0", c_int), ("rm1", c_int), ("rm2", c_int), ("rm3", c_int),
         ("head_w", c_void_p), ("head_b", c_float),
+        ("qkv_split", c_int), ("qkv_tokens_out", c_int), ("qkv_token_offset", c_int),
     ]
 
 
@@ -38,6 +39,7 @@ SIGNATURES = {
     "vdn_reset_launch_count": (None, []),
     "vdn_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "vdn_flash_attn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdn_flash_attn_ex": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_temporal_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_int, c_void_p]),
     "vdn_groupnorm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
@@ -58,6 +60,12 @@ SIGNATURES = {
     "vdn_frame_median_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_float, c_void_p]),
     "vdn_v5_net_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "vdn_v5_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "vdn_rope2d": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "vdn_add_rowvec": (c_int, [c_void_p, c_int, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p]),
+    "vdn_add_rowscalar": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vdn_dwconv7_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "vdn_mask_down1": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdn_mask_down2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -44,8 +44,8 @@ constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_
 // Two independent CTAs per SM (the previous design) drifted into phase and left the XU pipe 47 % busy (ncu, profiles/).
 template <int FMT>
 __global__ void __launch_bounds__(FA_THREADS, 1)
-flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT, void* __restrict__ out, int tokens,
-                  int heads, int C) {
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVT,
+                  void* __restrict__ out, int tokens, int tokens_kv, int heads, int C) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                      // [group]
   uint8_t* sK = smem + 2 * FA_TILE;        // [stage]
@@ -66,7 +66,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const int nt = (tokens + FA_BN - 1) / FA_BN;
+  const int nt = (tokens_kv + FA_BN - 1) / FA_BN;  // KV tiles (cross-attention: tokens_kv != tokens)
   const int q_tile0 = blockIdx.x * FA_GROUPS;
   const bool two = (q_tile0 + 1) * FA_BM < tokens;  // the second query tile exists
   const int ngroups = two ? 2 : 1;
@@ -75,7 +75,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 
   if (warp_idx == 8) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmQK);
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmVT);
       mbar_init(q_full, 1);
       for (int i = 0; i < 2; ++i) {
@@ -106,7 +107,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     // ---------------- TMA producer (warp-uniform control flow, one elected lane issues) ----------------
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ngroups * FA_TILE);
-      for (int g = 0; g < ngroups; ++g) tma_load_5d(sQ + g * FA_TILE, &tmQK, q_full, 0, h, 0, (q_tile0 + g) * FA_BM, b);
+      for (int g = 0; g < ngroups; ++g) tma_load_4d(sQ + g * FA_TILE, &tmQ, q_full, 0, h, (q_tile0 + g) * FA_BM, b);
     }
     __syncwarp();
     for (int j = 0; j < nt; ++j) {
@@ -115,7 +116,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       mbar_wait(&k_empty[st], ph ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[st], FA_TILE);
-        tma_load_5d(sK + st * FA_TILE, &tmQK, &k_full[st], 0, h, 1, j * FA_BN, b);
+        tma_load_4d(sK + st * FA_TILE, &tmK, &k_full[st], 0, h, j * FA_BN, b);
       }
       __syncwarp();
       mbar_wait(&v_empty[st], ph ^ 1);
@@ -197,7 +198,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_off;
 
     for (int j = 0; j < nt; ++j) {
-      const int nvalid = min(FA_BN, tokens - j * FA_BN);
+      const int nvalid = min(FA_BN, tokens_kv - j * FA_BN);
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
       uint32_t s0[32], s1[32], s2[32], s3[32];
@@ -403,26 +404,34 @@ temporal_attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int D, int 
 
 using namespace vdn;
 
-extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens, int32_t heads,
-                              void* stream_v) {
+extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_stride, const void* k, int64_t ld_k, int64_t k_batch_stride,
+                                 const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens_q, int32_t tokens_kv, int32_t heads,
+                                 void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  if (!qk || !vT || !out) return set_error("vdn_flash_attn: null pointer");
-  if (B <= 0 || tokens <= 0 || heads <= 0) return set_error("vdn_flash_attn: bad shape");
+  if (!q || !k || !vT || !out) return set_error("vdn_flash_attn: null pointer");
+  if (B <= 0 || tokens_q <= 0 || tokens_kv <= 0 || heads <= 0) return set_error("vdn_flash_attn: bad shape");
   const int C = heads * FA_D;
-  if (ld_qk < 2 * C || (ld_qk * 2) % 16 != 0) return set_error("vdn_flash_attn: ld_qk must be >= 2*C and 16-byte aligned");
-  if (ld_vT < tokens || (ld_vT * 2) % 16 != 0) return set_error("vdn_flash_attn: ld_vT must be >= tokens and a multiple of 8");
+  if (ld_q < C || (ld_q * 2) % 16 != 0 || ld_k < C || (ld_k * 2) % 16 != 0) return set_error("vdn_flash_attn: ld_q / ld_k must be >= C and 16-byte aligned");
+  if ((q_batch_stride * 2) % 16 != 0 || (k_batch_stride * 2) % 16 != 0) return set_error("vdn_flash_attn: batch strides must be 16-byte aligned");
+  if (ld_vT < tokens_kv || (ld_vT * 2) % 16 != 0) return set_error("vdn_flash_attn: ld_vT must be >= tokens_kv and a multiple of 8");
   const int fmt = get_operand_format();
-  CUtensorMap tmQK, tmVT;
+  CUtensorMap tmQ, tmK, tmVT;
   {
-    // element (b, t, s, h, d) of the q|k buffer; innermost first: d, h, s (0 = q, 1 = k), t, b
-    const uint64_t dims[5] = {(uint64_t)FA_D, (uint64_t)heads, 2, (uint64_t)tokens, (uint64_t)B};
-    const uint64_t strides[4] = {(uint64_t)FA_D * 2, (uint64_t)C * 2, (uint64_t)ld_qk * 2, (uint64_t)ld_qk * 2 * tokens};
-    const uint32_t box[5] = {(uint32_t)FA_D, 1, 1, (uint32_t)FA_BM, 1};
-    if (make_tensor_map(&tmQK, qk, fmt, 5, dims, strides, box)) return 1;
+    // element (b, t, h, d); innermost first: d, h, t, b
+    const uint64_t dims[4] = {(uint64_t)FA_D, (uint64_t)heads, (uint64_t)tokens_q, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)FA_D * 2, (uint64_t)ld_q * 2, (uint64_t)q_batch_stride * 2};
+    const uint32_t box[4] = {(uint32_t)FA_D, 1, (uint32_t)FA_BM, 1};
+    if (make_tensor_map(&tmQ, q, fmt, 4, dims, strides, box)) return 1;
   }
   {
-    // V^T: (bh, d, t) with t contiguous; innermost first: t, d, bh.  Columns >= tokens are out of bounds -> zero filled.
-    const uint64_t dims[3] = {(uint64_t)tokens, (uint64_t)FA_D, (uint64_t)B * heads};
+    const uint64_t dims[4] = {(uint64_t)FA_D, (uint64_t)heads, (uint64_t)tokens_kv, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)FA_D * 2, (uint64_t)ld_k * 2, (uint64_t)k_batch_stride * 2};
+    const uint32_t box[4] = {(uint32_t)FA_D, 1, (uint32_t)FA_BN, 1};
+    if (make_tensor_map(&tmK, k, fmt, 4, dims, strides, box)) return 1;
+  }
+  {
+    // V^T: (bh, d, t) with t contiguous; innermost first: t, d, bh.  Columns >= tokens_kv are out of bounds -> zero filled.
+    const uint64_t dims[3] = {(uint64_t)tokens_kv, (uint64_t)FA_D, (uint64_t)B * heads};
     const uint64_t strides[2] = {(uint64_t)ld_vT * 2, (uint64_t)ld_vT * 2 * FA_D};
     const uint32_t box[3] = {64, (uint32_t)FA_D, 1};
     if (make_tensor_map(&tmVT, vT, fmt, 3, dims, strides, box)) return 1;
@@ -434,11 +443,20 @@ extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(flash_attn): ") + cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid((tokens + FA_GROUPS * FA_BM - 1) / (FA_GROUPS * FA_BM), heads, B);
-  if (fmt) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQK, tmVT, out, tokens, heads, C);
-  else flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQK, tmVT, out, tokens, heads, C);
+  dim3 grid((tokens_q + FA_GROUPS * FA_BM - 1) / (FA_GROUPS * FA_BM), heads, B);
+  if (fmt) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C);
+  else flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C);
   count_launch();
   return check_launch("flash_attn_kernel");
+}
+
+extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens, int32_t heads,
+                              void* stream_v) {
+  if (!qk) return set_error("vdn_flash_attn: null pointer");
+  const int C = heads * FA_D;
+  if (ld_qk < 2 * C) return set_error("vdn_flash_attn: ld_qk must be >= 2*C and 16-byte aligned");
+  const uint16_t* base = reinterpret_cast<const uint16_t*>(qk);
+  return vdn_flash_attn_ex(base, ld_qk, (int64_t)tokens * ld_qk, base + C, ld_qk, (int64_t)tokens * ld_qk, vT, ld_vT, out, B, tokens, tokens, heads, stream_v);
 }
 
 extern "C" int vdn_temporal_attn(const void* qkv, void* out, int32_t D, int32_t T, int32_t C, int32_t heads, void* stream_v) {

@@ -1,0 +1,269 @@
+// Bandwidth-bound pieces of the DepthAnythingV2 memory block (depth_anything_v2/memory_block.py, sam2/modeling/*):
+//   vdn_rope2d         : axial rotary encoding of q / k heads in place (position_encoding.py:186-239)
+//   vdn_add_rowvec     : out_f32 = x + alpha * vec   (pos_enc_at_input, memory_attention.py:137-138; constant empty-bank cross-attention term)
+//   vdn_add_rowscalar  : x[r, :] += m[r]             (pix_feat + downsampled mask, memory_encoder.py:173)
+//   vdn_dwconv7_ln     : depthwise 7x7 conv + LayerNorm2d over channels, NHWC fp32 -> 16-bit rows (memory_encoder.py:96-99)
+//   vdn_mask_down1 / 2 : the two MaskDownSamplers on the 1-channel sigmoid(depth) map (memory_encoder.py:17-60, memory_block.py:68-71)
+#include "../../include/vdn_b200.h"
+#include "vdn_common.cuh"
+#include "vdn_host.h"
+
+namespace vdn {
+
+template <int FMT>
+__global__ void __launch_bounds__(256)
+rope2d_kernel(uint4* __restrict__ x, long long rows, int ld8 /*row pitch in 16-byte units*/, int col8 /*first column / 8*/, int heads,
+              const float* __restrict__ cs, int P, long long rows_per_batch, long long batch_pitch) {
+  const long long total = rows * heads * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = int(idx & 7);  // 16-byte piece of the 64-wide head: pairs 4v .. 4v+3
+    const long long t = idx >> 3;
+    const int h = int(t % heads);
+    const long long r = t / heads;
+    const int pos = int(r % P);
+    const long long bb = r / rows_per_batch;
+    const long long phys = bb * batch_pitch + (r - bb * rows_per_batch);  // rows of one batch are contiguous, batches batch_pitch rows apart
+    uint4* p = x + phys * ld8 + col8 + h * 8 + v;
+    uint4 u = *p;
+    uint32_t* w = &u.x;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + (long long)pos * 64 + 4 * v));
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + (long long)pos * 64 + 32 + 4 * v));
+    const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 ab = T16f<FMT>::unpack(w[i]);
+      w[i] = T16f<FMT>::pack(ab.x * cc[i] - ab.y * ss[i], ab.x * ss[i] + ab.y * cc[i]);
+    }
+    *p = u;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_rowvec_kernel(const void* __restrict__ x, int x_f32, const float* __restrict__ vec, float alpha, float* __restrict__ out, long long rows, int C, int fmt) {
+  const long long total = rows * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = int(idx % C);
+    const float v = x_f32 ? reinterpret_cast<const float*>(x)[idx] : load16(x, idx, fmt);
+    out[idx] = v + alpha * __ldg(vec + c);
+  }
+}
+
+__global__ void __launch_bounds__(256) add_rowscalar_kernel(float* __restrict__ x, const float* __restrict__ m, long long rows, int C) {
+  const long long total = rows * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) x[idx] += __ldg(m + idx / C);
+}
+
+constexpr int DW_MAXC = 4;  // channels per thread (C <= 1024 with 256 threads)
+
+__global__ void __launch_bounds__(256)
+dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ ln_w,
+                  const float* __restrict__ ln_b, void* __restrict__ out, int H, int W, int C, float eps, int fmt) {
+  const long long pix = blockIdx.x;
+  const int xx = int(pix % W);
+  const int yy = int((pix / W) % H);
+  const long long img = pix / ((long long)W * H);
+  const float* base = x + img * (long long)H * W * C;
+  float acc[DW_MAXC];
+#pragma unroll
+  for (int i = 0; i < DW_MAXC; ++i) {
+    const int c = threadIdx.x + i * 256;
+    acc[i] = c < C ? __ldg(bias + c) : 0.0f;
+  }
+  for (int dy = -3; dy <= 3; ++dy) {
+    const int y2 = yy + dy;
+    if (y2 < 0 || y2 >= H) continue;
+    for (int dx = -3; dx <= 3; ++dx) {
+      const int x2 = xx + dx;
+      if (x2 < 0 || x2 >= W) continue;
+      const float* src = base + ((long long)y2 * W + x2) * C;
+      const float* wt = w + ((dy + 3) * 7 + (dx + 3)) * C;
+#pragma unroll
+      for (int i = 0; i < DW_MAXC; ++i) {
+        const int c = threadIdx.x + i * 256;
+        if (c < C) acc[i] = fmaf(src[c], __ldg(wt + c), acc[i]);
+      }
+    }
+  }
+  __shared__ float red[8];
+  __shared__ float stat;
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < DW_MAXC; ++i)
+    if (threadIdx.x + i * 256 < C) s += acc[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    stat = t / (float)C;
+  }
+  __syncthreads();
+  const float mean = stat;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < DW_MAXC; ++i)
+    if (threadIdx.x + i * 256 < C) q = fmaf(acc[i] - mean, acc[i] - mean, q);
+  q = warp_sum(q);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    stat = rsqrtf(t / (float)C + eps);
+  }
+  __syncthreads();
+  const float rstd = stat;
+#pragma unroll
+  for (int i = 0; i < DW_MAXC; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < C) store16(out, pix * C + c, (acc[i] - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c), fmt);
+  }
+}
+
+__device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+// sigmoid -> conv 3x3 / stride 2 / pad 1 (1 -> 4) -> LayerNorm2d(4) -> GELU -> conv 1x1 (4 -> 1)
+__global__ void __launch_bounds__(256)
+mask_down1_kernel(const float* __restrict__ depth, const float* __restrict__ prm, float* __restrict__ out, int B, int H, int W, int Ho, int Wo) {
+  // prm: w0[4][9], b0[4], lnw[4], lnb[4], w1[4], b1
+  const long long total = (long long)B * Ho * Wo;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int xo = int(idx % Wo);
+    const int yo = int((idx / Wo) % Ho);
+    const long long b = idx / ((long long)Wo * Ho);
+    const float* p = depth + b * (long long)H * W;
+    float t[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int y = 2 * yo - 1 + r, x = 2 * xo - 1 + s;
+        t[r * 3 + s] = (y >= 0 && y < H && x >= 0 && x < W) ? 1.0f / (1.0f + expf(-p[(long long)y * W + x])) : 0.0f;
+      }
+    float c[4], mean = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = prm[36 + k];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) a = fmaf(prm[k * 9 + j], t[j], a);
+      c[k] = a;
+      mean += a;
+    }
+    mean *= 0.25f;
+    float var = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) var += (c[k] - mean) * (c[k] - mean);
+    const float rstd = 1.0f / sqrtf(var * 0.25f + 1e-6f);
+    float o = prm[52];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o = fmaf(prm[48 + k], gelu_exact((c[k] - mean) * rstd * prm[40 + k] + prm[44 + k]), o);
+    out[idx] = o;
+  }
+}
+
+// conv 7x7 / stride 7 (1 -> 49) -> LayerNorm2d(49) -> GELU -> conv 1x1 (49 -> 1); one warp per output pixel
+__global__ void __launch_bounds__(256)
+mask_down2_kernel(const float* __restrict__ in, const float* __restrict__ prm, float* __restrict__ out, int B, int Hi, int Wi, int Ho, int Wo) {
+  // prm: w0[49][49], b0[49], lnw[49], lnb[49], w1[49], b1
+  __shared__ float sp[49 * 49 + 4 * 49 + 1];
+  for (int i = threadIdx.x; i < 49 * 49 + 4 * 49 + 1; i += blockDim.x) sp[i] = prm[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * Ho * Wo;
+  for (long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < total; pix += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int xo = int(pix % Wo);
+    const int yo = int((pix / Wo) % Ho);
+    const long long b = pix / ((long long)Wo * Ho);
+    const float* p = in + b * (long long)Hi * Wi + (long long)(7 * yo) * Wi + 7 * xo;
+    // lane handles channels lane and lane + 32 (< 49)
+    float c0 = sp[2401 + lane], c1 = lane + 32 < 49 ? sp[2401 + lane + 32] : 0.0f;
+    for (int j = 0; j < 49; ++j) {
+      const float t = p[(long long)(j / 7) * Wi + (j % 7)];
+      c0 = fmaf(sp[lane * 49 + j], t, c0);
+      if (lane + 32 < 49) c1 = fmaf(sp[(lane + 32) * 49 + j], t, c1);
+    }
+    const bool has1 = lane + 32 < 49;
+    const float mean = warp_sum(c0 + (has1 ? c1 : 0.0f)) * (1.0f / 49.0f);
+    const float d0 = c0 - mean, d1 = has1 ? c1 - mean : 0.0f;
+    const float rstd = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / 49.0f) + 1e-6f);
+    float o = sp[2401 + 3 * 49 + lane] * gelu_exact(d0 * rstd * sp[2401 + 49 + lane] + sp[2401 + 2 * 49 + lane]);
+    if (has1) o += sp[2401 + 3 * 49 + lane + 32] * gelu_exact(d1 * rstd * sp[2401 + 49 + lane + 32] + sp[2401 + 2 * 49 + lane + 32]);
+    o = warp_sum(o);
+    if (lane == 0) out[pix] = o + sp[2401 + 4 * 49];
+  }
+}
+
+static inline unsigned blocks_for(long long work, int per_block) {
+  long long b = (work + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace vdn
+
+using namespace vdn;
+#define VDN_STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v)
+
+extern "C" int vdn_rope2d(void* x, int64_t rows, int64_t ld, int32_t col0, int32_t heads, const float* cos_sin, int32_t P, int64_t rows_per_batch,
+                          int64_t batch_pitch, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !cos_sin) return set_error("vdn_rope2d: null pointer");
+  if (ld % 8 != 0 || col0 % 8 != 0 || heads <= 0 || P <= 0 || rows <= 0) return set_error("vdn_rope2d: bad geometry");
+  if (col0 + (int64_t)heads * 64 > ld) return set_error("vdn_rope2d: heads exceed the row");
+  if (rows_per_batch <= 0) { rows_per_batch = rows; batch_pitch = rows; }
+  if (rows_per_batch % P != 0 || batch_pitch < rows_per_batch) return set_error("vdn_rope2d: rows_per_batch must be a multiple of P and <= batch_pitch");
+  const unsigned grid = blocks_for(rows * heads * 8, 256);
+  if (get_operand_format()) rope2d_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch);
+  else rope2d_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch);
+  count_launch();
+  return check_launch("rope2d_kernel");
+}
+
+extern "C" int vdn_add_rowvec(const void* x, int32_t x_f32, const float* vec, float alpha, float* out, int64_t rows, int32_t C, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !vec || !out) return set_error("vdn_add_rowvec: null pointer");
+  add_rowvec_kernel<<<blocks_for(rows * C, 256), 256, 0, stream>>>(x, x_f32, vec, alpha, out, rows, C, get_operand_format());
+  count_launch();
+  return check_launch("add_rowvec_kernel");
+}
+
+extern "C" int vdn_add_rowscalar(float* x, const float* m, int64_t rows, int32_t C, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !m) return set_error("vdn_add_rowscalar: null pointer");
+  add_rowscalar_kernel<<<blocks_for(rows * C, 256), 256, 0, stream>>>(x, m, rows, C);
+  count_launch();
+  return check_launch("add_rowscalar_kernel");
+}
+
+extern "C" int vdn_dwconv7_ln(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out, int32_t B, int32_t H,
+                              int32_t W, int32_t C, float eps, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !w || !bias || !ln_w || !ln_b || !out) return set_error("vdn_dwconv7_ln: null pointer");
+  if (C <= 0 || C > 256 * DW_MAXC) return set_error("vdn_dwconv7_ln: C must be <= 1024");
+  dwconv7_ln_kernel<<<(unsigned)((long long)B * H * W), 256, 0, stream>>>(x, w, bias, ln_w, ln_b, out, H, W, C, eps, get_operand_format());
+  count_launch();
+  return check_launch("dwconv7_ln_kernel");
+}
+
+extern "C" int vdn_mask_down1(const float* depth, const float* params, float* out, int32_t B, int32_t H, int32_t W, void* stream_v) {
+  VDN_STREAM;
+  if (!depth || !params || !out) return set_error("vdn_mask_down1: null pointer");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  mask_down1_kernel<<<blocks_for((long long)B * Ho * Wo, 256), 256, 0, stream>>>(depth, params, out, B, H, W, Ho, Wo);
+  count_launch();
+  return check_launch("mask_down1_kernel");
+}
+
+extern "C" int vdn_mask_down2(const float* in, const float* params, float* out, int32_t B, int32_t Hi, int32_t Wi, void* stream_v) {
+  VDN_STREAM;
+  if (!in || !params || !out) return set_error("vdn_mask_down2: null pointer");
+  if (Hi < 7 || Wi < 7) return set_error("vdn_mask_down2: input smaller than the 7x7 kernel");
+  const int Ho = (Hi - 7) / 7 + 1, Wo = (Wi - 7) / 7 + 1;
+  mask_down2_kernel<<<blocks_for((long long)B * Ho * Wo * 32, 256), 256, 0, stream>>>(in, params, out, B, Hi, Wi, Ho, Wo);
+  count_launch();
+  return check_launch("mask_down2_kernel");
+}

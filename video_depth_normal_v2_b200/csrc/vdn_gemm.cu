@@ -63,6 +63,7 @@ struct GemmKParams {
   int act, row_map, rm0, rm1, rm2, rm3;
   const float* head_w;
   float head_b;
+  int qkv_split, qkv_tpo, qkv_toff;
 };
 
 template <int BLOCK_N, int EPI = EPI_PLAIN>
@@ -225,7 +226,7 @@ __device__ __forceinline__ void epi_plain(const GemmKParams& p, const RowCtx& rc
 
 template <int FMT>
 __device__ __forceinline__ void epi_qkv(const GemmKParams& p, const RowCtx& rc, int n0, float (&v)[32]) {
-  const int twoC = 2 * p.rm2;
+  const int twoC = p.qkv_split;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int n = n0 + g * 8;
@@ -234,7 +235,7 @@ __device__ __forceinline__ void epi_qkv(const GemmKParams& p, const RowCtx& rc, 
       store8_16<FMT>(p.out, rc.out_row * p.ldc + n, v + g * 8);
     } else {
       const int c = n - twoC;  // h*64 + d
-      const int heads = p.rm2 >> 6;
+      const int heads = (p.N - twoC) >> 6;
       uint16_t* vt = reinterpret_cast<uint16_t*>(p.out2) + ((long long)(rc.b * heads + (c >> 6)) * 64 + (c & 63)) * p.rm1 + rc.x;
 #pragma unroll
       for (int i = 0; i < 8; ++i) vt[(long long)i * p.rm1] = static_cast<uint16_t>(pack2<FMT>(v[g * 8 + i], 0.0f) & 0xFFFFu);
@@ -445,7 +446,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rc.x = rem - rc.y * p.rm1;
       } else if constexpr (EPI == EPI_QKV) {
         rc.b = int(row / p.rm0);
-        rc.x = int(row - (long long)rc.b * p.rm0);
+        rc.x = int(row - (long long)rc.b * p.rm0) + p.qkv_toff;      // token index in the output (KV-cache slot offset)
+        rc.out_row = (long long)rc.b * p.qkv_tpo + rc.x;
       } else if constexpr (EPI == EPI_PLAIN || EPI == EPI_RES) {
         if (p.row_map == VDN_ROWMAP_TEMPORAL) {
           const int T = p.rm0, D = p.rm1;
@@ -709,6 +711,9 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
   p.act = d->act;
   p.row_map = d->row_map; p.rm0 = d->rm0; p.rm1 = d->rm1; p.rm2 = d->rm2; p.rm3 = d->rm3;
   p.head_w = d->head_w; p.head_b = d->head_b;
+  p.qkv_split = d->qkv_split > 0 ? d->qkv_split : 2 * d->rm2;
+  p.qkv_tpo = d->qkv_tokens_out > 0 ? d->qkv_tokens_out : d->rm0;
+  p.qkv_toff = d->qkv_token_offset;
   p.conv = d->conv;
   int epi = EPI_PLAIN;
   if (d->head_w != nullptr) epi = EPI_HEAD;
@@ -726,6 +731,9 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
       epi = EPI_TMA;
   }
   if (epi == EPI_QKV && (d->out_f32 || d->out2 == nullptr || d->res || d->gamma || d->act)) return set_error("vdn_gemm: QKV split takes bias only, 16-bit out and out2 = V^T");
+  if (epi == EPI_QKV && (p.qkv_split % 8 != 0 || p.qkv_split >= d->N || (d->N - p.qkv_split) % 64 != 0 || d->rm0 <= 0 || d->rm1 <= 0 ||
+                         p.qkv_toff < 0 || p.qkv_toff + d->rm0 > p.qkv_tpo || p.qkv_tpo > d->rm1))
+    return set_error("vdn_gemm: bad QKV split geometry");
   if (epi == EPI_PIXSHUF && (d->out_f32 || d->res || d->res2 || d->gamma || d->act || d->out2)) return set_error("vdn_gemm: pixel-shuffle takes bias only and a 16-bit output");
   if (epi == EPI_GEGLU && (d->gamma || d->act || d->out2 || d->res2)) return set_error("vdn_gemm: geglu takes bias only");
   if (epi != EPI_PLAIN && epi != EPI_RES && epi != EPI_HEAD && epi != EPI_TMA && d->N < 256) return set_error("vdn_gemm: QKV / GEGLU / pixel-shuffle epilogues need N >= 256");

@@ -1,0 +1,273 @@
+"""Drop-in host module for the fork's ``DepthAnythingV2`` with its SAM2-style memory block
+(depth_anything_v2/depth_anything_v2.py:12-92, memory_block.py, sam2/modeling/{memory_attention,memory_encoder}.py,
+sam2/modeling/sam/transformer.py:254-311), SURVEY.md §8a row a11.
+
+Same constructor, ``state_dict`` keys, ``forward`` / ``infer_image`` / ``clear_memory`` as the reference; stateful and not
+re-entrant, like the reference.  Every contraction runs on the tcgen05 GEMM / flash-attention kernels.  Two exact
+restructurings remove work:
+  * the memory bank stores, per attention layer, the already projected and rotated keys and the transposed values of each
+    memory entry (a ring of ``max_memory_length`` slots): the reference re-projects all <= 6 x HW memory tokens in each of the
+    4 layers on every call; here a new entry is projected once.  Attention is invariant to key order and the temporal
+    position term never reaches the keys (pos_enc_at_cross_attn_keys=False, memory_block.py:38-47), so ring order is immaterial;
+  * with an empty bank every key shares one value row, so the cross-attention adds the constant out_proj(v_proj(no_mem_embed))
+    to every token (softmax weights sum to 1): a row-vector add instead of an HW x HW attention.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops, packing
+from .models import ENCODER_CONFIGS, _PackedModule, _empty, _encoder_shapes, _head_shapes, encoder_forward, head_forward
+
+NUM_MEM_ATTENTION_LAYERS = 4  # depth_anything_v2.py:31
+
+
+def _memory_block_shapes(prefix: str, C: int, max_len: int) -> Dict[str, tuple]:
+    from collections import OrderedDict
+    s = OrderedDict()
+    s[prefix + "curr_pos_enc"] = (1, 1, C)
+    s[prefix + "maskmem_tpos_enc"] = (1, max_len, C)
+    s[prefix + "no_mem_embed"] = (1, 1, C)
+    for l in range(NUM_MEM_ATTENTION_LAYERS):
+        p = f"{prefix}memory_attention.layers.{l}."
+        for att in ("self_attn", "cross_attn_image"):
+            for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                s[f"{p}{att}.{proj}.weight"], s[f"{p}{att}.{proj}.bias"] = (C, C), (C,)
+        s[p + "linear1.weight"], s[p + "linear1.bias"] = (2 * C, C), (2 * C,)
+        s[p + "linear2.weight"], s[p + "linear2.bias"] = (C, 2 * C), (C,)
+        for n in ("norm1", "norm2", "norm3"):
+            s[p + n + ".weight"] = s[p + n + ".bias"] = (C,)
+    s[prefix + "memory_attention.norm.weight"] = s[prefix + "memory_attention.norm.bias"] = (C,)
+    me = prefix + "memory_encoder."
+    s[me + "mask_downsampler.0.encoder.0.weight"], s[me + "mask_downsampler.0.encoder.0.bias"] = (4, 1, 3, 3), (4,)
+    s[me + "mask_downsampler.0.encoder.1.weight"] = s[me + "mask_downsampler.0.encoder.1.bias"] = (4,)
+    s[me + "mask_downsampler.0.encoder.3.weight"], s[me + "mask_downsampler.0.encoder.3.bias"] = (1, 4, 1, 1), (1,)
+    s[me + "mask_downsampler.1.encoder.0.weight"], s[me + "mask_downsampler.1.encoder.0.bias"] = (49, 1, 7, 7), (49,)
+    s[me + "mask_downsampler.1.encoder.1.weight"] = s[me + "mask_downsampler.1.encoder.1.bias"] = (49,)
+    s[me + "mask_downsampler.1.encoder.3.weight"], s[me + "mask_downsampler.1.encoder.3.bias"] = (1, 49, 1, 1), (1,)
+    s[me + "pix_feat_proj.weight"], s[me + "pix_feat_proj.bias"] = (C, C, 1, 1), (C,)
+    for l in range(2):
+        p = f"{me}fuser.layers.{l}."
+        s[p + "gamma"] = (C,)
+        s[p + "dwconv.weight"], s[p + "dwconv.bias"] = (C, 1, 7, 7), (C,)
+        s[p + "norm.weight"] = s[p + "norm.bias"] = (C,)
+        s[p + "pwconv1.weight"], s[p + "pwconv1.bias"] = (4 * C, C), (4 * C,)
+        s[p + "pwconv2.weight"], s[p + "pwconv2.bias"] = (C, 4 * C), (C,)
+    return s
+
+
+def pack_memory_block(sd, prefix: str, C: int, dev, dt) -> dict:
+    f32, w16 = packing._f32, packing._w16
+    mb = {"C": C, "heads": C // 64, "layers": []}
+    mb["curr_pos"] = f32(sd[prefix + "curr_pos_enc"].reshape(C), dev)
+    no_mem = sd[prefix + "no_mem_embed"].detach().double().reshape(C)
+    for l in range(NUM_MEM_ATTENTION_LAYERS):
+        p = f"{prefix}memory_attention.layers.{l}."
+        sa, ca = p + "self_attn.", p + "cross_attn_image."
+        cat = lambda names, key: torch.cat([sd[n + key] for n in names], dim=0)
+        # empty bank: out_proj(v_proj(no_mem_embed)) added to every token (weights-only, evaluated once in fp64)
+        v = sd[ca + "v_proj.weight"].double() @ no_mem + sd[ca + "v_proj.bias"].double()
+        c_empty = sd[ca + "out_proj.weight"].double() @ v + sd[ca + "out_proj.bias"].double()
+        mb["layers"].append({
+            "n1_w": f32(sd[p + "norm1.weight"], dev), "n1_b": f32(sd[p + "norm1.bias"], dev),
+            "n2_w": f32(sd[p + "norm2.weight"], dev), "n2_b": f32(sd[p + "norm2.bias"], dev),
+            "n3_w": f32(sd[p + "norm3.weight"], dev), "n3_b": f32(sd[p + "norm3.bias"], dev),
+            "sa_qkv_w": w16(cat([sa + "q_proj", sa + "k_proj", sa + "v_proj"], ".weight"), dev, dt),
+            "sa_qkv_b": f32(cat([sa + "q_proj", sa + "k_proj", sa + "v_proj"], ".bias"), dev),
+            "sa_out": packing.pack_linear(sd, sa + "out_proj", dev, dt),
+            "ca_q": packing.pack_linear(sd, ca + "q_proj", dev, dt),
+            "ca_kv_w": w16(cat([ca + "k_proj", ca + "v_proj"], ".weight"), dev, dt),
+            "ca_kv_b": f32(cat([ca + "k_proj", ca + "v_proj"], ".bias"), dev),
+            "ca_out": packing.pack_linear(sd, ca + "out_proj", dev, dt),
+            "ca_empty": f32(c_empty.float(), dev),
+            "l1": packing.pack_linear(sd, p + "linear1", dev, dt), "l2": packing.pack_linear(sd, p + "linear2", dev, dt),
+        })
+    mb["norm_w"], mb["norm_b"] = f32(sd[prefix + "memory_attention.norm.weight"], dev), f32(sd[prefix + "memory_attention.norm.bias"], dev)
+    me = prefix + "memory_encoder."
+    flat = lambda *names: f32(torch.cat([sd[me + n].detach().float().reshape(-1) for n in names]), dev)
+    mb["md1"] = flat("mask_downsampler.0.encoder.0.weight", "mask_downsampler.0.encoder.0.bias", "mask_downsampler.0.encoder.1.weight",
+                     "mask_downsampler.0.encoder.1.bias", "mask_downsampler.0.encoder.3.weight", "mask_downsampler.0.encoder.3.bias")
+    mb["md2"] = flat("mask_downsampler.1.encoder.0.weight", "mask_downsampler.1.encoder.0.bias", "mask_downsampler.1.encoder.1.weight",
+                     "mask_downsampler.1.encoder.1.bias", "mask_downsampler.1.encoder.3.weight", "mask_downsampler.1.encoder.3.bias")
+    mb["pix_proj"] = packing.pack_conv1x1(sd, me + "pix_feat_proj", dev, dt)
+    mb["fuser"] = []
+    for l in range(2):
+        p = f"{me}fuser.layers.{l}."
+        mb["fuser"].append({
+            "dw_w": f32(sd[p + "dwconv.weight"].reshape(C, 49).t(), dev), "dw_b": f32(sd[p + "dwconv.bias"], dev),  # tap-major [49, C]
+            "ln_w": f32(sd[p + "norm.weight"], dev), "ln_b": f32(sd[p + "norm.bias"], dev),
+            "pw1": packing.pack_linear(sd, p + "pwconv1", dev, dt), "pw2": packing.pack_linear(sd, p + "pwconv2", dev, dt),
+            "gamma": f32(sd[p + "gamma"], dev),
+        })
+    mb["rope"] = {}
+    return mb
+
+
+def rope_table(mb: dict, side: int, dev) -> torch.Tensor:
+    """[side*side, 64] fp32: cos[32] | sin[32] per grid position (compute_axial_cis, position_encoding.py:186-210), cached."""
+    if side not in mb["rope"]:
+        freqs = 1.0 / (10000.0 ** (torch.arange(0, 64, 4)[:16].float() / 64))
+        t = torch.arange(side * side, dtype=torch.float32)
+        tx, ty = t % side, torch.div(t, side, rounding_mode="floor")
+        ang = torch.cat([torch.outer(tx, freqs), torch.outer(ty, freqs)], dim=-1)
+        mb["rope"][side] = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(dev).contiguous()
+    return mb["rope"][side]
+
+
+class _MemoryState:
+    """Device-resident ring of projected memory entries: per layer k [B, L*P, C] (RoPE applied) and V^T [B*heads, 64, L*P]."""
+
+    def __init__(self, B, P, C, heads, max_len, dev, dt):
+        self.B, self.P, self.count, self.max_len = B, P, 0, max_len
+        self.ld_vT = (max_len * P + 7) // 8 * 8
+        self.k = [torch.zeros((B, max_len * P, C), dtype=dt, device=dev) for _ in range(NUM_MEM_ATTENTION_LAYERS)]
+        self.vT = [torch.zeros((B * heads, 64, self.ld_vT), dtype=dt, device=dev) for _ in range(NUM_MEM_ATTENTION_LAYERS)]
+
+    @property
+    def entries(self) -> int:
+        return min(self.count, self.max_len)
+
+
+class DepthAnythingV2(_PackedModule):
+    """Drop-in for depth_anything_v2/depth_anything_v2.py:12 (encoder vits / vitl; use_bn=False, use_clstoken=False)."""
+
+    def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False, use_clstoken=False, max_memory_length=6):
+        super().__init__()
+        if encoder not in ENCODER_CONFIGS:
+            raise KeyError(encoder)
+        if use_bn or use_clstoken:
+            raise NotImplementedError("use_bn / use_clstoken are never exercised by the reference (SURVEY.md §8b)")
+        self.encoder, self.max_memory_length = encoder, int(max_memory_length)
+        self.cfg = dict(ENCODER_CONFIGS[encoder], features=features, out_channels=list(out_channels))
+        self.intermediate_layer_idx = {k: v["taps"] for k, v in ENCODER_CONFIGS.items()}
+        self._mem: Optional[_MemoryState] = None
+
+    def _expected_shapes(self):
+        s = _encoder_shapes("pretrained.", self.cfg)
+        s.update(_memory_block_shapes("memory_block.", self.cfg["embed_dim"], self.max_memory_length))
+        s.update(_head_shapes("depth_head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], False))
+        return s
+
+    def _pack(self, sd, dev, dt):
+        self._mem = None
+        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "depth_head.", self.cfg, dev, dt, False),
+                "mb": pack_memory_block(sd, "memory_block.", self.cfg["embed_dim"], dev, dt)}
+
+    def clear_memory(self):
+        """depth_anything_v2.py:42-43"""
+        self._mem = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _memory_attention(self, mb: dict, f3: torch.Tensor, B: int, P: int, side: int) -> torch.Tensor:
+        """memory_block.py:102-125 + memory_attention.py:102-169: f3 [B*P, C] 16-bit -> [B*P, C] 16-bit."""
+        dev, od, C, heads = f3.device, ops.operand_dtype(), mb["C"], mb["heads"]
+        rows = B * P
+        cs = rope_table(mb, side, dev)
+        x = _empty((rows, C), torch.float32, dev)
+        ops.add_rowvec(f3, mb["curr_pos"], 0.1, x)  # pos_enc_at_input
+        npad = (P + 7) // 8 * 8
+        t16 = _empty((rows, C), od, dev)
+        qk = _empty((rows, 2 * C), od, dev)
+        vT = torch.zeros((B * heads, 64, npad), dtype=od, device=dev) if npad != P else _empty((B * heads, 64, npad), od, dev)
+        ao = _empty((rows, C), od, dev)
+        q = _empty((rows, C), od, dev)
+        hid = _empty((rows, 2 * C), od, dev)
+        mem = self._mem
+        for l, L in enumerate(mb["layers"]):
+            # self-attention with RoPE on q and k
+            ops.layernorm(x, L["n1_w"], L["n1_b"], t16, 1e-5)
+            ops.gemm(t16, L["sa_qkv_w"], qk, M=rows, N=3 * C, K=C, bias=L["sa_qkv_b"], ldc=2 * C, out2=vT, row_map=ops.ROWMAP_QKV_SPLIT, rm=(P, npad, C, 0))
+            ops.rope2d(qk, rows, 2 * C, 0, 2 * heads, cs, P)
+            ops.flash_attn(qk, vT, ao, B, P, heads)
+            ops.gemm(ao, L["sa_out"]["w"], x, M=rows, N=C, K=C, bias=L["sa_out"]["b"], res=x)
+            # cross-attention to the memory bank
+            if mem is None or mem.entries == 0:
+                ops.add_rowvec(x, L["ca_empty"], 1.0, x)
+            else:
+                ops.layernorm(x, L["n2_w"], L["n2_b"], t16, 1e-5, pe=mb["curr_pos"].view(1, C))  # norm2(tgt) + query_pos
+                ops.gemm(t16, L["ca_q"]["w"], q, M=rows, N=C, K=C, bias=L["ca_q"]["b"])
+                ops.rope2d(q, rows, C, 0, heads, cs, P)
+                n_kv = mem.entries * P
+                ops.flash_attn_ex(q, C, P * C, mem.k[l], C, mem.max_len * P * C, mem.vT[l], mem.ld_vT, ao, B, P, n_kv, heads)
+                ops.gemm(ao, L["ca_out"]["w"], x, M=rows, N=C, K=C, bias=L["ca_out"]["b"], res=x)
+            # MLP
+            ops.layernorm(x, L["n3_w"], L["n3_b"], t16, 1e-5)
+            ops.gemm(t16, L["l1"]["w"], hid, M=rows, N=2 * C, K=C, bias=L["l1"]["b"], act=ops.ACT_GELU)
+            ops.gemm(hid, L["l2"]["w"], x, M=rows, N=C, K=2 * C, bias=L["l2"]["b"], res=x)
+        out = _empty((rows, C), od, dev)
+        ops.layernorm(x, mb["norm_w"], mb["norm_b"], out, 1e-5)
+        return out
+
+    def _update_memory(self, mb: dict, f3m: torch.Tensor, depth: torch.Tensor, B: int, side: int):
+        """memory_block.py:85-93 + memory_encoder.py:158-181, then one K/V projection of the new entry per attention layer."""
+        dev, od, C, heads = f3m.device, ops.operand_dtype(), mb["C"], mb["heads"]
+        P = side * side
+        rows = B * P
+        H, W = depth.shape[-2:]
+        H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        m1 = _empty((B, H1, W1), torch.float32, dev)
+        ops.mask_down1(depth, mb["md1"], m1, B, H, W)
+        m2 = _empty((B, (H1 - 7) // 7 + 1, (W1 - 7) // 7 + 1), torch.float32, dev)
+        ops.mask_down2(m1, mb["md2"], m2, B, H1, W1)
+        if m2.shape[1] != side or m2.shape[2] != side:
+            raise RuntimeError(f"mask grid {tuple(m2.shape[1:])} does not match the feature grid {side}x{side}")  # memory_encoder.py:173 broadcast
+        x = _empty((rows, C), torch.float32, dev)
+        ops.gemm(f3m, mb["pix_proj"]["w"], x, M=rows, N=C, K=C, bias=mb["pix_proj"]["b"])
+        ops.add_rowscalar(x, m2.view(rows))
+        y16 = _empty((rows, C), od, dev)
+        hid = _empty((rows, 4 * C), od, dev)
+        for Fz in mb["fuser"]:  # ConvNeXt block: x += gamma * pw2(gelu(pw1(LN(dwconv(x)))))
+            ops.dwconv7_ln(x, Fz["dw_w"], Fz["dw_b"], Fz["ln_w"], Fz["ln_b"], y16, B, side, side, C, 1e-6)
+            ops.gemm(y16, Fz["pw1"]["w"], hid, M=rows, N=4 * C, K=C, bias=Fz["pw1"]["b"], act=ops.ACT_GELU)
+            ops.gemm(hid, Fz["pw2"]["w"], x, M=rows, N=C, K=4 * C, bias=Fz["pw2"]["b"], gamma=Fz["gamma"], res=x)
+        ops.cast_f32_to_16(x, y16)
+        if self._mem is None:
+            self._mem = _MemoryState(B, P, C, heads, self.max_memory_length, dev, od)
+        mem = self._mem
+        slot = mem.count % mem.max_len  # ring: the oldest entry is overwritten once the bank is full (memory_bank.py:17-20)
+        cs = rope_table(mb, side, dev)
+        for l, L in enumerate(mb["layers"]):
+            ops.gemm(y16, L["ca_kv_w"], mem.k[l], M=rows, N=2 * C, K=C, bias=L["ca_kv_b"], ldc=C, out2=mem.vT[l], row_map=ops.ROWMAP_QKV_SPLIT,
+                     rm=(P, mem.ld_vT, C, 0), qkv_split=C, qkv_tokens_out=mem.max_len * P, qkv_token_offset=slot * P)
+            ops.rope2d(mem.k[l], rows, C, 0, heads, cs, P, rows_per_batch=P, batch_pitch=mem.max_len * P, ptr_offset=slot * P * C)
+        mem.count += 1
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B, 3, H, H) fp32 -> depth (B, H, H) fp32; reads and then updates the memory bank (depth_anything_v2.py:45-55)."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"expected (B, 3, H, W), got {tuple(x.shape)}")
+        w = self._weights()
+        B, _, H, W = x.shape
+        if H != W:
+            raise RuntimeError("the memory block assumes a square patch grid (memory_block.py:87)")
+        side = H // 14
+        P = side * side
+        if self._mem is not None and (self._mem.B != B or self._mem.P != P):
+            raise RuntimeError("batch size / resolution changed while the memory bank is not empty: call clear_memory() first")
+        x = x.to(device=self._dev, dtype=torch.float32)
+        feats = encoder_forward(w["enc"], x)
+        feats[3] = self._memory_attention(w["mb"], feats[3], B, P, side)
+        depth = head_forward(w["head"], feats, B, side, side, None)  # [B, H, W], already through output_conv2's ReLUs
+        self._update_memory(w["mb"], feats[3], depth, B, side)
+        return depth
+
+    @torch.no_grad()
+    def infer_image(self, raw_image: np.ndarray, input_size: int = 518) -> np.ndarray:
+        """depth_anything_v2.py:57-65: BGR uint8 (H, W, 3) -> float32 depth (H, W)."""
+        import cv2
+        from .video import IMAGENET_MEAN, IMAGENET_STD, _target_size
+        h, w = raw_image.shape[:2]
+        tw, th = _target_size(w, h, input_size)
+        img = cv2.cvtColor(raw_image, cv2.COLOR_BGR2RGB) / 255.0
+        img = cv2.resize(img, (tw, th), interpolation=cv2.INTER_CUBIC)
+        img = (img - IMAGENET_MEAN) / IMAGENET_STD
+        t = torch.from_numpy(np.ascontiguousarray(np.transpose(img, (2, 0, 1))).astype(np.float32)).unsqueeze(0)
+        d = self.forward(t)
+        out = torch.empty((1, h, w), dtype=torch.float32, device=d.device)
+        ops.bilinear_f32(d.contiguous(), out, 1, d.shape[-2], d.shape[-1], h, w)
+        return out[0].cpu().numpy()

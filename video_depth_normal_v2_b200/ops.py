@@ -100,7 +100,7 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: Optional[int] = None, ldw: Optional[int] = None,
          ldc: Optional[int] = None, conv: Optional[Tuple[int, int, int]] = None, bias=None, gamma=None, res=None, ld_res=None, res2=None,
          ld_res2=None, out2=None, out2_relu=False, ld_out2=None, act=ACT_NONE, geglu=False, row_map=ROWMAP_IDENTITY,
-         rm: Sequence[int] = (0, 0, 0, 0), head_w=None, head_b: float = 0.0):
+         rm: Sequence[int] = (0, 0, 0, 0), head_w=None, head_b: float = 0.0, qkv_split: int = 0, qkv_tokens_out: int = 0, qkv_token_offset: int = 0):
     """out = epilogue(A @ W^T) on tcgen05.  See vdn_gemm_desc in include/vdn_b200.h for the field meanings."""
     od = operand_dtype()
     d = GemmDesc()
@@ -134,6 +134,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         d.ld_out2 = ld_out2 if ld_out2 is not None else n_out
     d.act, d.geglu, d.row_map = act, 1 if geglu else 0, row_map
     d.rm0, d.rm1, d.rm2, d.rm3 = [int(v) for v in rm]
+    d.qkv_split, d.qkv_tokens_out, d.qkv_token_offset = int(qkv_split), int(qkv_tokens_out), int(qkv_token_offset)
     if head_w is not None:
         d.head_w = _ptr(head_w, torch.float32, "head_w")
         d.head_b = float(head_b)
@@ -149,6 +150,16 @@ def flash_attn(qk: torch.Tensor, vT: torch.Tensor, out: torch.Tensor, B: int, to
     od = operand_dtype()
     _check(_run("flash_attn", "tensor", 4.0 * B * heads * tokens * tokens * 64, lib().vdn_flash_attn, _ptr(qk, od, "qk"), qk.shape[-1],
                 _ptr(vT, od, "vT"), vT.shape[-1], _ptr(out, od, "out"), B, tokens, heads, _stream()), "vdn_flash_attn")
+    return out
+
+
+def flash_attn_ex(q: torch.Tensor, ld_q: int, q_batch_stride: int, k: torch.Tensor, ld_k: int, k_batch_stride: int, vT: torch.Tensor, ld_vT: int,
+                  out: torch.Tensor, B: int, tokens_q: int, tokens_kv: int, heads: int):
+    """Cross-attention form: q [B, tokens_q, ld_q], k [B, tokens_kv, ld_k] (element strides), V^T [B*heads, 64, ld_vT]."""
+    od = operand_dtype()
+    _check(_run("flash_attn", "tensor", 4.0 * B * heads * tokens_q * tokens_kv * 64, lib().vdn_flash_attn_ex, _ptr(q, od, "q"), ld_q, q_batch_stride,
+                _ptr(k, od, "k"), ld_k, k_batch_stride, _ptr(vT, od, "vT"), ld_vT, _ptr(out, od, "out"), B, tokens_q, tokens_kv, heads, _stream()),
+           "vdn_flash_attn_ex")
     return out
 
 
@@ -279,4 +290,46 @@ def v5_residual(din, o, scale, out, N, H, W, h, w, ws: float, bs: float, max_dep
     _check(_run("v5_residual", "hbm", 8.0 * N * H * W + 4.0 * N * h * w, lib().vdn_v5_residual, _ptr(din, torch.float32, "din"), _ptr(o, torch.float32, "o"),
                 _ptr(scale, torch.float32, "scale"), _ptr(out, torch.float32, "out"), N, H, W, h, w, float(ws), float(bs), float(max_depth), _stream()),
            "vdn_v5_residual")
+    return out
+
+
+def rope2d(x, rows: int, ld: int, col0: int, heads: int, cos_sin, P: int, rows_per_batch: int = 0, batch_pitch: int = 0, ptr_offset: int = 0):
+    """In-place axial RoPE; ``ptr_offset`` (elements) selects a slot of a KV cache whose batches are ``batch_pitch`` rows apart."""
+    base = _ptr(x, operand_dtype(), "x") + 2 * ptr_offset
+    _check(_run("rope2d", "hbm", 4.0 * rows * heads * 64, lib().vdn_rope2d, base, rows, ld, col0, heads, _ptr(cos_sin, torch.float32, "cos_sin"), P,
+                rows_per_batch, batch_pitch, _stream()), "vdn_rope2d")
+    return x
+
+
+def add_rowvec(x, vec, alpha: float, out):
+    rows, C_ = out.shape[0], out.shape[1]
+    _check(_run("add_rowvec", "hbm", (4.0 if x.dtype == torch.float32 else 2.0) * rows * C_ + 4.0 * rows * C_, lib().vdn_add_rowvec, _ptr(x, None, "x"),
+                1 if x.dtype == torch.float32 else 0, _ptr(vec, torch.float32, "vec"), float(alpha), _ptr(out, torch.float32, "out"), rows, C_, _stream()),
+           "vdn_add_rowvec")
+    return out
+
+
+def add_rowscalar(x, m):
+    rows, C_ = x.shape[0], x.shape[1]
+    _check(_run("add_rowscalar", "hbm", 8.0 * rows * C_, lib().vdn_add_rowscalar, _ptr(x, torch.float32, "x"), _ptr(m, torch.float32, "m"), rows, C_, _stream()),
+           "vdn_add_rowscalar")
+    return x
+
+
+def dwconv7_ln(x, w, bias, ln_w, ln_b, out, B, H, W, C_, eps: float):
+    _check(_run("dwconv7_ln", "hbm", 6.0 * B * H * W * C_, lib().vdn_dwconv7_ln, _ptr(x, torch.float32, "x"), _ptr(w, torch.float32, "w"),
+                _ptr(bias, torch.float32, "bias"), _ptr(ln_w, torch.float32, "ln_w"), _ptr(ln_b, torch.float32, "ln_b"), _ptr(out, operand_dtype(), "out"),
+                B, H, W, C_, float(eps), _stream()), "vdn_dwconv7_ln")
+    return out
+
+
+def mask_down1(depth, params, out, B, H, W):
+    _check(lib().vdn_mask_down1(_ptr(depth, torch.float32, "depth"), _ptr(params, torch.float32, "params"), _ptr(out, torch.float32, "out"), B, H, W, _stream()),
+           "vdn_mask_down1")
+    return out
+
+
+def mask_down2(x, params, out, B, Hi, Wi):
+    _check(lib().vdn_mask_down2(_ptr(x, torch.float32, "in"), _ptr(params, torch.float32, "params"), _ptr(out, torch.float32, "out"), B, Hi, Wi, _stream()),
+           "vdn_mask_down2")
     return out
