@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--operands", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--da2-batch", type=int, default=16, help="batch of the DepthAnythingV2 ViT-L 518x518 measurement (BASELINE configs[1]); 0 = skip")
     ap.add_argument("--lv-windows", type=int, default=6, help="windows per GPU of the long-video (sharded infer_video_depth) measurement; 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -279,6 +280,36 @@ def main():
                               "feature reuse for the 10 overlap slots, temporal head on all 32 slots, device-side scale/shift chain + cross-fade, "
                               "NCCL boundary exchange + gather when n_gpus > 1, D2H of all output frames"}
 
+    # ---------------- BASELINE configs[1]: DepthAnythingV2 ViT-L, single images 518x518, batch 16, stateful memory bank ----------------
+    da2 = None
+    if args.da2_batch > 0:
+        from video_depth_normal_v2_b200 import DepthAnythingV2
+        from oracle.init_recipe import make_state_dict  # weights only (seeded recipe); the oracle itself is not called here
+        m2 = DepthAnythingV2(encoder=ENCODER, features=FEATURES, out_channels=OUT_CHANNELS).to(dev).eval()
+        m2.load_state_dict(make_state_dict("da2", ENCODER, 0))
+        xb = torch.randn((args.da2_batch, 3, SIZE, SIZE), generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+        m2(xb)                      # call 0: empty bank
+        barrier()
+        e0.record(); m2(xb); e1.record()
+        barrier()
+        first_ms = max_over_ranks(e0.elapsed_time(e1))
+        for _ in range(6):          # fill the bank (6 entries): steady state
+            m2(xb)
+        barrier()
+        n_da2 = max(3, args.steps // 4)
+        e0.record()
+        for _ in range(n_da2):
+            m2(xb)
+        e1.record()
+        barrier()
+        da2_ms = max_over_ranks(e0.elapsed_time(e1)) / n_da2
+        da2 = {"value": world * args.da2_batch / (da2_ms / 1e3), "unit": "frames/s", "batch": args.da2_batch, "ms_per_call_full_bank": da2_ms,
+               "ms_per_call_one_entry": first_ms, "gflop_per_frame_reference_equivalent": 1820.9,
+               "tensor_frac": 1820.9e9 * args.da2_batch / (da2_ms / 1e3) / 1e12 / _peaks()["tflops"],
+               "note": "DepthAnythingV2 (memory-block fork) ViT-L 518x518, device-resident batch, steady state with a full 6-entry memory bank"}
+        del m2, xb
+        torch.cuda.empty_cache()
+
     # ---------------- live per-kernel timing (CUDA events on the launching stream), extra instrumented steps ----------------
     prof = ops.KernelProfiler()
     ops.set_profiler(prof)
@@ -328,7 +359,7 @@ def main():
                    "frames_per_step_per_gpu": FRAMES, "tokens_per_frame": 1370, "parallelism": f"window-sharded x{world}, no data-path collective",
                    "l2": "activations per step (>2 GB) exceed the 126 MB L2, no explicit flush", "operands": args.operands + " (fp32 accumulate, fp32 residual stream)"},
         "tensor_frac_of_step": (GFLOP_PER_FRAME * 1e9 * FRAMES / (ms_per_step / 1e3)) / 1e12 / peaks["tflops"],
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "long_video": long_video, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "long_video": long_video, "da2_batch16": da2, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
