@@ -95,6 +95,10 @@ int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_stride, const
  * TemporalAttention.forward (motion_module.py:296-313).  qkv: [D*T, 3C] rows (d, f), q|k|v column blocks.
  * out: [D*T, C].  head_dim = C/heads (any multiple of 8).                                              */
 int vdn_temporal_attn(const void* qkv, void* out, int32_t D, int32_t T, int32_t C, int32_t heads, void* stream);
+/* tcgen05 form for T == 32 frames, head_dim 32 / 64 / 128: qk [rows, ld_qk] = q | k (rows = (pixel, frame), 32 consecutive rows per
+   pixel), vT [ceil(rows/128), C, 128] = V transposed per 128-row tile (vdn_gemm with VDN_ROWMAP_QKV_SPLIT, rm0 = rm1 = 128; must be
+   zero beyond the last valid row), out [rows, C] */
+int vdn_temporal_attn_tc(const void* qk, int64_t ld_qk, const void* vT, void* out, int64_t rows, int32_t C, int32_t heads, void* stream);
 
 /* ---- normalisation ----------------------------------------------------------------------------- */
 /* LayerNorm over C of fp32 rows -> 16-bit.  out row = map(row):

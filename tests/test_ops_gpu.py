@@ -227,6 +227,28 @@ def test_temporal_attention(ops, D, T, C):
     _close(f"temporal attn D{D} T{T} C{C}", out, ref)
 
 
+@pytest.mark.parametrize("D,C", [(37, 1024), (1369, 256), (5, 512), (361, 1024), (130, 256)])
+def test_temporal_attention_tcgen05(ops, D, C):
+    """T = 32 fast path: fused q|k|v projection writing V^T per 128-row tile (QKV-split epilogue), then the tcgen05 kernel."""
+    od = ops.operand_dtype()
+    T, heads = 32, 8
+    rows = D * T
+    x = _r16(ops, rows, C, seed=1)
+    w = _r16(ops, 3 * C, C, scale=C ** -0.5, seed=2)
+    qk = torch.empty(rows, 2 * C, device="cuda", dtype=od)
+    ntiles = (rows + 127) // 128
+    vT = torch.zeros(ntiles * C, 128, device="cuda", dtype=od)
+    ops.gemm(x, w, qk, M=rows, N=3 * C, K=C, ldc=2 * C, out2=vT, row_map=ops.ROWMAP_QKV_SPLIT, rm=(128, 128, C, 0))
+    out = torch.empty(rows, C, device="cuda", dtype=od)
+    ops.temporal_attn_tc(qk, vT, out, rows, C, heads)
+    torch.cuda.synchronize()
+    dh = C // heads
+    qkv = (x.float() @ w.float().T).to(od)  # the projection rounds to 16 bits before the attention, as in the product
+    q, k, v = [t.float().reshape(D, T, heads, dh).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+    ref = ((q @ k.transpose(-1, -2) * dh ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(rows, C)
+    _close(f"temporal attn tcgen05 D{D} C{C}", out, ref, rtol=5e-3, atol_frac=3e-3)
+
+
 # ----------------------------------------------------------------------------------------------- norms / layout
 @pytest.mark.parametrize("rows,C", [(1370 * 2, 384), (1000, 1024), (77, 64), (300, 192), (64, 256)])
 def test_layernorm(ops, rows, C):

@@ -400,6 +400,239 @@ temporal_attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int D, int 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// temporal attention on tcgen05 (T == 32 frames, head_dim 32 / 64 / 128)
+// ------------------------------------------------------------------------------------------------
+// A tile is 128 consecutive rows of the pixel-major sequence = 4 pixels x 32 frames.  S = Q K^T is computed for the whole
+// 128 x 128 tile (4x the needed FLOPs — irrelevant, the op is HBM-bound at 8 bytes per token-channel) and only its four
+// 32 x 32 diagonal blocks are kept: warp w owns rows 32w..32w+31 and reads exactly columns 32w..32w+31 of S from TMEM,
+// normalises them and writes them to its 16 packed columns of the block-diagonal P operand (all other columns stay zero);
+// O = P V then runs as a TS-mode MMA against V^T (produced transposed per tile by the QKV GEMM epilogue).
+// Persistent CTAs, 2-stage TMA ring: the loads of unit i+1 run under the MMAs / softmax / stores of unit i.
+constexpr int TT_THREADS = 192;  // 4 softmax warps, MMA issuer, TMA producer
+
+template <int DH, int FMT>
+__global__ void __launch_bounds__(TT_THREADS, 1)
+temporal_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT, void* __restrict__ out, long long rows,
+                        int C, int num_tiles) {
+  constexpr int CU = DH < 64 ? 64 : DH;        // channels per work unit (one 64-column TMA box minimum)
+  constexpr int HPU = CU / DH;                 // heads per unit (2 for head_dim 32)
+  constexpr int NB = CU / 64;                  // 64-column boxes per unit
+  constexpr int QBYTES = NB * 128 * 128;       // Q (and K) bytes per stage
+  constexpr int VBYTES = 2 * CU * 128;         // V^T: two 64-key chunks of [CU rows x 128 B]
+  constexpr int STAGE = 2 * QBYTES + VBYTES;
+  constexpr uint32_t S_COL = 0, P_COL = HPU * 128, O_COL = HPU * 128 + HPU * 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
+  uint64_t* full = bars;        // [2]
+  uint64_t* empty = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_full = bars + 5;
+  uint64_t* o_full = bars + 6;
+  uint64_t* o_free = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units_per_tile = C / CU;
+  const long long num_units = (long long)num_tiles * units_per_tile;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp_idx == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQK);
+      tma_prefetch_desc(&tmVT);
+      mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+      mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+      mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(o_free, 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 5) {
+    // ---------------- TMA producer ----------------
+    int it = 0;
+    for (long long u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int tile = int(u / units_per_tile), cu = int(u % units_per_tile);
+      mbar_wait(&empty[st], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* sQ = smem + st * STAGE;
+        uint8_t* sK = sQ + QBYTES;
+        uint8_t* sV = sK + QBYTES;
+        mbar_arrive_expect_tx(&full[st], STAGE);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          tma_load_2d(sQ + b * 16384, &tmQK, &full[st], cu * CU + b * 64, tile * 128);
+          tma_load_2d(sK + b * 16384, &tmQK, &full[st], C + cu * CU + b * 64, tile * 128);
+        }
+        tma_load_3d(sV, &tmVT, &full[st], 0, cu * CU, tile);
+        tma_load_3d(sV + CU * 128, &tmVT, &full[st], 64, cu * CU, tile);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx == 4) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, 128);
+    constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, DH);
+    const uint32_t smem_addr = smem_u32(smem);
+    auto issue_s = [&](int st) {
+      if (elect_one()) {
+        const uint32_t q_addr = smem_addr + st * STAGE, k_addr = q_addr + QBYTES;
+#pragma unroll
+        for (int hh = 0; hh < HPU; ++hh) {
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {
+            const int col = hh * DH + kk * 16;  // column inside the unit
+            const uint64_t dq = make_sdesc_sw128(q_addr + (col >> 6) * 16384) + 2 * ((col & 63) >> 4);
+            const uint64_t dk = make_sdesc_sw128(k_addr + (col >> 6) * 16384) + 2 * ((col & 63) >> 4);
+            umma_f16(tb + S_COL + hh * 128, dq, dk, idesc_s, kk != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    int it = 0;
+    const long long first = blockIdx.x;
+    if (first < num_units) {
+      mbar_wait(&full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+    }
+    for (long long u = first; u < num_units; u += gridDim.x, ++it) {
+      const int st = it & 1;
+      mbar_wait(p_full, it & 1);                     // P(it) written, S(it) consumed
+      if (it > 0) mbar_wait(o_free, (it - 1) & 1);   // O(it-1) drained by the epilogue
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t v_addr = smem_addr + st * STAGE + 2 * QBYTES;
+#pragma unroll
+        for (int hh = 0; hh < HPU; ++hh) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {  // 128 keys, 16 per MMA; B = V^T rows [hh*DH, +DH) of chunk kk >> 2
+            const uint64_t dv = make_sdesc_sw128(v_addr + (kk >> 2) * (CU * 128) + hh * DH * 128) + 2 * (kk & 3);
+            umma_f16_ts(tb + O_COL + hh * DH, tb + P_COL + hh * 64 + kk * 8, dv, idesc_pv, kk != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(o_full);
+        umma_commit(&empty[st]);
+      }
+      __syncwarp();
+      if (u + gridDim.x < num_units) {  // S of the next unit runs under this unit's epilogue
+        const int it2 = it + 1;
+        mbar_wait(&full[it2 & 1], (it2 >> 1) & 1);
+        tc_fence_after();
+        issue_s(it2 & 1);
+      }
+    }
+  } else {
+    // ---------------- softmax + output warps ----------------
+    const uint32_t lane_off = uint32_t(warp_idx * 32) << 16;
+    const int r = warp_idx * 32 + lane;
+    const float sc = rsqrtf((float)DH) * 1.4426950408889634f;
+    // zero the P operand once: every warp only ever rewrites its own diagonal block
+    {
+      uint32_t z[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) z[i] = 0u;
+#pragma unroll
+      for (int c = 0; c < HPU * 2; ++c) tmem_st32(tmem_base + P_COL + lane_off + c * 32, z);
+      tmem_st_wait();
+    }
+    int it = 0;
+    for (long long u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+      const int tile = int(u / units_per_tile), cu = int(u % units_per_tile);
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < HPU; ++hh) {
+        uint32_t sv[32];
+        tmem_ld32(tmem_base + S_COL + hh * 128 + lane_off + warp_idx * 32, sv);  // this row's 32 keys = its own pixel's frames
+        tmem_ld_wait();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        mx *= sc;
+        float p[32], sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          p[i] = ex2_approx(fmaf(__uint_as_float(sv[i]), sc, -mx));
+          sum += p[i];
+        }
+        const float inv = 1.0f / sum;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = T16f<FMT>::pack(p[2 * i] * inv, p[2 * i + 1] * inv);
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+                tmem_base + P_COL + hh * 64 + lane_off + warp_idx * 16),
+            "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]), "r"(pk[10]),
+            "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+            : "memory");
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // output: O [128 x CU] fp32 in TMEM -> 16-bit rows of `out`
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      const long long row = (long long)tile * 128 + r;
+      uint16_t* o = reinterpret_cast<uint16_t*>(out) + row * C + cu * CU;
+#pragma unroll
+      for (int c = 0; c < CU / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + O_COL + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (row < rows) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 q4;
+            q4.x = T16f<FMT>::pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            q4.y = T16f<FMT>::pack(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            q4.z = T16f<FMT>::pack(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+            q4.w = T16f<FMT>::pack(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+            *reinterpret_cast<uint4*>(o + c * 32 + i) = q4;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int DH, int FMT>
+static int launch_temporal_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVT, void* out, long long rows, int C, int num_tiles, cudaStream_t stream) {
+  constexpr int CU = DH < 64 ? 64 : DH;
+  constexpr int STAGE = 2 * (CU / 64) * 16384 + 2 * CU * 128;
+  constexpr int SMEM = 2 * STAGE + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_tc_kernel<DH, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(temporal_attn_tc): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long units = (long long)num_tiles * (C / CU);
+  const int grid = units < num_sms() ? (int)units : num_sms();
+  temporal_attn_tc_kernel<DH, FMT><<<grid, TT_THREADS, SMEM, stream>>>(tmQK, tmVT, out, rows, C, num_tiles);
+  count_launch();
+  return check_launch("temporal_attn_tc_kernel");
+}
+
 }  // namespace vdn
 
 using namespace vdn;
@@ -457,6 +690,37 @@ extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int
   if (ld_qk < 2 * C) return set_error("vdn_flash_attn: ld_qk must be >= 2*C and 16-byte aligned");
   const uint16_t* base = reinterpret_cast<const uint16_t*>(qk);
   return vdn_flash_attn_ex(base, ld_qk, (int64_t)tokens * ld_qk, base + C, ld_qk, (int64_t)tokens * ld_qk, vT, ld_vT, out, B, tokens, tokens, heads, stream_v);
+}
+
+extern "C" int vdn_temporal_attn_tc(const void* qk, int64_t ld_qk, const void* vT, void* out, int64_t rows, int32_t C, int32_t heads, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!qk || !vT || !out) return set_error("vdn_temporal_attn_tc: null pointer");
+  if (rows <= 0 || rows % 32 != 0 || heads <= 0 || C % heads != 0) return set_error("vdn_temporal_attn_tc: rows must be a multiple of T = 32");
+  const int dh = C / heads;
+  if (dh != 32 && dh != 64 && dh != 128) return set_error("vdn_temporal_attn_tc: head_dim must be 32, 64 or 128");
+  if (C % 64 != 0 || ld_qk < 2 * C || (ld_qk * 2) % 16 != 0) return set_error("vdn_temporal_attn_tc: bad C / ld_qk");
+  const int fmt = get_operand_format();
+  const int num_tiles = (int)((rows + 127) / 128);
+  CUtensorMap tmQK, tmVT;
+  {
+    const uint64_t dims[2] = {(uint64_t)(2 * C), (uint64_t)rows};
+    const uint64_t strides[1] = {(uint64_t)ld_qk * 2};
+    const uint32_t box[2] = {64u, 128u};
+    if (make_tensor_map(&tmQK, qk, fmt, 2, dims, strides, box)) return 1;
+  }
+  {
+    // V^T per tile: [tile][channel][128 keys]; innermost first: key, channel, tile
+    const int cu = dh < 64 ? 64 : dh;
+    const uint64_t dims[3] = {128u, (uint64_t)C, (uint64_t)num_tiles};
+    const uint64_t strides[2] = {256u, (uint64_t)C * 256u};
+    const uint32_t box[3] = {64u, (uint32_t)cu, 1u};
+    if (make_tensor_map(&tmVT, vT, fmt, 3, dims, strides, box)) return 1;
+  }
+#define VDN_TT(DH) (fmt ? launch_temporal_tc<DH, 1>(tmQK, tmVT, out, rows, C, num_tiles, stream) : launch_temporal_tc<DH, 0>(tmQK, tmVT, out, rows, C, num_tiles, stream))
+  if (dh == 32) return VDN_TT(32);
+  if (dh == 64) return VDN_TT(64);
+  return VDN_TT(128);
+#undef VDN_TT
 }
 
 extern "C" int vdn_temporal_attn(const void* qkv, void* out, int32_t D, int32_t T, int32_t C, int32_t heads, void* stream_v) {

@@ -92,12 +92,26 @@ def motion_module_forward(mm: dict, x: torch.Tensor, Bv: int, T: int, D: int, re
     h = _empty((rows, C), torch.float32, dev)  # fp32 hidden state, pixel-major rows (b*D+d)*T+f
     ops.gemm(xt, mm["proj_in"]["w"], h, M=rows, N=C, K=C, bias=mm["proj_in"]["b"])
     n16 = xt  # reuse
-    qkv = _empty((rows, 3 * C), od, dev)
     ao = _empty((rows, C), od, dev)
+    # T == 32 with head_dim 32 / 64 / 128 (ViT-L) runs on the tcgen05 kernel: the fused q|k|v projection writes q|k row-major
+    # and V transposed per 128-row tile (4 pixels x 32 frames); other shapes (ViT-S heads, short clips) take the CUDA-core kernel
+    tc = T == 32 and (C // 8) in (32, 64, 128)
+    if tc:
+        qk = _empty((rows, 2 * C), od, dev)
+        key = ("vT", rows, od)
+        if key not in mm:  # zero beyond the last valid row of the last tile, written only inside the valid rows afterwards
+            mm[key] = torch.zeros(((rows + 127) // 128 * C, 128), dtype=od, device=dev)
+        vT = mm[key]
+    else:
+        qkv = _empty((rows, 3 * C), od, dev)
     for a in mm["attn"]:
         ops.layernorm(h, a["ln_w"], a["ln_b"], n16, 1e-5, pe=a["pe"][:T])
-        ops.gemm(n16, a["qkv_w"], qkv, M=rows, N=3 * C, K=C)
-        ops.temporal_attn(qkv, ao, Bv * D, T, C, 8)
+        if tc:
+            ops.gemm(n16, a["qkv_w"], qk, M=rows, N=3 * C, K=C, ldc=2 * C, out2=vT, row_map=ops.ROWMAP_QKV_SPLIT, rm=(128, 128, C, 0))
+            ops.temporal_attn_tc(qk, vT, ao, rows, C, 8)
+        else:
+            ops.gemm(n16, a["qkv_w"], qkv, M=rows, N=3 * C, K=C)
+            ops.temporal_attn(qkv, ao, Bv * D, T, C, 8)
         ops.gemm(ao, a["out"]["w"], h, M=rows, N=C, K=C, bias=a["out"]["b"], res=h)
     ops.layernorm(h, mm["ffn_w"], mm["ffn_b"], n16, 1e-5)
     g = _empty((rows, 4 * C), od, dev)

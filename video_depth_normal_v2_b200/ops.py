@@ -170,6 +170,13 @@ def temporal_attn(qkv: torch.Tensor, out: torch.Tensor, D: int, T: int, C_: int,
     return out
 
 
+def temporal_attn_tc(qk: torch.Tensor, vT: torch.Tensor, out: torch.Tensor, rows: int, C_: int, heads: int):
+    od = operand_dtype()
+    _check(_run("temporal_attn", "hbm", 8.0 * rows * C_, lib().vdn_temporal_attn_tc, _ptr(qk, od, "qk"), qk.shape[-1], _ptr(vT, od, "vT"),
+                _ptr(out, od, "out"), rows, C_, heads, _stream()), "vdn_temporal_attn_tc")
+    return out
+
+
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor, eps: float, drop_first: bool = False, rows_per_batch: int = 0,
               pe: Optional[torch.Tensor] = None):
     rows, C_ = x.shape[0], x.shape[1]
