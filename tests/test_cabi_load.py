@@ -62,3 +62,15 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.load()
+
+
+def test_torch_ops_are_registered_and_cuda_only():
+    """The kernels are exposed as torch.ops.vdn.* (SURVEY.md §8b); no CPU implementation exists, so CPU tensors raise."""
+    import torch
+    import video_depth_normal_v2_b200 as pkg
+    for name in pkg.torch_ops.REGISTERED:
+        assert hasattr(torch.ops.vdn, name), name
+    x = torch.zeros(4, 8)
+    import pytest
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.vdn.layernorm(x, torch.ones(8), torch.zeros(8), torch.empty(4, 8, dtype=torch.float16), 1e-6)

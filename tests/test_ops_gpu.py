@@ -410,3 +410,18 @@ def test_bf16_operand_mode(ops):
         _close("gemm bf16", out, a.float() @ w.float().T, rtol=1e-2, atol_frac=8e-3)
     finally:
         ops.set_operand_dtype(torch.float16)
+
+
+def test_torch_ops_dispatch_to_the_kernels(ops):
+    """torch.ops.vdn.* run the same kernels as the ctypes wrappers."""
+    od = ops.operand_dtype()
+    a, w, b = _r16(ops, 300, 192, seed=1), _r16(ops, 256, 192, scale=192 ** -0.5, seed=2), _f32(256, seed=3)
+    out = torch.empty(300, 256, device="cuda", dtype=od)
+    ops.reset_launch_count()
+    torch.ops.vdn.linear(a, w, out, b)
+    assert ops.launch_count() == 1
+    _close("torch.ops.vdn.linear", out, a.float() @ w.float().T + b)
+    x = _f32(100, 384, seed=4)
+    o2 = torch.empty(100, 384, device="cuda", dtype=od)
+    torch.ops.vdn.layernorm(x, torch.ones(384, device="cuda"), torch.zeros(384, device="cuda"), o2, 1e-6)
+    _close("torch.ops.vdn.layernorm", o2, F.layer_norm(x, (384,), eps=1e-6))

@@ -5,6 +5,7 @@ Host code is Python; every device kernel lives in the in-tree C-ABI library ``li
 (``include/vdn_b200.h``).  There is no CPU fallback: using the ops without the built library raises.
 """
 from . import ops  # noqa: F401
+from . import torch_ops  # noqa: F401  (registers torch.ops.vdn.*)
 
 _LAZY = {"VideoDepthAnything": "models", "VideoDepthRefinerV5": "models", "ENCODER_CONFIGS": "models", "DepthAnythingV2": "da2"}
 
