@@ -27,6 +27,8 @@ int vdn_get_operand_format(void);
 /* number of kernel launches issued by this library since the last reset (bench.py "gpu_launches"). */
 int64_t vdn_launch_count(void);
 void vdn_reset_launch_count(void);
+/* account for kernels launched by replaying a CUDA graph that captured n of this library's launches */
+void vdn_add_launch_count(int64_t n);
 
 /* ---- tcgen05 GEMM / implicit-GEMM convolution with fused epilogue ---------------------------
  * out = epilogue( A[M,K] * W[N,K]^T ), fp32 accumulation in TMEM.

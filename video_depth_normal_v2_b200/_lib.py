@@ -37,6 +37,7 @@ SIGNATURES = {
     "vdn_get_operand_format": (c_int, []),
     "vdn_launch_count": (c_int64, []),
     "vdn_reset_launch_count": (None, []),
+    "vdn_add_launch_count": (None, [c_int64]),
     "vdn_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "vdn_flash_attn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdn_flash_attn_ex": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -95,4 +95,5 @@ int vdn_set_operand_format(int fmt) {
 int vdn_get_operand_format(void) { return vdn::g_fmt.load(); }
 int64_t vdn_launch_count(void) { return vdn::g_launches.load(); }
 void vdn_reset_launch_count(void) { vdn::g_launches.store(0); }
+void vdn_add_launch_count(int64_t n) { vdn::g_launches.fetch_add(n, std::memory_order_relaxed); }
 }

@@ -13,6 +13,8 @@ from __future__ import annotations
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -34,6 +36,46 @@ INTERP_LEN = 8
 
 def _empty(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
+
+
+class GraphRunner:
+    """Replays a fixed-shape kernel sequence as one CUDA graph.  A forward is ~270 launches of which ~150 are short head /
+    motion-module kernels: launched one by one from Python the GPU idles between them (~5 ms of a 59 ms ViT-L window); the
+    sequence is static for a given input shape (tensor maps are baked into the kernel parameters), so it is captured once —
+    first call eager (fills the weight / pos-embed / workspace caches), second call captured, later calls replayed.
+    ``fn(*static_inputs) -> tensor or list of tensors``; results live in graph-owned buffers that the next replay overwrites."""
+
+    enabled = os.environ.get("VDN_NO_GRAPHS", "0") != "1"
+
+    def __init__(self):
+        self.entries = {}
+
+    def clear(self):
+        self.entries.clear()
+
+    def run(self, key, fn, inputs):
+        if not GraphRunner.enabled or ops._profiler is not None or torch.cuda.is_current_stream_capturing():
+            return fn(*inputs)
+        e = self.entries.get(key)
+        if e is None:
+            self.entries[key] = {"calls": 1}
+            return fn(*inputs)
+        if "graph" not in e:
+            static_in = [torch.empty_like(t) for t in inputs]
+            for s_, t in zip(static_in, inputs):
+                s_.copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                out = fn(*static_in)
+            e.update(graph=g, inputs=static_in, out=out, launches=ops.launch_count() - n0)
+            ops.lib().vdn_add_launch_count(-e["launches"])  # capture issued no work; every replay (below) counts them
+        for s_, t in zip(e["inputs"], inputs):
+            s_.copy_(t, non_blocking=True)
+        e["graph"].replay()
+        ops.lib().vdn_add_launch_count(e["launches"])
+        return e["out"]
 
 
 # ======================================================================================================
@@ -240,6 +282,7 @@ class _PackedModule(nn.Module):
         self._packed: Optional[dict] = None
         self._packed_key = None
         self._dev = torch.device("cpu")
+        self._graphs = GraphRunner()
 
     # --- nn.Module surface the reference callers use -----------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True):
@@ -274,6 +317,7 @@ class _PackedModule(nn.Module):
                 raise RuntimeError("no weights loaded: call load_state_dict() with a reference-format state_dict")
             self._packed = self._pack(self._sd, self._dev, ops.operand_dtype())
             self._packed_key = key
+            self._graphs.clear()  # captured graphs hold pointers into the old packed weights
         return self._packed
 
     def _expected_shapes(self) -> Dict[str, tuple]:
@@ -377,12 +421,19 @@ class VideoDepthAnything(_PackedModule):
         B, T, _, H, W = x.shape
         if T > 32:
             raise RuntimeError("temporal attention supports at most 32 frames per window")
-        x = x.to(device=self._dev, dtype=torch.float32)
         ph, pw = H // 14, W // 14
-        feats = encoder_forward(w["enc"], x.reshape(B * T, 3, H, W))
-        depth = head_forward(w["head"], feats, B * T, ph, pw, T)
-        # F.interpolate(depth, (H, W), align_corners=True) is the identity here (H == 14*ph) and the head's output is already >= 0
-        return depth.view(B, T, H, W)
+
+        def run(xd):
+            feats = encoder_forward(w["enc"], xd.reshape(B * T, 3, H, W))
+            # F.interpolate(depth, (H, W), align_corners=True) is the identity here (H == 14*ph) and the head's output is already >= 0
+            return head_forward(w["head"], feats, B * T, ph, pw, T)
+
+        if x.device != self._dev or x.dtype != torch.float32:
+            xs = torch.empty(x.shape, dtype=torch.float32, device=self._dev)
+            xs.copy_(x, non_blocking=True)  # H2D straight from (pinned) host memory
+            x = xs
+        depth = self._graphs.run(("forward", B, T, H, W), run, [x.contiguous()])
+        return depth.view(B, T, H, W).clone()  # the graph's output buffer is overwritten by the next call
 
     # --- the two halves of forward(), exposed for the long-video driver: the encoder is per-frame (dinov2.py:212-321 has no
     # cross-frame op), so the features of the 10 key frames a window shares with its predecessor are computed once.
@@ -390,7 +441,9 @@ class VideoDepthAnything(_PackedModule):
     def encode_frames(self, x: torch.Tensor) -> List[torch.Tensor]:
         """x (F, 3, H, W) fp32 -> 4 x [F*ph*pw, C] tapped, final-norm'ed patch tokens (frame-major)."""
         w = self._weights()
-        return encoder_forward(w["enc"], x.to(device=self._dev, dtype=torch.float32))
+        x = x.to(device=self._dev, dtype=torch.float32).contiguous()
+        feats = self._graphs.run(("encode",) + tuple(x.shape), lambda xd: encoder_forward(w["enc"], xd), [x])
+        return [f.clone() for f in feats]  # the long-video driver keeps per-frame views of these across windows
 
     @torch.no_grad()
     def head_from_features(self, feats: List[torch.Tensor], T: int, ph: int, pw: int) -> torch.Tensor:
@@ -398,7 +451,7 @@ class VideoDepthAnything(_PackedModule):
         w = self._weights()
         if T > 32:
             raise RuntimeError("temporal attention supports at most 32 frames per window")
-        return head_forward(w["head"], feats, T, ph, pw, T)
+        return self._graphs.run(("head", T, ph, pw), lambda *f: head_forward(w["head"], list(f), T, ph, pw, T), [f.contiguous() for f in feats]).clone()
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
