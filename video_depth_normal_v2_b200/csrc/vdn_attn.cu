@@ -45,7 +45,7 @@ constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_
 template <int FMT>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVT,
-                  void* __restrict__ out, int tokens, int tokens_kv, int heads, int C) {
+                  void* __restrict__ out, int tokens, int tokens_kv, int heads, int C, int num_units) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                      // [group]
   uint8_t* sK = smem + 2 * FA_TILE;        // [stage]
@@ -60,16 +60,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* s_free = bars + 11;   // [group]
   uint64_t* p_full = bars + 13;   // [group]
   uint64_t* pv_done = bars + 15;  // [group]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* o_free = bars + 17;   // [group]
+  uint64_t* q_empty = bars + 19;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
   const int nt = (tokens_kv + FA_BN - 1) / FA_BN;  // KV tiles (cross-attention: tokens_kv != tokens)
-  const int q_tile0 = blockIdx.x * FA_GROUPS;
-  const bool two = (q_tile0 + 1) * FA_BM < tokens;  // the second query tile exists
-  const int ngroups = two ? 2 : 1;
+  const int nq_tiles = (tokens + FA_BM - 1) / FA_BM;
+  const int nqp = (nq_tiles + FA_GROUPS - 1) / FA_GROUPS;  // query-tile pairs per (frame, head)
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1024-byte alignment
 
@@ -79,6 +78,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmVT);
       mbar_init(q_full, 1);
+      mbar_init(q_empty, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&k_full[i], 1);
         mbar_init(&k_empty[i], 1);
@@ -88,6 +88,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_init(&s_free[i], 128);
         mbar_init(&p_full[i], 128);
         mbar_init(&pv_done[i], 1);
+        mbar_init(&o_free[i], 128);
       }
       fence_barrier_init();
     }
@@ -99,33 +100,43 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // Registers are allocated per warpgroup: the control warpgroup gives most of its share to the two softmax warpgroups,
-  // whose threads each hold a whole 128-key score row (12 warps x 168 = 8 x 232 + 4 x 40 registers per lane).
+  // Persistent CTA: work unit u = (query-tile pair, head, frame); TMEM, barriers and the K / V rings live across units, so
+  // the producer prefetches the next unit's Q / K / V under the current unit's last tiles and output stores (one CTA per SM:
+  // a per-unit launch would expose ~3 us of allocation + first-load latency 21 times per SM).  All barrier parities come from
+  // running counters.  Registers are allocated per warpgroup: the control warpgroup gives most of its share to the two softmax
+  // warpgroups, whose threads each hold a whole 128-key score row (12 warps x 168 = 8 x 232 + 4 x 40 registers per lane).
   if (warp_idx >= 8) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
   if (warp_idx == 9) {
     // ---------------- TMA producer (warp-uniform control flow, one elected lane issues) ----------------
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, ngroups * FA_TILE);
-      for (int g = 0; g < ngroups; ++g) tma_load_4d(sQ + g * FA_TILE, &tmQ, q_full, 0, h, (q_tile0 + g) * FA_BM, b);
-    }
-    __syncwarp();
-    for (int j = 0; j < nt; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&k_empty[st], ph ^ 1);
+    int kvc = 0, ui = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+      const int qp = u % nqp, h = (u / nqp) % heads, b = u / (nqp * heads);
+      const int q_tile0 = qp * FA_GROUPS;
+      const int ngroups = (q_tile0 + 1) * FA_BM < tokens ? 2 : 1;
+      if (ui > 0) mbar_wait(q_empty, (ui - 1) & 1);  // every S MMA of the previous unit has read its Q tiles
       if (elect_one()) {
-        mbar_arrive_expect_tx(&k_full[st], FA_TILE);
-        tma_load_4d(sK + st * FA_TILE, &tmK, &k_full[st], 0, h, j * FA_BN, b);
+        mbar_arrive_expect_tx(q_full, ngroups * FA_TILE);
+        for (int g = 0; g < ngroups; ++g) tma_load_4d(sQ + g * FA_TILE, &tmQ, q_full, 0, h, (q_tile0 + g) * FA_BM, b);
       }
       __syncwarp();
-      mbar_wait(&v_empty[st], ph ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&v_full[st], FA_TILE);
-        tma_load_3d(sV + st * FA_TILE, &tmVT, &v_full[st], j * FA_BN, 0, b * heads + h);
-        tma_load_3d(sV + st * FA_TILE + FA_TILE / 2, &tmVT, &v_full[st], j * FA_BN + 64, 0, b * heads + h);
+      for (int j = 0; j < nt; ++j, ++kvc) {
+        const int st = kvc & 1;
+        const uint32_t ph = (kvc >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], FA_TILE);
+          tma_load_4d(sK + st * FA_TILE, &tmK, &k_full[st], 0, h, j * FA_BN, b);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], FA_TILE);
+          tma_load_3d(sV + st * FA_TILE, &tmVT, &v_full[st], j * FA_BN, 0, b * heads + h);
+          tma_load_3d(sV + st * FA_TILE + FA_TILE / 2, &tmVT, &v_full[st], j * FA_BN + 64, 0, b * heads + h);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp_idx == 8) {
     // ---------------- MMA issuer ----------------
@@ -135,169 +146,187 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, 128);
     constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, 64);
     const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-    auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T
-      if (elect_one()) {
-        const uint64_t dq = make_sdesc_sw128(q_addr + g * FA_TILE);
-        const uint64_t dk = make_sdesc_sw128(k_addr + (j & 1) * FA_TILE);
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tb + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&s_full[g]);
-        if (g == ngroups - 1) umma_commit(&k_empty[j & 1]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    // prologue: S(0) and S(1) of both groups (each group's S buffer is refilled as soon as the group has pulled it into registers)
-    for (int j = 0; j < 2 && j < nt; ++j) {
-      mbar_wait(&k_full[j], 0);
-      for (int g = 0; g < ngroups; ++g) {
-        if (j > 0) mbar_wait(&s_free[g], 0);
-        tc_fence_after();
-        issue_s(g, j);
-      }
-    }
-    for (int j = 0; j < nt; ++j) {
-      const int st = j & 1;
-      for (int g = 0; g < ngroups; ++g) {
-        mbar_wait(&p_full[g], j & 1);
-        if (g == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
+    int kv0 = 0, ui = 0;
+    int si[2] = {0, 0};  // S tiles issued per group (global): S tile n may overwrite the buffer once tile n-1 was pulled into registers
+    int pi[2] = {0, 0};  // PV tiles issued per group (global)
+    int ug[2] = {0, 0};  // units processed per group
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+      const int qp = u % nqp;
+      const int ngroups = (qp * FA_GROUPS + 1) * FA_BM < tokens ? 2 : 1;
+      auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T
+        const int kst = (kv0 + j) & 1;
+        if (si[g] > 0) mbar_wait(&s_free[g], (si[g] - 1) & 1);
+        if (g == 0) mbar_wait(&k_full[kst], ((kv0 + j) >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t dv0 = make_sdesc_sw128(v_addr + st * FA_TILE);
+          const uint64_t dq = make_sdesc_sw128(q_addr + g * FA_TILE);
+          const uint64_t dk = make_sdesc_sw128(k_addr + kst * FA_TILE);
 #pragma unroll
-          for (int kk = 0; kk < FA_BN / 16; ++kk) {
-            // B = V^T chunk (kk >> 2), 16 keys further per MMA; A = P_g from TMEM (16 keys = 8 packed columns per MMA);
-            // O accumulates in TMEM across KV tiles
-            const uint64_t dv = dv0 + uint64_t(((kk >> 2) * (FA_TILE / 2)) >> 4) + 2 * (kk & 3);
-            umma_f16_ts(tb + 256 + g * 64, tb + 384 + g * 64 + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tb + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+          if (g == ngroups - 1) {
+            umma_commit(&k_empty[kst]);
+            if (j == nt - 1) umma_commit(q_empty);  // last S of this unit: Q may be replaced
           }
-          umma_commit(&pv_done[g]);
-          if (g == ngroups - 1) umma_commit(&v_empty[st]);
         }
         __syncwarp();
-        if (j + 2 < nt) {
-          mbar_wait(&s_free[g], (j + 1) & 1);
-          if (g == 0) mbar_wait(&k_full[st], ((j + 2) >> 1) & 1);
+        ++si[g];
+      };
+      mbar_wait(q_full, ui & 1);
+      // prologue: S(0) and S(1) of both groups (each group's S buffer is refilled as soon as the group has pulled it into registers)
+      for (int j = 0; j < 2 && j < nt; ++j)
+        for (int g = 0; g < ngroups; ++g) issue_s(g, j);
+      for (int j = 0; j < nt; ++j) {
+        const int vst = (kv0 + j) & 1;
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&p_full[g], pi[g] & 1);
+          if (g == 0) mbar_wait(&v_full[vst], ((kv0 + j) >> 1) & 1);
+          if (j == 0 && ug[g] > 0) mbar_wait(&o_free[g], (ug[g] - 1) & 1);  // the group has read the previous unit's O
           tc_fence_after();
-          issue_s(g, j + 2);
+          if (elect_one()) {
+            const uint64_t dv0 = make_sdesc_sw128(v_addr + vst * FA_TILE);
+#pragma unroll
+            for (int kk = 0; kk < FA_BN / 16; ++kk) {
+              // B = V^T chunk (kk >> 2), 16 keys further per MMA; A = P_g from TMEM (16 keys = 8 packed columns per MMA);
+              // O accumulates in TMEM across KV tiles
+              const uint64_t dv = dv0 + uint64_t(((kk >> 2) * (FA_TILE / 2)) >> 4) + 2 * (kk & 3);
+              umma_f16_ts(tb + 256 + g * 64, tb + 384 + g * 64 + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&pv_done[g]);
+            if (g == ngroups - 1) umma_commit(&v_empty[vst]);
+          }
+          __syncwarp();
+          ++pi[g];
+          if (j + 2 < nt) issue_s(g, j + 2);
         }
       }
+      kv0 += nt;
+      for (int g = 0; g < ngroups; ++g) ++ug[g];
     }
   }
   } else {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-  if (warp_idx < 4 * ngroups) {
+  {
     // ---------------- softmax / output warpgroups: one query row per thread ----------------
     const int g = warp_idx >> 2;
     const int r = threadIdx.x & 127;  // row in the query tile == TMEM lane
     const uint32_t lane_off = uint32_t((warp_idx & 3) * 32) << 16;
     const uint32_t tmem_S = tmem_base + g * 128 + lane_off;
     const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
-    const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-    float m = -INFINITY, l = 0.0f;
     const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_off;
-
-    for (int j = 0; j < nt; ++j) {
-      const int nvalid = min(FA_BN, tokens_kv - j * FA_BN);
-      mbar_wait(&s_full[g], j & 1);
-      tc_fence_after();
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld32(tmem_S + 0, s0);
-      tmem_ld32(tmem_S + 32, s1);
-      tmem_ld32(tmem_S + 64, s2);
-      tmem_ld32(tmem_S + 96, s3);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_free[g]);  // S(j) is out of TMEM: the issuer may overwrite it with S(j+2)
-      if (nvalid < FA_BN) {     // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
+    const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+    int t = 0;  // tiles processed by this group (global)
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int qp = u % nqp, h = (u / nqp) % heads, b = u / (nqp * heads);
+      const int q_tile0 = qp * FA_GROUPS;
+      if (g == 1 && !((q_tile0 + 1) * FA_BM < tokens)) continue;  // this unit has a single query tile
+      float m = -INFINITY, l = 0.0f;
+      for (int j = 0; j < nt; ++j, ++t) {
+        const int nvalid = min(FA_BN, tokens_kv - j * FA_BN);
+        mbar_wait(&s_full[g], t & 1);
+        tc_fence_after();
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        tmem_ld32(tmem_S + 0, s0);
+        tmem_ld32(tmem_S + 32, s1);
+        tmem_ld32(tmem_S + 64, s2);
+        tmem_ld32(tmem_S + 96, s3);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);  // S(j) is out of TMEM: the issuer may overwrite it with S(j+2)
+        if (nvalid < FA_BN) {     // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= nvalid) s0[i] = 0xff800000u;
+            if (32 + i >= nvalid) s1[i] = 0xff800000u;
+            if (64 + i >= nvalid) s2[i] = 0xff800000u;
+            if (96 + i >= nvalid) s3[i] = 0xff800000u;
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (i >= nvalid) s0[i] = 0xff800000u;
-          if (32 + i >= nvalid) s1[i] = 0xff800000u;
-          if (64 + i >= nvalid) s2[i] = 0xff800000u;
-          if (96 + i >= nvalid) s3[i] = 0xff800000u;
+          mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+          mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+          mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
         }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+        // lazy rescaling: keep the stale running max unless it grows by more than 2^8 (p stays <= 256, exact after the final 1/l)
+        float m_new = m;
+        const bool grow = mx > m + 8.0f;
+        if (grow) m_new = mx;
+        const bool warp_rescale = __any_sync(0xffffffffu, grow);
+        // P(j) may only overwrite P(j-1) once PV(j-1) has consumed it; the same wait makes O safe to rescale
+        if (j > 0) {
+          mbar_wait(&pv_done[g], (t - 1) & 1);
+          tc_fence_after();
+          if (warp_rescale) {
+            const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move
+            l *= alpha;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
-        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
-      // lazy rescaling: keep the stale running max unless it grows by more than 2^8 (p stays <= 256, exact after the final 1/l)
-      float m_new = m;
-      const bool grow = mx > m + 8.0f;
-      if (grow) m_new = mx;
-      const bool warp_rescale = __any_sync(0xffffffffu, grow);
-      // P(j) may only overwrite P(j-1) once PV(j-1) has consumed it; the same wait makes O safe to rescale
-      if (j > 0) {
-        mbar_wait(&pv_done[g], (j - 1) & 1);
-        tc_fence_after();
-        if (warp_rescale) {
-          const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move
-          l *= alpha;
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tmem_O + c * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_O + c * 32, o);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tmem_O + c * 32, o);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
         }
+        m = m_new;
+        float sum0 = 0.0f, sum1 = 0.0f;
+        uint32_t pk[32];  // 64 probabilities packed to 16 bits = 32 TMEM columns
+        auto emit = [&](const uint32_t (&sv)[32], int c) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = fmaf(__uint_as_float(sv[8 * q + i]), sc, -m_new);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(pv[i]);
+            sum0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+            sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[(c & 1) * 16 + q * 4 + i] = T16f<FMT>::pack(pv[2 * i], pv[2 * i + 1]);
+          }
+          if (c & 1) tmem_st32(tmem_P + (c >> 1) * 32, pk);
+        };
+        emit(s0, 0);
+        emit(s1, 1);
+        emit(s2, 2);
+        emit(s3, 3);
+        l += sum0 + sum1;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[g]);
       }
-      m = m_new;
-      float sum0 = 0.0f, sum1 = 0.0f;
-      uint32_t pk[32];  // 64 probabilities packed to 16 bits = 32 TMEM columns
-      auto emit = [&](const uint32_t (&sv)[32], int c) {
+      mbar_wait(&pv_done[g], (t - 1) & 1);
+      tc_fence_after();
+      const int q_row = (q_tile0 + g) * FA_BM + r;
+      const bool ok = q_row < tokens;
+      const float inv = 1.0f / l;
+      uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q_row) * C + h * FA_D;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = fmaf(__uint_as_float(sv[8 * q + i]), sc, -m_new);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(pv[i]);
-          sum0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-          sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pk[(c & 1) * 16 + q * 4 + i] = T16f<FMT>::pack(pv[2 * i], pv[2 * i + 1]);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_O + c * 32, v);
+        tmem_ld_wait();
+        if (c == 1) {  // O is in registers: the issuer may start the next unit's accumulation
+          tc_fence_before();
+          mbar_arrive(&o_free[g]);
         }
-        if (c & 1) tmem_st32(tmem_P + (c >> 1) * 32, pk);
-      };
-      emit(s0, 0);
-      emit(s1, 1);
-      emit(s2, 2);
-      emit(s3, 3);
-      l += sum0 + sum1;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[g]);
-    }
-    mbar_wait(&pv_done[g], (nt - 1) & 1);
-    tc_fence_after();
-    const int q_row = (q_tile0 + g) * FA_BM + r;
-    const bool ok = q_row < tokens;
-    const float inv = 1.0f / l;
-    uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q_row) * C + h * FA_D;
+        if (ok) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_O + c * 32, v);
-      tmem_ld_wait();
-      if (ok) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = T16f<FMT>::pack(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-          u.y = T16f<FMT>::pack(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-          u.z = T16f<FMT>::pack(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-          u.w = T16f<FMT>::pack(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(o + c * 32 + i) = u;
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u4;
+            u4.x = T16f<FMT>::pack(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+            u4.y = T16f<FMT>::pack(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+            u4.z = T16f<FMT>::pack(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+            u4.w = T16f<FMT>::pack(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(o + c * 32 + i) = u4;
+          }
         }
       }
     }
@@ -676,9 +705,11 @@ extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_st
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(flash_attn): ") + cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid((tokens_q + FA_GROUPS * FA_BM - 1) / (FA_GROUPS * FA_BM), heads, B);
-  if (fmt) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C);
-  else flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C);
+  const long long units = (long long)((tokens_q + FA_GROUPS * FA_BM - 1) / (FA_GROUPS * FA_BM)) * heads * B;
+  if (units > 0x7fffffffLL) return set_error("vdn_flash_attn: too many work units");
+  const int grid = units < num_sms() ? (int)units : num_sms();
+  if (fmt) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, (int)units);
+  else flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, (int)units);
   count_launch();
   return check_launch("flash_attn_kernel");
 }
