@@ -66,17 +66,27 @@ struct GemmKParams {
   int qkv_split, qkv_tpo, qkv_toff;
 };
 
-template <int BLOCK_N, int EPI = EPI_PLAIN>
+// HALO convolution (3x3, spatial tile 16 rows x 8 pixels): per 64-channel chunk the A operand is three column-shifted haloed
+// tiles [18 rows x 8 px x 64 ch] (one per horizontal tap dx; each image row is one 1024-byte swizzle atom), and the nine taps are
+// MMA descriptors into them — tap (dy, dx) starts dy atoms into tile dx.  54 KB of smem fill per chunk instead of 9 x 16 KB:
+// the small-N convolutions (output_conv1/2) were bound by bytes in flight, not by the tensor pipe.
+constexpr int kHaloTH = 16, kHaloTW = 8;
+constexpr int kHaloBoxBytes = (kHaloTH + 2) * kHaloTW * BLOCK_K * 2;  // 18432
+constexpr int kHaloABytes = 3 * kHaloBoxBytes;                        // 55296 per A stage
+constexpr int kHaloAStages = 2;
+
+template <int BLOCK_N, int EPI = EPI_PLAIN, int HALO = 0>
 struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
-  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStageBytes = HALO ? kStageBytesB : kStageBytesA + kStageBytesB;  // HALO: the ring holds B (per-tap) tiles only
   static constexpr int kStagingBytes = EPI == EPI_TMA ? kNumEpiWarps * kStagingBytesPerWarp : 0;
-  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
+  static constexpr int kARingBytes = HALO ? kHaloAStages * kHaloABytes : 0;
+  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kARingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kParamBytes = 2 * BLOCK_N * 4;  // this tile's bias and gamma slices
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + kParamBytes;
+  static constexpr int kSmemBytes = kARingBytes + kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + kParamBytes;
 };
 
 // Per-thread output-row context, computed once per tile.
@@ -283,24 +293,27 @@ __device__ __forceinline__ void epi_head(const GemmKParams& p, const RowCtx& rc,
   reinterpret_cast<float*>(p.out)[rc.out_row] = fmaxf(s, 0.0f);
 }
 
-template <int BLOCK_N, int EPI, int FMT>
+template <int BLOCK_N, int EPI, int FMT, int HALO = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const GemmKParams p) {
-  using Cfg = GemmCfg<BLOCK_N, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, EPI, HALO>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
-  uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;  // EPI_TMA staging (1024-byte aligned: stage sizes are multiples of 1 KB)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint8_t* smem_b = smem + (HALO ? Cfg::kARingBytes : kStages * Cfg::kStageBytesA);
+  constexpr int kRingBytes = Cfg::kARingBytes + kStages * Cfg::kStageBytes;
+  uint8_t* smem_stg = smem + kRingBytes;  // EPI_TMA staging (1024-byte aligned: stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* sbias = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes + 256);
+  uint64_t* a_full = bars + 2 * kStages + 5;   // HALO: [2]
+  uint64_t* a_empty = bars + 2 * kStages + 7;  // HALO: [2]
+  float* sbias = reinterpret_cast<float*>(smem + kRingBytes + Cfg::kStagingBytes + 256);
   float* sgamma = sbias + BLOCK_N;
 
   const int warp_idx = threadIdx.x >> 5;
@@ -318,6 +331,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kNumEpiWarps * 32);
+      if constexpr (HALO) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
     }
     fence_barrier_init();
   } else if (warp_idx == 1) {
@@ -333,6 +350,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // Producer and issuer warps run their (warp-uniform) loops with all lanes and elect one lane per issue: under a plain
     // `if (lane == 0)` the compiler cannot prove descriptors / coordinates uniform and wraps every tcgen05.mma and TMA in an
     // R2UR + ELECT + BRA.U.ANY waterfall (~80 cycles per MMA, longer than a 128x64x16 MMA itself).
+    if constexpr (HALO) {
+      int stage = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.num_n_blocks;
+        const int m_tile = tile / p.num_n_blocks;
+        const int tw_i = m_tile % p.tiles_w;
+        const int t2 = m_tile / p.tiles_w;
+        const int th_i = t2 % p.tiles_h;
+        const int img = t2 / p.tiles_h;
+        const int h0 = th_i * kHaloTH, w0 = tw_i * kHaloTW;
+        for (int kc = 0; kc < p.cin_blocks; ++kc) {
+          mbar_wait(&a_empty[astage], aphase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[astage], kHaloABytes);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_4d(smem_a + astage * kHaloABytes + dx * kHaloBoxBytes, &tmA, &a_full[astage], kc * BLOCK_K, w0 + dx - 1, h0 - 1, img);
+          }
+          __syncwarp();
+          if (++astage == kHaloAStages) {
+            astage = 0;
+            aphase ^= 1;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytesB);
+              tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], (tap * p.cin_blocks + kc) * BLOCK_K, n_blk * BLOCK_N);
+            }
+            __syncwarp();
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else {
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -368,11 +424,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(FMT ? 1u : 0u, BLOCK_M, BLOCK_N);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
+    if constexpr (HALO) {
+      int stage = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tb + acc * BLOCK_N;
+        for (int kc = 0; kc < p.cin_blocks; ++kc) {
+          mbar_wait(&a_full[astage], aphase);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              // output pixel (y, x) of the 16 x 8 tile reads haloed row y + dy of the tile loaded at column offset dx
+              const uint64_t da = make_sdesc_sw128(a_addr + astage * kHaloABytes + dx * kHaloBoxBytes + dy * 1024);
+              const uint64_t db = make_sdesc_sw128(b_addr + stage * Cfg::kStageBytesB);
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / 16; ++kk) umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kc | tap | kk) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (tap == 8) {
+                umma_commit(&a_empty[astage]);
+                if (kc == p.cin_blocks - 1) umma_commit(&tmem_full_bar[acc]);
+              }
+            }
+            __syncwarp();
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (++astage == kHaloAStages) {
+            astage = 0;
+            aphase ^= 1;
+          }
+        }
+      }
+    } else {
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
@@ -402,6 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           phase ^= 1;
         }
       }
+    }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -622,18 +721,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int EPI, int FMT>
+template <int BLOCK_N, int EPI, int FMT, int HALO = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, EPI, HALO>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, EPI, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, EPI, FMT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
     configured = true;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_blocks;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N, EPI, FMT><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  gemm_tc_kernel<BLOCK_N, EPI, FMT, HALO><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }
@@ -654,6 +753,30 @@ static int launch_gemm_bn(int block_n, const CUtensorMap& tmA, const CUtensorMap
     // QKV / GEGLU / pixel-shuffle outputs are always wide (N >= 256): two tile widths suffice
     if (block_n == 256) return launch_gemm<256, EPI, FMT>(tmA, tmB, tmC, p, stream);
     return launch_gemm<128, EPI, FMT>(tmA, tmB, tmC, p, stream);
+  }
+}
+
+// HALO convolutions: conv-capable epilogues only, tile widths <= 128 (the wide 256-channel convolutions already run tensor-bound)
+template <int EPI, int FMT>
+static int launch_halo_bn(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p, cudaStream_t stream) {
+  if constexpr (EPI == EPI_HEAD) {
+    return launch_gemm<32, EPI, FMT, 1>(tmA, tmB, tmC, p, stream);
+  } else {
+    switch (block_n) {
+      case 128: return launch_gemm<128, EPI, FMT, 1>(tmA, tmB, tmC, p, stream);
+      case 64: return launch_gemm<64, EPI, FMT, 1>(tmA, tmB, tmC, p, stream);
+      default: return launch_gemm<32, EPI, FMT, 1>(tmA, tmB, tmC, p, stream);
+    }
+  }
+}
+
+template <int FMT>
+static int launch_halo_epi(int epi, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p,
+                           cudaStream_t stream) {
+  switch (epi) {
+    case EPI_HEAD: return launch_halo_bn<EPI_HEAD, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    case EPI_RES: return launch_halo_bn<EPI_RES, FMT>(block_n, tmA, tmB, tmC, p, stream);
+    default: return launch_halo_bn<EPI_PLAIN, FMT>(block_n, tmA, tmB, tmC, p, stream);
   }
 }
 
@@ -757,10 +880,21 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
   p.num_n_blocks = (int)((d->N + block_n - 1) / block_n);
 
   CUtensorMap tmA, tmB;
+  bool halo = false;
   if (d->conv) {
     if (d->M != (int64_t)d->B * d->H * d->W) return set_error("vdn_gemm(conv): M != B*H*W");
     if ((d->K * 2) % 16 != 0) return set_error("vdn_gemm(conv): C_in*2 must be a multiple of 16 bytes");
     pick_spatial_tile(d->H, d->W, &p.TH, &p.TW);
+    {
+      // HALO path (16 x 8 tiles, three column-shifted haloed loads per channel chunk): narrow-N convolutions on maps large enough
+      // that the fixed tile shape wastes < 12 % more pixels than the best free choice
+      static const char* env = getenv("VDN_CONV_HALO");
+      const long long best = (long long)((d->H + p.TH - 1) / p.TH) * ((d->W + p.TW - 1) / p.TW);
+      const long long fixed = (long long)((d->H + kHaloTH - 1) / kHaloTH) * ((d->W + kHaloTW - 1) / kHaloTW);
+      const bool want = env ? atoi(env) != 0 : true;
+      halo = want && block_n <= 128 && (epi == EPI_PLAIN || epi == EPI_RES || epi == EPI_HEAD) && fixed * 100 <= best * 112;
+      if (halo) { p.TH = kHaloTH; p.TW = kHaloTW; }
+    }
     p.H = d->H; p.W = d->W;
     p.tiles_h = (d->H + p.TH - 1) / p.TH;
     p.tiles_w = (d->W + p.TW - 1) / p.TW;
@@ -770,7 +904,7 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     if (d->ldw < (int64_t)p.num_k_blocks * BLOCK_K) return set_error("vdn_gemm(conv): ldw < 9*roundup(C_in,64)");
     const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     const uint64_t strides[3] = {(uint64_t)d->K * 2, (uint64_t)d->K * 2 * d->W, (uint64_t)d->K * 2 * d->W * d->H};
-    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)p.TW, (uint32_t)p.TH, 1u};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)p.TW, (uint32_t)(halo ? p.TH + 2 : p.TH), 1u};
     if (make_tensor_map(&tmA, d->a, fmt, 4, dims, strides, box)) return 1;
   } else {
     if ((d->lda * 2) % 16 != 0) return set_error("vdn_gemm: lda*2 must be a multiple of 16 bytes");
@@ -796,5 +930,6 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     const uint32_t box[2] = {32u, 32u};
     if (make_tensor_map_ex(&tmC, d->out, d->out_f32 ? 2 : fmt, d->out_f32 ? 128 : 64, 2, dims, strides, box)) return 1;
   }
+  if (halo) return fmt ? launch_halo_epi<1>(epi, block_n, tmA, tmB, tmC, p, stream) : launch_halo_epi<0>(epi, block_n, tmA, tmB, tmC, p, stream);
   return fmt ? launch_gemm_epi<1>(epi, block_n, tmA, tmB, tmC, p, stream) : launch_gemm_epi<0>(epi, block_n, tmA, tmB, tmC, p, stream);
 }
