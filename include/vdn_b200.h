@@ -101,6 +101,11 @@ int vdn_temporal_attn(const void* qkv, void* out, int32_t D, int32_t T, int32_t 
    pixel), vT [ceil(rows/128), C, 128] = V transposed per 128-row tile (vdn_gemm with VDN_ROWMAP_QKV_SPLIT, rm0 = rm1 = 128; must be
    zero beyond the last valid row), out [rows, C] */
 int vdn_temporal_attn_tc(const void* qk, int64_t ld_qk, const void* vT, void* out, int64_t rows, int32_t C, int32_t heads, void* stream);
+/* streaming form (video_depth_stream.py:76-160, motion_module.py:252-269): one new frame (entry L-1) attends to L <= 32 cached frames.
+   qkv_entries[j] = the cached bias-free projection [D, ld] = (Wq n_j | Wk n_j | Wv n_j) of frame j's normed hidden state; pos [32, 3C] fp32 =
+   the positional part (Wq pe_j | Wk pe_j | Wv pe_j); out [D, C] = softmax((q+pq)(k+pk)^T / sqrt(dh)) (v+pv) per (pixel, head) */
+int vdn_stream_temporal_attn(const void* const* qkv_entries, int32_t L, int64_t ld, const float* pos, void* out, int32_t D, int32_t C, int32_t heads,
+                             void* stream);
 
 /* ---- normalisation ----------------------------------------------------------------------------- */
 /* LayerNorm over C of fp32 rows -> 16-bit.  out row = map(row):

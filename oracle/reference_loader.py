@@ -64,3 +64,14 @@ def load_da2(encoder: str, state_dict):
     m = DepthAnythingV2(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
     m.load_state_dict(state_dict, strict=True)
     return m
+
+
+def load_vda_stream(encoder: str, state_dict):
+    """Reference streaming model (video_depth_anything/video_depth_stream.py:32), same weights / keys as load_vda, strict."""
+    from .init_recipe import ENCODERS
+    _install_shims()
+    from video_depth_anything.video_depth_stream import VideoDepthAnything as VDAStream
+    cfg = ENCODERS[encoder]
+    m = VDAStream(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
+    m.load_state_dict(state_dict, strict=True)
+    return m

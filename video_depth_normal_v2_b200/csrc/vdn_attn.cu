@@ -431,6 +431,68 @@ temporal_attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int D, int 
 
 
 // ------------------------------------------------------------------------------------------------
+// streaming temporal attention: one new frame against <= 32 cached frames (video_depth_stream.py:76-160, motion_module.py:252-269)
+// ------------------------------------------------------------------------------------------------
+// The reference re-projects the concatenated [cached, current] hidden states (+ positional encoding) on every frame.  to_q / to_k /
+// to_v have no bias, so W (n_j + pe_j) = W n_j + W pe_j: each frame's projection W n is computed once when the frame arrives and
+// cached, and the position-dependent part is a weights-only table pos[L, 3C] = pe W^T.  This kernel then reads L cached k / v rows
+// per pixel (HBM-bound): warp per (pixel, head), lanes over channels, entries in a loop.
+struct StreamAttnParams {
+  const uint16_t* qkv[32];  // per entry: [D, ld] 16-bit rows, q | k | v at column offsets 0, C, 2C
+  const float* pos;         // [32, 3C] fp32: row j = (Wq pe_j | Wk pe_j | Wv pe_j)
+  void* out;                // [D, C] 16-bit
+  int D, C, heads, L, ld, fmt;
+};
+
+__global__ void __launch_bounds__(256) stream_temporal_attn_kernel(const StreamAttnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int dh = p.C / p.heads;
+  const float scale = rsqrtf((float)dh);
+  const long long npairs = (long long)p.D * p.heads;
+  const int L = p.L;
+  for (long long pair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pair < npairs; pair += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const long long d = pair / p.heads;
+    const int h = int(pair - d * p.heads);
+    const int c0 = h * dh;
+    // query = current frame (entry L-1) at position L-1
+    float q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      q[i] = c < dh ? load16(p.qkv[L - 1], d * p.ld + c0 + c, p.fmt) + __ldg(p.pos + (long long)(L - 1) * 3 * p.C + c0 + c) : 0.0f;
+    }
+    float sj = -INFINITY;  // lane j keeps score j
+    for (int j = 0; j < L; ++j) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i;
+        if (c < dh) acc = fmaf(q[i], load16(p.qkv[j], d * p.ld + p.C + c0 + c, p.fmt) + __ldg(p.pos + (long long)j * 3 * p.C + p.C + c0 + c), acc);
+      }
+      acc = warp_sum(acc) * scale;
+      if (lane == j) sj = acc;
+    }
+    const float mx = warp_max(sj);
+    const float e = lane < L ? __expf(sj - mx) : 0.0f;
+    const float pj = e / warp_sum(e);
+    float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int j = 0; j < L; ++j) {
+      const float w = __shfl_sync(0xffffffffu, pj, j);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i;
+        if (c < dh) o[i] = fmaf(w, load16(p.qkv[j], d * p.ld + 2 * p.C + c0 + c, p.fmt) + __ldg(p.pos + (long long)j * 3 * p.C + 2 * p.C + c0 + c), o[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < dh) store16(p.out, d * p.C + c0 + c, o[i], p.fmt);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // temporal attention on tcgen05 (T == 32 frames, head_dim 32 / 64 / 128)
 // ------------------------------------------------------------------------------------------------
 // A tile is 128 consecutive rows of the pixel-major sequence = 4 pixels x 32 frames.  S = Q K^T is computed for the whole
@@ -721,6 +783,25 @@ extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int
   if (ld_qk < 2 * C) return set_error("vdn_flash_attn: ld_qk must be >= 2*C and 16-byte aligned");
   const uint16_t* base = reinterpret_cast<const uint16_t*>(qk);
   return vdn_flash_attn_ex(base, ld_qk, (int64_t)tokens * ld_qk, base + C, ld_qk, (int64_t)tokens * ld_qk, vT, ld_vT, out, B, tokens, tokens, heads, stream_v);
+}
+
+extern "C" int vdn_stream_temporal_attn(const void* const* qkv_entries, int32_t L, int64_t ld, const float* pos, void* out, int32_t D, int32_t C,
+                                        int32_t heads, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!qkv_entries || !pos || !out) return set_error("vdn_stream_temporal_attn: null pointer");
+  if (L < 1 || L > 32) return set_error("vdn_stream_temporal_attn: L must be in [1, 32]");
+  if (heads <= 0 || C % heads != 0 || C / heads > 128 || ld < 3 * C) return set_error("vdn_stream_temporal_attn: head_dim must be <= 128 and ld >= 3*C");
+  StreamAttnParams p{};
+  for (int j = 0; j < L; ++j) {
+    if (!qkv_entries[j]) return set_error("vdn_stream_temporal_attn: null entry");
+    p.qkv[j] = reinterpret_cast<const uint16_t*>(qkv_entries[j]);
+  }
+  p.pos = pos; p.out = out; p.D = D; p.C = C; p.heads = heads; p.L = L; p.ld = (int)ld; p.fmt = get_operand_format();
+  long long blocks = ((long long)D * heads + 7) / 8;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  stream_temporal_attn_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  count_launch();
+  return check_launch("stream_temporal_attn_kernel");
 }
 
 extern "C" int vdn_temporal_attn_tc(const void* qk, int64_t ld_qk, const void* vT, void* out, int64_t rows, int32_t C, int32_t heads, void* stream_v) {

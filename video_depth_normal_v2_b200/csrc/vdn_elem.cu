@@ -2,6 +2,8 @@
 // bilinear resize (align_corners=True), ReLU / casts, window alignment reductions, Sobel normals.
 // All are coalesced, 16-byte vectorised where the layout allows, warp-shuffle reductions, no shared-memory staging
 // beyond block reductions (each element is touched once).
+#include <stdlib.h>
+
 #include "../../include/vdn_b200.h"
 #include "vdn_common.cuh"
 #include "vdn_host.h"
@@ -82,6 +84,81 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
       }
     }
   }
+}
+
+// Plain rows (no row map, no positional term), C = 128 * NV: two rows per warp in flight (all 2 x NV 16-byte loads are issued
+// before the first reduction), 32-bit index arithmetic, streaming loads — the ViT blocks' 48 LayerNorms per window.
+template <int NV, int FMT>
+__global__ void __launch_bounds__(256)
+layernorm_rows2_kernel(const float4* __restrict__ x, const float4* __restrict__ w, const float4* __restrict__ b, uint2* __restrict__ out, int rows,
+                       float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  constexpr float invC = 1.0f / (float)(NV * 128);
+  for (int row = warp0; row < rows; row += 2 * nwarps) {
+    const int row2 = row + nwarps;
+    const bool has2 = row2 < rows;
+    const float4* xa = x + (long long)row * (NV * 32);
+    const float4* xb = x + (long long)(has2 ? row2 : row) * (NV * 32);
+    float4 va[NV], vb[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) va[i] = __ldcs(xa + lane + 32 * i);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vb[i] = __ldcs(xb + lane + 32 * i);
+    float sa = 0.0f, sb = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      sa += (va[i].x + va[i].y) + (va[i].z + va[i].w);
+      sb += (vb[i].x + vb[i].y) + (vb[i].z + vb[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    const float ma = sa * invC, mb = sb * invC;
+    float qa = 0.0f, qb = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a0 = va[i].x - ma, a1 = va[i].y - ma, a2 = va[i].z - ma, a3 = va[i].w - ma;
+      const float b0 = vb[i].x - mb, b1 = vb[i].y - mb, b2 = vb[i].z - mb, b3 = vb[i].w - mb;
+      qa += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      qb += (b0 * b0 + b1 * b1) + (b2 * b2 + b3 * b3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      qa += __shfl_xor_sync(0xffffffffu, qa, o);
+      qb += __shfl_xor_sync(0xffffffffu, qb, o);
+    }
+    const float ra = rsqrtf(qa * invC + eps), rb = rsqrtf(qb * invC + eps);
+    uint2* oa = out + (long long)row * (NV * 32);
+    uint2* ob = out + (long long)row2 * (NV * 32);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 g = __ldg(w + lane + 32 * i);
+      const float4 be = __ldg(b + lane + 32 * i);
+      uint2 u;
+      u.x = T16f<FMT>::pack((va[i].x - ma) * ra * g.x + be.x, (va[i].y - ma) * ra * g.y + be.y);
+      u.y = T16f<FMT>::pack((va[i].z - ma) * ra * g.z + be.z, (va[i].w - ma) * ra * g.w + be.w);
+      oa[lane + 32 * i] = u;
+      if (has2) {
+        u.x = T16f<FMT>::pack((vb[i].x - mb) * rb * g.x + be.x, (vb[i].y - mb) * rb * g.y + be.y);
+        u.y = T16f<FMT>::pack((vb[i].z - mb) * rb * g.z + be.z, (vb[i].w - mb) * rb * g.w + be.w);
+        ob[lane + 32 * i] = u;
+      }
+    }
+  }
+}
+
+template <int NV>
+static void launch_layernorm_rows2(const float* x, const float* w, const float* b, void* out, long long rows, float eps, cudaStream_t stream) {
+  const unsigned grid = grid_for((rows + 1) / 2, 8);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  if (get_operand_format()) layernorm_rows2_kernel<NV, 1><<<grid, 256, 0, stream>>>(x4, w4, b4, reinterpret_cast<uint2*>(out), (int)rows, eps);
+  else layernorm_rows2_kernel<NV, 0><<<grid, 256, 0, stream>>>(x4, w4, b4, reinterpret_cast<uint2*>(out), (int)rows, eps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -460,7 +537,12 @@ extern "C" int vdn_layernorm(const float* x, const float* w, const float* b, voi
   if (C % 4 != 0 || C > 32 * LN_MAXV * 4) return set_error("vdn_layernorm: C must be a multiple of 4 and <= 1024");
   if (drop_first && (rows_per_batch < 2 || rows % rows_per_batch != 0)) return set_error("vdn_layernorm: bad rows_per_batch");
   if (pe && pe_len <= 0) return set_error("vdn_layernorm: bad pe_len");
-  layernorm_kernel<<<grid_for(rows, 8), 256, 0, stream>>>(x, w, b, out, rows, C, eps, drop_first, rows_per_batch, pe, pe_len, get_operand_format());
+  static const char* env = getenv("VDN_LN_V1");
+  const bool plain = !drop_first && pe == nullptr && rows < 0x3fffffffLL && env == nullptr;
+  if (plain && C == 1024) launch_layernorm_rows2<8>(x, w, b, out, rows, eps, stream);
+  else if (plain && C == 384) launch_layernorm_rows2<3>(x, w, b, out, rows, eps, stream);
+  else if (plain && C == 256) launch_layernorm_rows2<2>(x, w, b, out, rows, eps, stream);
+  else layernorm_kernel<<<grid_for(rows, 8), 256, 0, stream>>>(x, w, b, out, rows, C, eps, drop_first, rows_per_batch, pe, pe_len, get_operand_format());
   count_launch();
   return check_launch("layernorm_kernel");
 }

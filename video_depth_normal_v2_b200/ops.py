@@ -177,6 +177,16 @@ def temporal_attn_tc(qk: torch.Tensor, vT: torch.Tensor, out: torch.Tensor, rows
     return out
 
 
+def stream_temporal_attn(entries, pos: torch.Tensor, out: torch.Tensor, D: int, C_: int, heads: int):
+    """entries: list of L <= 32 cached [D, 3C] 16-bit projections (oldest first, the current frame last)."""
+    od = operand_dtype()
+    L = len(entries)
+    arr = (C.c_void_p * L)(*[_ptr(e, od, "entry") for e in entries])
+    _check(_run("stream_temporal_attn", "hbm", 2.0 * L * D * 2 * C_ + 4.0 * D * C_, lib().vdn_stream_temporal_attn, arr, L, entries[0].shape[-1],
+                _ptr(pos, torch.float32, "pos"), _ptr(out, od, "out"), D, C_, heads, _stream()), "vdn_stream_temporal_attn")
+    return out
+
+
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor, eps: float, drop_first: bool = False, rows_per_batch: int = 0,
               pe: Optional[torch.Tensor] = None):
     rows, C_ = x.shape[0], x.shape[1]
