@@ -32,6 +32,8 @@ VDA_CASES = [
 V5_CASES = [("v5_vits_s4_60x80", "vits", 4, 60, 80, 3)]
 # (name, encoder, batch, H(=W), calls, seed, stride): DepthAnythingV2 is stateful -> a sequence of forward() calls on one model
 DA2_CASES = [("da2_vits_b2_70_calls8", "vits", 2, 70, 8, 5, 1), ("da2_vits_b1_518_calls2", "vits", 1, 518, 2, 6, 4), ("da2_vitl_b1_70_calls3", "vitl", 1, 70, 3, 7, 1)]
+# (name, encoder, frames, H, W, seed): streaming inference, one infer_video_depth_one call per frame (window slides after frame 10)
+STREAM_CASES = [("stream_vits_n16_56x70", "vits", 16, 56, 70, 8)]
 VIDEO_CASES = [("video_vits_n50_56x70", "vits", 50, 56, 70, 4)]
 SCHEDULE_NS = [1, 5, 21, 22, 23, 32, 44, 45, 50, 60, 100]
 
@@ -65,12 +67,26 @@ def gen_da2():
         del m
 
 
+def gen_stream():
+    for name, enc, N, H, W, seed in STREAM_CASES:
+        sd = make_state_dict("vda", enc, seed)
+        m = RL.load_vda_stream(enc, sd)
+        frames = video_frames(N, H, W, seed)
+        outs = [m.infer_video_depth_one(frames[i], input_size=min(H, W), device="cpu", fp32=True) for i in range(N)]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), depths=np.stack(outs).astype(np.float32), meta=np.array([N, H, W, seed]))
+        print(name, np.stack(outs).shape, float(np.stack(outs).mean()))
+        del m
+
+
 def main():
     assert RL.available(), "reference not present"
     torch.set_grad_enabled(False)
     if len(sys.argv) > 1 and sys.argv[1] == "da2":
         return gen_da2()
+    if len(sys.argv) > 1 and sys.argv[1] == "stream":
+        return gen_stream()
     gen_da2()
+    gen_stream()
     for name, enc, T, H, W, seed, stride in VDA_CASES:
         sd = make_state_dict("vda", enc, seed)
         m = RL.load_vda(enc, sd)

@@ -221,3 +221,23 @@ def test_da2_infer_image_shape_and_state(vdn):
         m(torch.zeros(2, 3, 70, 70).cuda())  # batch size changed while the bank holds an entry
     m.clear_memory()
     m(torch.zeros(2, 3, 70, 70).cuda())
+
+
+# ------------------------------------------------------------------------------------------ f1: streaming inference
+def test_streaming_infer_video_depth_one_matches_reference_golden(vdn):
+    """video_depth_stream.py:76-160 frame by frame: cached projections + positional table against the live reference's outputs
+    (which re-project the cached hidden states on every frame)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from gen_golden import video_frames
+    g = np.load(os.path.join(GOLD, "stream_vits_n16_56x70.npz"))
+    N, H, W, seed = [int(v) for v in g["meta"]]
+    m, _ = _model(vdn, "vits", seed)
+    frames = video_frames(N, H, W, seed)
+    for i in range(N):
+        d = m.infer_video_depth_one(frames[i], input_size=min(H, W), device="cuda")
+        assert d.shape == (H, W) and d.dtype == np.float32
+        _check(f"stream frame {i}", torch.from_numpy(d)[None], torch.from_numpy(g["depths"][i])[None])
+    m.reset_stream()
+    d0 = m.infer_video_depth_one(frames[0], input_size=min(H, W), device="cuda")
+    _check("stream frame 0 after reset", torch.from_numpy(d0)[None], torch.from_numpy(g["depths"][0])[None])

@@ -112,3 +112,22 @@ def test_da2_memory_changes_the_output():
     O.da2_forward(sd, xs[1], "vits", bank)
     with_mem = O.da2_forward(sd, xs[0], "vits", bank)
     assert float((with_mem - first).abs().mean() / first.abs().mean()) > 2e-3  # twice the AbsRel parity tolerance
+
+
+# ------------------------------------------------------------------------------------------ f1: streaming inference
+def test_stream_steps_match_reference():
+    """video_depth_stream.py infer_video_depth_one, 16 frames (cache list growing to 42 entries, then sliding)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from gen_golden import video_frames
+    from video_depth_normal_v2_b200 import video as V
+    g = _load("stream_vits_n16_56x70")
+    N, H, W, seed = [int(v) for v in g["meta"]]
+    sd = make_state_dict("vda", "vits", seed)
+    ft = torch.from_numpy(V.preprocess_frames(video_frames(N, H, W, seed), min(H, W)))
+    state = {}
+    for i in range(N):
+        y = O.vda_stream_step(sd, ft[i][None, None], "vits", state)
+        ref = torch.from_numpy(g["depths"][i])
+        assert (y - ref).abs().max() / ref.abs().max() < 2e-4, i
+    assert len(state["cache"]) == 42

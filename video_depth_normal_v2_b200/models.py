@@ -167,6 +167,39 @@ def motion_module_forward(mm: dict, x: torch.Tensor, Bv: int, T: int, D: int, re
     return (y, y_relu) if relu_copy else y
 
 
+def motion_module_stream(mm: dict, x: torch.Tensor, D: int, cached: Optional[list], new_cache: list):
+    """One new frame through a motion module with cached history (motion_module.py:102-136 with cached_hidden_state_list,
+    TemporalAttention.forward :252-259).  x: [1, D, C] 16-bit NHWC.  ``cached``: per attention block the list of earlier frames'
+    cached projections (oldest first); ``new_cache`` receives this frame's two projections.  The reference caches the normed hidden
+    state n_j and re-projects all <= 32 frames on every call; to_q/k/v have no bias, so W (n_j + pe_j) = W n_j + W pe_j: the
+    projection W n_j is cached instead and the positional part is the weights-only table ``pos_qkv``."""
+    dev, od, C = x.device, ops.operand_dtype(), mm["C"]
+    stats = _empty((32 * 2,), torch.float32, dev)
+    ops.groupnorm_stats(x, stats, 1, D, C, 32, 1e-6)
+    xt = _empty((D, C), od, dev)
+    ops.groupnorm_apply_tc(x, stats, mm["gn_w"], mm["gn_b"], xt, 1, 1, D, C, 32)
+    h = _empty((D, C), torch.float32, dev)
+    ops.gemm(xt, mm["proj_in"]["w"], h, M=D, N=C, K=C, bias=mm["proj_in"]["b"])
+    n16 = xt
+    ao = _empty((D, C), od, dev)
+    for i, a in enumerate(mm["attn"]):
+        ops.layernorm(h, a["ln_w"], a["ln_b"], n16, 1e-5)  # the positional term is applied in the attention kernel
+        proj = _empty((D, 3 * C), od, dev)                 # (Wq n | Wk n | Wv n) of this frame: what gets cached
+        ops.gemm(n16, a["qkv_w"], proj, M=D, N=3 * C, K=C)
+        new_cache.append(proj)
+        entries = (cached[i] if cached is not None else []) + [proj]
+        ops.stream_temporal_attn(entries, a["pos_qkv"], ao, D, C, 8)
+        ops.gemm(ao, a["out"]["w"], h, M=D, N=C, K=C, bias=a["out"]["b"], res=h)
+    ops.layernorm(h, mm["ffn_w"], mm["ffn_b"], n16, 1e-5)
+    g = _empty((D, 4 * C), od, dev)
+    ops.gemm(n16, mm["ff1_w"], g, M=D, N=8 * C, K=C, bias=mm["ff1_b"], geglu=True)
+    h16 = ao
+    ops.gemm(g, mm["ff2"]["w"], h, M=D, N=C, K=4 * C, bias=mm["ff2"]["b"], res=h, out2=h16)
+    y = _empty((1, D, C), od, dev)
+    ops.gemm(h16, mm["proj_out"]["w"], y, M=D, N=C, K=C, bias=mm["proj_out"]["b"], res=x)
+    return y
+
+
 # ======================================================================================================
 # DPT head (dpt.py:126-159, dpt_temporal.py:53-127, util/blocks.py:68-162)
 # ======================================================================================================
@@ -209,8 +242,10 @@ def _fusion(rf, B, H, W, Ho, Wo, x0, x0_relu=None, x1=None, x1_relu=None, relu_c
     return up
 
 
-def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: int, T: Optional[int]) -> torch.Tensor:
-    """-> depth fp32 [Bf, 14*ph, 14*pw] (after output_conv2's ReLUs)."""
+def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: int, T: Optional[int], stream: Optional[dict] = None) -> torch.Tensor:
+    """-> depth fp32 [Bf, 14*ph, 14*pw] (after output_conv2's ReLUs).
+    ``stream`` (Bf == 1): {"cached": per motion module, per attention block, the list of cached projections or None; "new": []}
+    — the streaming path of video_depth_stream.py / dpt_temporal.py:72-96 with cached_hidden_state_list."""
     dev, od = feats[0].device, ops.operand_dtype()
     C, Fe, oc = feats[0].shape[-1], head["features"], head["oc"]
     P = ph * pw
@@ -235,7 +270,14 @@ def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: in
     layer4 = _empty((Bf, H4 * W4, oc[3]), od, dev)
     ops.gemm(col, head["resize3"]["w"], layer4, M=Bf * H4 * W4, N=oc[3], K=9 * oc[3], bias=head["resize3"]["b"])
     # ---- temporal mixing on layer_3 / layer_4 (dpt_temporal.py:81-84)
-    if T is not None:
+    def mm_stream(m, x, D):
+        cached = stream["cached"][m] if stream["cached"] is not None else None
+        return motion_module_stream(head["mm"][m], x, D, cached, stream["new"])
+
+    if stream is not None:
+        layer3 = mm_stream(0, layer3, P)
+        layer4 = mm_stream(1, layer4, H4 * W4)
+    elif T is not None:
         Bv = Bf // T
         layer3 = motion_module_forward(head["mm"][0], layer3, Bv, T, P)
         layer4 = motion_module_forward(head["mm"][1], layer4, Bv, T, H4 * W4)
@@ -251,10 +293,14 @@ def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: in
     # ---- refinenets (dpt_temporal.py:91-101)
     rf = head["refine"]
     path4 = _fusion(rf[4], Bf, H4, W4, H3, W3, l4r, x0_relu=l4r_relu)
-    if T is not None:
+    if stream is not None:
+        path4 = mm_stream(2, path4.view(Bf, H3 * W3, Fe), H3 * W3)
+    elif T is not None:
         path4 = motion_module_forward(head["mm"][2], path4.view(Bf, H3 * W3, Fe), Bv, T, H3 * W3)
     path3 = _fusion(rf[3], Bf, H3, W3, H2, W2, path4, x1=l3r, x1_relu=l3r_relu)
-    if T is not None:
+    if stream is not None:
+        path3 = mm_stream(3, path3.view(Bf, H2 * W2, Fe), H2 * W2)
+    elif T is not None:
         path3 = motion_module_forward(head["mm"][3], path3.view(Bf, H2 * W2, Fe), Bv, T, H2 * W2)
     path2 = _fusion(rf[2], Bf, H2, W2, H1, W1, path3, x1=l2r, x1_relu=l2r_relu)
     path1 = _fusion(rf[1], Bf, H1, W1, 2 * H1, 2 * W1, path2, x1=l1r, x1_relu=l1r_relu)
@@ -454,6 +500,58 @@ class VideoDepthAnything(_PackedModule):
         return self._graphs.run(("head", T, ph, pw), lambda *f: head_forward(w["head"], list(f), T, ph, pw, T), [f.contiguous() for f in feats]).clone()
 
     # ------------------------------------------------------------------------------------------------
+    # streaming: drop-in for video_depth_anything/video_depth_stream.py:76-160 (same class name there; one model serves both here)
+    def reset_stream(self):
+        self._stream = None
+
+    @torch.no_grad()
+    def stream_step(self, x: torch.Tensor) -> torch.Tensor:
+        """One pre-processed frame x (3, h, w) fp32 -> depth (h, w) fp32 on the device, attending to the cached history:
+        frame 0, the second-oldest kept frame and the last 29 frames (video_depth_stream.py:130-158)."""
+        w = self._weights()
+        st = getattr(self, "_stream", None)
+        if st is None:
+            st = self._stream = {"id": -1, "cache": []}
+        st["id"] += 1
+        _, h, wd = x.shape
+        ph, pw = h // 14, wd // 14
+        feats = encoder_forward(w["enc"], x.to(device=self._dev, dtype=torch.float32).unsqueeze(0).contiguous())
+        new: list = []
+        if st["id"] == 0:
+            depth = head_forward(w["head"], feats, 1, ph, pw, 1, stream={"cached": None, "new": new})
+            st["cache"] = [new] * INFER_LEN  # "copy multiple cache to simulate the windows"
+        else:
+            cl = st["cache"]
+            cur = cl[0:2] + cl[-INFER_LEN + 3:]
+            cached = [[[fr[2 * m + a] for fr in cur] for a in range(2)] for m in range(4)]
+            depth = head_forward(w["head"], feats, 1, ph, pw, 1, stream={"cached": cached, "new": new})
+            st["cache"] = cl + [new]
+        gap = (INFER_LEN - OVERLAP) * 2 - 1 - (OVERLAP - INTERP_LEN)
+        if st["id"] + INFER_LEN > gap + 1:
+            st["cache"] = st["cache"][:1] + st["cache"][2:]
+        return depth[0]
+
+    @torch.no_grad()
+    def infer_video_depth_one(self, frame, input_size=518, device="cuda", fp32=False):
+        """video_depth_stream.py:76: frame np.uint8 (H, W, 3) RGB -> np.float32 depth (H, W) of this frame; call once per frame."""
+        from . import video as V
+        if str(device).split(":")[0] != "cuda":
+            raise RuntimeError("infer_video_depth_one runs on CUDA only (no CPU fallback)")
+        st = getattr(self, "_stream", None)
+        fh, fw = frame.shape[:2]
+        if st is None:
+            self._stream_size = V._resolve_input_size(fh, fw, input_size)
+            self._stream_hw = (fh, fw)
+        elif (fh, fw) != self._stream_hw:
+            raise RuntimeError("frame size changed mid-stream")  # video_depth_stream.py:131-133 asserts
+        x = torch.from_numpy(V.preprocess_frames(frame[None], self._stream_size)[0])
+        d = self.stream_step(x)
+        if tuple(d.shape) != (fh, fw):
+            r = torch.empty((1, fh, fw), dtype=torch.float32, device=d.device)
+            ops.bilinear_f32(d.unsqueeze(0).contiguous(), r, 1, d.shape[0], d.shape[1], fh, fw)
+            d = r[0]
+        return d.cpu().numpy()
+
     @torch.no_grad()
     def infer_video_depth(self, frames, target_fps, input_size=518, device="cuda", fp32=False, **kw):
         """Drop-in for video_depth.py:67-156.  frames: np.uint8 (N, H, W, 3) RGB -> (np.float32 (N, H, W), target_fps).

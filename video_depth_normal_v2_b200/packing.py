@@ -110,10 +110,13 @@ def pack_motion_module(sd, prefix: str, C: int, dev, dt) -> dict:
     for a in range(2):
         ab = f"{tb}attention_blocks.{a}."
         qkv = torch.cat([sd[ab + "to_q.weight"], sd[ab + "to_k.weight"], sd[ab + "to_v.weight"]], dim=0)
+        pe = sd[ab + "pos_encoder.pe"][0].detach().double()
         mm["attn"].append({
             "ln_w": _f32(sd[f"{tb}norms.{a}.weight"], dev), "ln_b": _f32(sd[f"{tb}norms.{a}.bias"], dev),
             "qkv_w": _w16(qkv, dev, dt), "out": pack_linear(sd, ab + "to_out.0", dev, dt),
             "pe": _f32(sd[ab + "pos_encoder.pe"][0], dev),  # (32, C)
+            # streaming path: positional part of the bias-free projections, W (n + pe_j) = W n + W pe_j (weights only, fp64 once)
+            "pos_qkv": _f32((pe @ qkv.detach().double().t()).float(), dev),  # (32, 3C)
         })
     w1, b1 = sd[tb + "ff.net.0.proj.weight"].detach().float(), sd[tb + "ff.net.0.proj.bias"].detach().float()
     h = w1.shape[0] // 2  # rows [0,h) = value, [h,2h) = gate (GEGLU.chunk(2), motion_module/attention.py:382-384)
