@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--operands", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--da2-batch", type=int, default=16, help="batch of the DepthAnythingV2 ViT-L 518x518 measurement (BASELINE configs[1]); 0 = skip")
+    ap.add_argument("--stream-frames", type=int, default=20, help="timed frames of the streaming (infer_video_depth_one) measurement; 0 = skip")
     ap.add_argument("--lv-windows", type=int, default=6, help="windows per GPU of the long-video (sharded infer_video_depth) measurement; 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -281,6 +282,26 @@ def main():
                               "feature reuse for the 10 overlap slots, temporal head on all 32 slots, device-side scale/shift chain + cross-fade, "
                               "NCCL boundary exchange + gather when n_gpus > 1, D2H of all output frames"}
 
+    # ---------------- streaming: one frame per call against the cached history (video_depth_stream.py) ----------------
+    stream = None
+    if args.stream_frames > 0 and rank == 0:
+        xs = torch.randn((3, SIZE, SIZE), generator=torch.Generator().manual_seed(3)).to(dev)
+        model.reset_stream()
+        for _ in range(14):  # past frame 11 the window has its steady-state 32 entries and slides
+            model.stream_step(xs)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.stream_frames):
+            d1 = model.stream_step(xs)
+        e1.record()
+        torch.cuda.synchronize()
+        st_ms = e0.elapsed_time(e1) / args.stream_frames
+        stream = {"value": 1e3 / st_ms, "unit": "frames/s", "ms_per_frame": st_ms,
+                  "note": "ViT-L 518x518, one new frame per call attending to 31 cached frames (cached projections + positional table), device-resident input"}
+        model.reset_stream()
+    if world > 1:
+        dist.barrier()
+
     # ---------------- BASELINE configs[1]: DepthAnythingV2 ViT-L, single images 518x518, batch 16, stateful memory bank ----------------
     da2 = None
     if args.da2_batch > 0:
@@ -360,7 +381,7 @@ def main():
                    "frames_per_step_per_gpu": FRAMES, "tokens_per_frame": 1370, "parallelism": f"window-sharded x{world}, no data-path collective",
                    "l2": "activations per step (>2 GB) exceed the 126 MB L2, no explicit flush", "operands": args.operands + " (fp32 accumulate, fp32 residual stream)"},
         "tensor_frac_of_step": (GFLOP_PER_FRAME * 1e9 * FRAMES / (ms_per_step / 1e3)) / 1e12 / peaks["tflops"],
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "long_video": long_video, "da2_batch16": da2, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "long_video": long_video, "da2_batch16": da2, "stream": stream, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

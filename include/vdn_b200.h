@@ -140,6 +140,11 @@ int vdn_relu16(const void* x, void* out, int64_t n, void* stream);
 /* out16 = x (fp32 -> 16-bit), n elements */
 int vdn_cast_f32_to_16(const float* x, void* out, int64_t n, void* stream);
 
+/* ---- frame pre-processing (util/transform.py Resize(INTER_CUBIC) + NormalizeImage + PrepareForNet, video_depth.py:74-99) ----
+ * frames uint8 [N, H, W, 3] RGB (device) -> out fp32 [N, 3, h, w] = ((cubic_resize(frames / 255) - mean) / std); mean3 / std3 are HOST pointers */
+int vdn_preprocess_u8(const void* frames, float* out, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, const float* mean3, const float* std3,
+                      void* stream);
+
 /* ---- window alignment (video_depth.py:118-154, utils/util.py:40-74) ------------------------------- */
 /* sums[0..4] = (sum p*p, sum p, n, sum p*t, sum t) over n elements, accumulated in fp64 on device */
 int vdn_lsq_sums(const float* pred, const float* target, int64_t n, double* sums5, void* stream);

@@ -4,6 +4,8 @@ Tolerances: operands are rounded to the 16-bit operand format *before* both side
 accumulation order and the final 16-bit output rounding (2^-11 relative for fp16, 2^-8 for bf16)."""
 import math
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -425,3 +427,16 @@ def test_torch_ops_dispatch_to_the_kernels(ops):
     o2 = torch.empty(100, 384, device="cuda", dtype=od)
     torch.ops.vdn.layernorm(x, torch.ones(384, device="cuda"), torch.zeros(384, device="cuda"), o2, 1e-6)
     _close("torch.ops.vdn.layernorm", o2, F.layer_norm(x, (384,), eps=1e-6))
+
+
+@pytest.mark.parametrize("H,W,size", [(90, 120, 84), (240, 426, 112), (56, 70, 56), (61, 47, 70)])
+def test_device_preprocess_matches_cv2_transform(ops, H, W, size):
+    """vdn_preprocess_u8 against the host transform the reference uses (cv2.INTER_CUBIC resize + ImageNet normalisation)."""
+    from video_depth_normal_v2_b200 import video as V
+    frames = np.random.RandomState(H).randint(0, 256, (3, H, W, 3), dtype=np.uint8)
+    ref = torch.from_numpy(V.preprocess_frames(frames, size))
+    h, w = ref.shape[-2:]
+    out = torch.empty(3, 3, h, w, device="cuda")
+    ops.preprocess_u8(torch.from_numpy(frames).cuda(), out, h, w)
+    torch.cuda.synchronize()
+    assert float((out.cpu() - ref).abs().max()) < 2e-4  # values span ~[-2.1, 2.6]; fp32 rounding of the 16 taps times 1/std

@@ -55,6 +55,7 @@ SIGNATURES = {
     "vdn_bilinear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_relu16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vdn_cast_f32_to_16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "vdn_preprocess_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p]),
     "vdn_lsq_sums": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "vdn_lsq_solve": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vdn_affine_clamp": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

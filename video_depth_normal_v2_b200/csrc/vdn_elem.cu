@@ -525,6 +525,64 @@ sobel_normals_kernel(const float* __restrict__ depth, float* __restrict__ normal
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// frame pre-processing on the device: uint8 RGB HWC -> /255 -> cv2.INTER_CUBIC resize -> ImageNet normalise -> fp32 CHW
+// (util/transform.py Resize + NormalizeImage + PrepareForNet as used at video_depth.py:74-99).  OpenCV's float cubic: A = -0.75,
+// source coordinate (d + 0.5) * scale - 0.5, 4 taps at floor-1 .. floor+2 with replicated borders, horizontal pass then vertical.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coeffs(float x, float (&c)[4]) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1.0f) - 5.0f * A) * (x + 1.0f) + 8.0f * A) * (x + 1.0f) - 4.0f * A;
+  c[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  c[2] = ((A + 2.0f) * (1.0f - x) - (A + 3.0f)) * (1.0f - x) * (1.0f - x) + 1.0f;
+  c[3] = 1.0f - c[0] - c[1] - c[2];
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_u8_kernel(const uint8_t* __restrict__ frames, float* __restrict__ out, int N, int H, int W, int h, int w, double scale_y, double scale_x,
+                     float m0, float m1, float m2, float is0, float is1, float is2) {
+  const long long total = (long long)N * h * w;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = int(idx % w);
+    const int y = int((idx / w) % h);
+    const long long n = idx / ((long long)w * h);
+    float fx = (float)((x + 0.5) * scale_x - 0.5);
+    float fy = (float)((y + 0.5) * scale_y - 0.5);
+    const int sx = (int)floorf(fx), sy = (int)floorf(fy);
+    fx -= (float)sx;
+    fy -= (float)sy;
+    float cx[4], cy[4];
+    cubic_coeffs(fx, cx);
+    cubic_coeffs(fy, cy);
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+    const uint8_t* img = frames + n * (long long)H * W * 3;
+    const bool identity = (H == h && W == w);  // cv2.resize returns the source unchanged for equal sizes
+    if (identity) {
+      const uint8_t* px = img + ((long long)y * W + x) * 3;
+      acc[0] = (float)px[0] / 255.0f; acc[1] = (float)px[1] / 255.0f; acc[2] = (float)px[2] / 255.0f;
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const int yy = min(max(sy - 1 + ky, 0), H - 1);
+        float row[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+          const int xx = min(max(sx - 1 + kx, 0), W - 1);
+          const uint8_t* px = img + ((long long)yy * W + xx) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) row[c] = fmaf((float)px[c] / 255.0f, cx[kx], row[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] = fmaf(row[c], cy[ky], acc[c]);
+      }
+    }
+    float* o = out + n * 3LL * h * w + (long long)y * w + x;
+    o[0] = (acc[0] - m0) * is0;
+    o[(long long)h * w] = (acc[1] - m1) * is1;
+    o[2LL * h * w] = (acc[2] - m2) * is2;
+  }
+}
+
 }  // namespace vdn
 
 using namespace vdn;
@@ -696,4 +754,17 @@ extern "C" int vdn_sobel_normals(const float* depth, float* normals, int32_t N, 
   sobel_normals_kernel<<<grid_for((long long)N * H * W, 256, 32), 256, 0, stream>>>(depth, normals, N, H, W, channels_out);
   count_launch();
   return check_launch("sobel_normals_kernel");
+}
+
+extern "C" int vdn_preprocess_u8(const void* frames, float* out, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, const float* mean3,
+                                 const float* std3, void* stream_v) {
+  VDN_STREAM;
+  if (!frames || !out || !mean3 || !std3) return set_error("vdn_preprocess_u8: null pointer");
+  if (N <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0) return set_error("vdn_preprocess_u8: bad shape");
+  const double sy = 1.0 / ((double)h / (double)H), sx = 1.0 / ((double)w / (double)W);  // OpenCV: scale = 1 / inv_scale
+  preprocess_u8_kernel<<<grid_for((long long)N * h * w, 256, 32), 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(frames), out, N, H, W, h, w, sy, sx,
+                                                                                      mean3[0], mean3[1], mean3[2], 1.0f / std3[0], 1.0f / std3[1],
+                                                                                      1.0f / std3[2]);
+  count_launch();
+  return check_launch("preprocess_u8_kernel");
 }

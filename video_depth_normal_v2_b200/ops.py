@@ -261,6 +261,15 @@ def cast_f32_to_16(x, out):
     return out
 
 
+def preprocess_u8(frames_u8, out, h: int, w: int, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """uint8 RGB [N, H, W, 3] (device) -> fp32 [N, 3, h, w]: /255, cv2.INTER_CUBIC-equivalent resize, ImageNet normalise."""
+    N, H, W = frames_u8.shape[:3]
+    m, s_ = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _check(_run("preprocess_u8", "hbm", 3.0 * N * H * W + 12.0 * N * h * w, lib().vdn_preprocess_u8, _ptr(frames_u8, torch.uint8, "frames"),
+                _ptr(out, torch.float32, "out"), N, H, W, h, w, m, s_, _stream()), "vdn_preprocess_u8")
+    return out
+
+
 def lsq_sums(pred, target, sums5):
     _check(lib().vdn_lsq_sums(_ptr(pred, torch.float32, "pred"), _ptr(target, torch.float32, "target"), pred.numel(), _ptr(sums5, torch.float64, "sums"),
                               _stream()), "vdn_lsq_sums")

@@ -186,10 +186,14 @@ class WindowForwarder:
     and resizes to ``out_hw``.  With ``reuse`` the encoder features of frames shared with the previous window are kept."""
 
     def __init__(self, model, frames_t: torch.Tensor, out_hw: Tuple[int, int], device, reuse: bool = True,
-                 frame_rows: Optional[Dict[int, int]] = None):
-        """``frame_rows``: source-frame index -> row of ``frames_t`` when only a rank's shard of the clip is resident."""
+                 frame_rows: Optional[Dict[int, int]] = None, net_hw: Optional[Tuple[int, int]] = None):
+        """``frame_rows``: source-frame index -> row of ``frames_t`` when only a rank's shard of the clip is resident.
+        ``frames_t`` is either pre-processed fp32 (N, 3, h, w) or raw uint8 RGB (N, H, W, 3) with ``net_hw`` = (h, w): raw frames are
+        uploaded as bytes and resized / normalised on the device (``vdn_preprocess_u8``), 4x less H2D traffic and no host cv2 loop."""
         self.model, self.frames_t, self.out_hw, self.device = model, frames_t, out_hw, device
         self.frame_rows = frame_rows
+        self.raw = frames_t.dtype == torch.uint8
+        self.net_hw = tuple(net_hw) if net_hw is not None else tuple(frames_t.shape[-2:])
         self.reuse = reuse and hasattr(model, "encode_frames")
         self.cache: Dict[int, List[torch.Tensor]] = {}
         self.encoded_frames = 0  # bookkeeping: encoder work actually done (frames)
@@ -205,6 +209,10 @@ class WindowForwarder:
                 run += 1
             x[pos:pos + run].copy_(self.frames_t[idx[pos]:idx[pos] + run], non_blocking=True)
             pos += run
+        if self.raw:
+            out = torch.empty((len(idx), 3) + self.net_hw, dtype=torch.float32, device=self.device)
+            ops.preprocess_u8(x, out, self.net_hw[0], self.net_hw[1])
+            return out
         return x
 
     def seed(self, feats: Dict[int, List[torch.Tensor]]):
@@ -217,7 +225,7 @@ class WindowForwarder:
 
     @torch.no_grad()
     def forward(self, win: Sequence[int]) -> torch.Tensor:
-        h, w = self.frames_t.shape[-2:]
+        h, w = self.net_hw
         H, W = self.out_hw
         if not self.reuse:
             d = self.model.forward(self._load(win).unsqueeze(0))[0]
@@ -247,6 +255,16 @@ class WindowForwarder:
         return d
 
 
+def _pinned_raw(frames: np.ndarray, indices: Optional[Sequence[int]]) -> torch.Tensor:
+    """The (selected) raw uint8 frames in page-locked memory, rows in the given order."""
+    sel = list(range(frames.shape[0])) if indices is None else list(indices)
+    t = torch.empty((len(sel),) + tuple(frames.shape[1:]), dtype=torch.uint8, pin_memory=True)
+    dst = t.numpy()
+    for row, i in enumerate(sel):
+        dst[row] = frames[i]
+    return t
+
+
 def _resolve_input_size(fh: int, fw: int, input_size: int) -> int:
     ratio = max(fh, fw) / min(fh, fw)
     if ratio > 1.78:  # video_depth.py:68-72
@@ -257,9 +275,12 @@ def _resolve_input_size(fh: int, fw: int, input_size: int) -> int:
 
 @torch.no_grad()
 def infer_video_depth(model, frames, target_fps, input_size=518, device="cuda", fp32=False, preprocessed: Optional[torch.Tensor] = None,
-                      reuse_features: bool = True, group=None, gather: str = "all"):
+                      reuse_features: bool = True, group=None, gather: str = "all", device_preprocess: bool = True):
     """video_depth.py:67-156.  ``fp32`` is accepted for signature compatibility: this path always accumulates in fp32 and its
     16-bit operands meet the fp32-reference tolerance.  Returns (np.float32 (N, H, W), target_fps).
+
+    ``device_preprocess``: upload the raw uint8 frames and run the cubic resize + normalisation on the GPU (default); False keeps the
+    reference's host-side cv2 transform.
 
     When ``torch.distributed`` is initialised with more than one rank (or ``group`` is given) the windows are sharded across
     the ranks; every rank must call with the same ``frames``.  ``gather='all'`` returns the full result on every rank,
@@ -279,17 +300,26 @@ def infer_video_depth(model, frames, target_fps, input_size=518, device="cuda", 
     if world > 1:
         rank = dist.get_rank(group)
         k0, k1 = partition_windows(len(windows), world)[rank]
-        frame_rows = None
-        if preprocessed is None:  # only this rank's frames are transformed and kept resident
+        frame_rows, net_hw = None, None
+        if preprocessed is None:  # only this rank's frames are kept resident (raw bytes, or transformed on the host)
             mine = sorted({f for win in windows[k0:k1] for f in win})
-            preprocessed = preprocess_frames(frames, input_size, indices=mine, pinned=True)
             frame_rows = {f: i for i, f in enumerate(mine)}
-        fwd = WindowForwarder(model, preprocessed, (fh, fw), model_dev, reuse=reuse_features, frame_rows=frame_rows)
+            if device_preprocess:
+                preprocessed, net_hw = _pinned_raw(frames, mine), _target_size(fw, fh, input_size)[::-1]
+            else:
+                preprocessed = preprocess_frames(frames, input_size, indices=mine, pinned=True)
+        fwd = WindowForwarder(model, preprocessed, (fh, fw), model_dev, reuse=reuse_features, frame_rows=frame_rows, net_hw=net_hw)
         out = sharded_video_depth(fwd.forward, windows, n, (fh, fw), model_dev, DeviceAlignOps(), group=group, gather=gather,
                                   forwarder=fwd if fwd.reuse else None)
         return (out.cpu().numpy() if out is not None else None), target_fps
-    ft = preprocessed if preprocessed is not None else preprocess_frames(frames, input_size, pinned=True)
-    fwd = WindowForwarder(model, ft, (fh, fw), model_dev, reuse=reuse_features)
+    net_hw = None
+    if preprocessed is not None:
+        ft = preprocessed
+    elif device_preprocess:
+        ft, net_hw = _pinned_raw(frames, None), _target_size(fw, fh, input_size)[::-1]
+    else:
+        ft = preprocess_frames(frames, input_size, pinned=True)
+    fwd = WindowForwarder(model, ft, (fh, fw), model_dev, reuse=reuse_features, net_hw=net_hw)
     aligner = WindowAligner(len(windows), fh, fw, model_dev)
     for win in windows:
         aligner.push(fwd.forward(win))
