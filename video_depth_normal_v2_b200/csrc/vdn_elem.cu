@@ -345,7 +345,9 @@ __device__ __forceinline__ void ac_coords(int dst, float scale, int in_size, int
 // grid (x-chunks of one output row, Ho, B): row coordinates are block-uniform, only 32-bit index arithmetic per thread
 // (the flat 64-bit div/mod version was instruction-bound at ~30 % of HBM bandwidth).  Each thread produces 8 channels of one
 // output pixel from four 16-byte loads (neighbouring pixels hit L1/L2) and writes one or two 16-byte results.
-template <int FMT>
+// VPT 16-byte channel vectors of one output pixel per thread: the coordinate / weight arithmetic is per pixel, and with one vector
+// per thread the kernel was issue-bound (87 % issue-active, 3.1 TB/s at 128 channels).
+template <int FMT, int RELU2, int VPT>
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4* __restrict__ o_relu, int H, int W, int Ho, int Wo, int cv,
                      int relu_out) {
@@ -358,34 +360,47 @@ bilinear_nhwc_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4
   ac_coords(ho, sh, H, h0, h1, lh);
   const uint4* row0 = xin + (bimg * H + h0) * (long long)W * cv;
   const uint4* row1 = xin + (bimg * H + h1) * (long long)W * cv;
-  const long long obase = (bimg * Ho + ho) * (long long)Wo * cv;
-  const int per_row = Wo * cv;
+  uint4* orow = o + (bimg * Ho + ho) * (long long)Wo * cv;
+  uint4* orow_relu = RELU2 ? o_relu + (bimg * Ho + ho) * (long long)Wo * cv : nullptr;
+  const int cq = cv / VPT;          // threads per pixel
+  const int per_row = Wo * cq;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
-    const int wo = i / cv;
-    const int c8 = i - wo * cv;
+    const int wo = i / cq;
+    const int c8 = i - wo * cq;     // this thread's vectors: c8, c8 + cq, c8 + 2 cq, ...
     int w0, w1;
     float lw;
     ac_coords(wo, sw, W, w0, w1, lw);
-    const uint4 a = __ldg(row0 + w0 * cv + c8);
-    const uint4 b = __ldg(row0 + w1 * cv + c8);
-    const uint4 c = __ldg(row1 + w0 * cv + c8);
-    const uint4 d = __ldg(row1 + w1 * cv + c8);
     const float w00 = (1.0f - lh) * (1.0f - lw), w01 = (1.0f - lh) * lw, w10 = lh * (1.0f - lw), w11 = lh * lw;
-    const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
-    uint4 r, rr;
-    uint32_t* pr = &r.x;
-    uint32_t* prr = &rr.x;
+    const uint4* pa4 = row0 + w0 * cv + c8;
+    const uint4* pb4 = row0 + w1 * cv + c8;
+    const uint4* pc4 = row1 + w0 * cv + c8;
+    const uint4* pd4 = row1 + w1 * cv + c8;
+    uint4 a[VPT], b[VPT], c[VPT], d[VPT];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fa = T16f<FMT>::unpack(pa[k]), fb = T16f<FMT>::unpack(pb[k]), fc = T16f<FMT>::unpack(pc[k]), fd = T16f<FMT>::unpack(pd[k]);
-      float y0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
-      float y1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
-      if (relu_out) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
-      pr[k] = T16f<FMT>::pack(y0, y1);
-      prr[k] = T16f<FMT>::pack(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f));
+    for (int v = 0; v < VPT; ++v) {
+      a[v] = __ldg(pa4 + v * cq);
+      b[v] = __ldg(pb4 + v * cq);
+      c[v] = __ldg(pc4 + v * cq);
+      d[v] = __ldg(pd4 + v * cq);
     }
-    o[obase + i] = r;
-    if (o_relu != nullptr) o_relu[obase + i] = rr;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const uint32_t* pa = &a[v].x; const uint32_t* pb = &b[v].x; const uint32_t* pc = &c[v].x; const uint32_t* pd = &d[v].x;
+      uint4 r, rr;
+      uint32_t* pr = &r.x;
+      uint32_t* prr = &rr.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = T16f<FMT>::unpack(pa[k]), fb = T16f<FMT>::unpack(pb[k]), fc = T16f<FMT>::unpack(pc[k]), fd = T16f<FMT>::unpack(pd[k]);
+        float y0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
+        float y1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+        if (relu_out) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
+        pr[k] = T16f<FMT>::pack(y0, y1);
+        if (RELU2) prr[k] = T16f<FMT>::pack(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f));
+      }
+      orow[wo * cv + c8 + v * cq] = r;
+      if (RELU2) orow_relu[wo * cv + c8 + v * cq] = rr;
+    }
   }
 }
 
@@ -664,8 +679,19 @@ static int launch_bilinear_nhwc(const void* x, void* out, void* out_relu, int B,
   const uint4* xi = reinterpret_cast<const uint4*>(x);
   uint4* o = reinterpret_cast<uint4*>(out);
   uint4* orl = reinterpret_cast<uint4*>(out_relu);
-  if (get_operand_format()) bilinear_nhwc_kernel<1><<<grid, 256, 0, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, relu_out);
-  else bilinear_nhwc_kernel<0><<<grid, 256, 0, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, relu_out);
+  const int fmt = get_operand_format();
+  const int vpt = (cv % 4 == 0) ? 4 : 1;
+  dim3 g2((Wo * (cv / vpt) + 255) / 256, Ho, B);
+  if (g2.x > 8) g2.x = 8;
+#define VDN_BIL(F, R, V) bilinear_nhwc_kernel<F, R, V><<<g2, 256, 0, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, relu_out)
+  if (orl != nullptr) {
+    if (fmt) { if (vpt == 4) VDN_BIL(1, 1, 4); else VDN_BIL(1, 1, 1); }
+    else { if (vpt == 4) VDN_BIL(0, 1, 4); else VDN_BIL(0, 1, 1); }
+  } else {
+    if (fmt) { if (vpt == 4) VDN_BIL(1, 0, 4); else VDN_BIL(1, 0, 1); }
+    else { if (vpt == 4) VDN_BIL(0, 0, 4); else VDN_BIL(0, 0, 1); }
+  }
+#undef VDN_BIL
   count_launch();
   return check_launch("bilinear_nhwc_kernel");
 }

@@ -64,6 +64,7 @@ struct GemmKParams {
   const float* head_w;
   float head_b;
   int qkv_split, qkv_tpo, qkv_toff;
+  int qkv_tma;  // the q|k columns leave through smem staging + TMA store (identity row placement only)
 };
 
 // HALO convolution (3x3, spatial tile 16 rows x 8 pixels): per 64-channel chunk the A operand is three column-shifted haloed
@@ -80,7 +81,7 @@ struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = HALO ? kStageBytesB : kStageBytesA + kStageBytesB;  // HALO: the ring holds B (per-tap) tiles only
-  static constexpr int kStagingBytes = EPI == EPI_TMA ? kNumEpiWarps * kStagingBytesPerWarp : 0;
+  static constexpr int kStagingBytes = (EPI == EPI_TMA || EPI == EPI_QKV) ? kNumEpiWarps * kStagingBytesPerWarp : 0;
   static constexpr int kARingBytes = HALO ? kHaloAStages * kHaloABytes : 0;
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kARingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -323,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if constexpr (EPI == EPI_TMA) tma_prefetch_desc(&tmC);
+    if constexpr (EPI == EPI_TMA || EPI == EPI_QKV) tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -680,6 +681,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // the accumulator registers are free again: next chunk's TMEM load runs under this chunk's math and stores
         if (c + 1 < c_end) tmem_ld32(t_row + (c + 1) * 32, accr);
+        if constexpr (EPI == EPI_QKV) {
+          if (p.qkv_tma && n0 < p.qkv_split) {  // warp-uniform: q|k chunk -> 64B-swizzled staging tile -> TMA store (rows >= M are clipped)
+            uint8_t* buf = smem_stg + e * kStagingBytesPerWarp + (c & 1) * 2048;
+            if (elect_one()) tma_store_wait_read<1>();
+            __syncwarp();
+            uint8_t* rowp = buf + lane * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(rowp + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pack2<FMT>(v[8 * k], v[8 * k + 1]), pack2<FMT>(v[8 * k + 2], v[8 * k + 3]), pack2<FMT>(v[8 * k + 4], v[8 * k + 5]),
+                             pack2<FMT>(v[8 * k + 6], v[8 * k + 7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              tma_store_2d(&tmC, buf, n0, m_tile * BLOCK_M + quarter * 32);
+              tma_store_commit();
+            }
+            return;
+          }
+        }
         if (rc.valid && n0 < p.N) {
           if constexpr (EPI == EPI_RES) {
             epi_plain<FMT>(p, rc, n0, c * 32, v, rb, r2, (c + 2 < c_end) ? nb + (c + 2) * 32 : -1, (c + 1 < c_end) ? nb + (c + 1) * 32 : -1, sgamma);
@@ -704,7 +725,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
-    if constexpr (EPI == EPI_TMA) {
+    if constexpr (EPI == EPI_TMA || EPI == EPI_QKV) {
       if (elect_one()) tma_store_wait_all();  // staging memory and the global writes must outlive the bulk copies
       __syncwarp();
     }
@@ -837,6 +858,7 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
   p.qkv_split = d->qkv_split > 0 ? d->qkv_split : 2 * d->rm2;
   p.qkv_tpo = d->qkv_tokens_out > 0 ? d->qkv_tokens_out : d->rm0;
   p.qkv_toff = d->qkv_token_offset;
+  p.qkv_tma = 0;
   p.conv = d->conv;
   int epi = EPI_PLAIN;
   if (d->head_w != nullptr) epi = EPI_HEAD;
@@ -923,6 +945,14 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     if (make_tensor_map(&tmB, d->w, fmt, 2, dims, strides, box)) return 1;
   }
   CUtensorMap tmC = tmB;  // placeholder unless the TMA epilogue is used
+  if (epi == EPI_QKV && p.qkv_tpo == d->rm0 && p.qkv_toff == 0 && (d->ldc * 2) % 16 == 0 && p.qkv_split % 32 == 0 && getenv("VDN_NO_TMA_EPI") == nullptr) {
+    // q|k rows land at their own row index: one 32 x 32 box per warp chunk
+    const uint64_t dims[2] = {(uint64_t)p.qkv_split, (uint64_t)d->M};
+    const uint64_t strides[1] = {(uint64_t)d->ldc * 2};
+    const uint32_t box[2] = {32u, 32u};
+    if (make_tensor_map_ex(&tmC, d->out, fmt, 64, 2, dims, strides, box)) return 1;
+    p.qkv_tma = 1;
+  }
   if (epi == EPI_TMA) {
     const int es = d->out_f32 ? 4 : 2;
     const uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
