@@ -26,6 +26,10 @@ constexpr int FA_GROUPS = 2;   // query tiles per CTA, processed ping-pong by tw
 constexpr int FA_THREADS = FA_GROUPS * 128 + 128;  // + one control warpgroup: MMA issuer warp, TMA producer warp, 2 idle warps
 constexpr int FA_TILE = FA_BM * FA_D * 2;         // 16 KB : one Q / K / V^T tile
 constexpr int FA_SMEM = 2 * FA_TILE /*Q*/ + 2 * FA_TILE /*K x2*/ + 2 * FA_TILE /*V^T x2*/ + 256;
+#ifndef VDN_FA_POLY
+#define VDN_FA_POLY 2
+#endif
+constexpr int FA_POLY = VDN_FA_POLY;  // of every 8 scores, this many take 2^x on the FMA pipe (exp2_poly), the rest on the XU pipe
 constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
 
 // The softmax of a head_dim-64 attention is bound by the XU pipe: one ex2 per score at 8 cycles per warp instruction per SM
@@ -285,7 +289,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 8; ++i) pv[i] = fmaf(__uint_as_float(sv[8 * q + i]), sc, -m_new);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(pv[i]);
+            for (int i = 0; i < 8; ++i) pv[i] = (i < FA_POLY) ? exp2_poly(pv[i]) : ex2_approx(pv[i]);
             sum0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
             sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
 #pragma unroll

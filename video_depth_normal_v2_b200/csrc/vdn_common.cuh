@@ -105,6 +105,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
+// (max relative error 7.6e-5, an order of magnitude below the 16-bit rounding of the probabilities it feeds) and the integer n added
+// into the exponent field.  x is clamped to >= -125 (result ~2e-38, i.e. 0 after rounding; also maps -inf of masked keys to ~0).
+// 1 FMNMX + 3 FADD + 3 FFMA + 1 IMAD versus one 8-cycle MUFU.EX2: used for a fraction of the softmax scores so that the XU pipe
+// and the FMA pipe are both busy (the attention kernel is bound by the XU pipe otherwise).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float n = t - 12582912.0f;
+  const float f = x - n;
+  float p = fmaf(0.05520550534129143f, f, 0.24261397123336792f);
+  p = fmaf(p, f, 0.6932547688484192f);
+  p = fmaf(p, f, 0.9999276995658875f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // Stage-major over a batch of N independent elements: the compiler keeps the statement order, so the N dependency chains are
 // interleaved (the scalar version was scheduled chain-by-chain: per-warp IPC 0.09 in the fc1 epilogue).
 template <int N>
