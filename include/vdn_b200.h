@@ -125,6 +125,9 @@ int vdn_groupnorm_apply_tc(const void* x, const float* stats, const float* w, co
 int vdn_patch_im2col(const float* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Kp, void* stream);
 /* x[b, 0, :] = cls + pos[0]  for every frame (dinov2.py:219-220) */
 int vdn_write_cls(float* x, const float* cls, const float* pos, int32_t B, int32_t tokens, int32_t C, void* stream);
+/* use_clstoken readout input (dpt.py:129-132, dpt_temporal.py:56-59): normed tokens xn [frames*tokens, C] (row 0 of a frame = cls) ->
+   out [frames*(tokens-1), 2C] = [patch token | that frame's cls token], the operand of readout_projects[i] (Linear 2C->C + GELU) */
+int vdn_readout_concat(const void* xn, void* out, int64_t frames, int32_t tokens, int32_t C, void* stream);
 /* im2col for the 3x3 stride-2 pad-1 conv (dpt.py:84-89): NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] */
 int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* bilinear resize, align_corners=True, NHWC 16-bit (F.interpolate at util/blocks.py:155-157, dpt_temporal.py:104-106).
@@ -173,6 +176,10 @@ int vdn_v5_residual(const float* din, const float* o, const float* scale, float*
    cos_sin [P, 64] fp32 = cos[32] | sin[32] per position (sam2/modeling/position_encoding.py:186-239) */
 int vdn_rope2d(void* x, int64_t rows, int64_t ld, int32_t col0, int32_t heads, const float* cos_sin, int32_t P, int64_t rows_per_batch,
                int64_t batch_pitch, void* stream); /* rows_per_batch consecutive rows per batch, batches batch_pitch rows apart (0 -> dense) */
+/* temporal RoPE (pe='rope', motion_module.py:236-240,279-282; attention.py:403-429): rotate `chunks` 64-wide column chunks starting at
+   col0 of 16-bit rows [rows, ld] in place; row r is frame r % P; cos_sin [P, chunks, 64] fp32 = cos[32] | sin[32] per (frame, chunk) —
+   the reference's frequencies run over the whole query_dim, so every chunk has its own table */
+int vdn_rope_chunks(void* x, int64_t rows, int64_t ld, int32_t col0, int32_t chunks, const float* cos_sin, int32_t P, void* stream);
 /* out_f32[r, c] = x[r, c] + alpha * vec[c]   (x fp32 or 16-bit; in place allowed for fp32) */
 int vdn_add_rowvec(const void* x, int32_t x_f32, const float* vec, float alpha, float* out, int64_t rows, int32_t C, void* stream);
 /* x[r, :] += m[r] */

@@ -134,7 +134,7 @@ def _dpt_head(sd, g, prefix, cfg):
     sd[prefix + "scratch.output_conv2.2.bias"] = torch.full((1,), 0.05)
 
 
-def _motion_modules(sd, g, prefix, cfg):
+def _motion_modules(sd, g, prefix, cfg, pe="ape"):
     oc, F = cfg["out_channels"], cfg["features"]
     for m, C in enumerate([oc[2], oc[3], F, F]):
         p = f"{prefix}motion_modules.{m}.temporal_transformer."
@@ -147,7 +147,8 @@ def _motion_modules(sd, g, prefix, cfg):
             _default_linear(sd, g, ab + "to_k", C, C, bias=False)
             _default_linear(sd, g, ab + "to_v", C, C, bias=False)
             _default_linear(sd, g, ab + "to_out.0", C, C)
-            sd[ab + "pos_encoder.pe"] = sinusoid_pe(C)
+            if pe == "ape":  # pe='rope' keeps freqs_cis as a plain attribute, not in the state_dict (motion_module.py:236-240)
+                sd[ab + "pos_encoder.pe"] = sinusoid_pe(C)
         for a in range(2):
             _norm_affine(sd, g, f"{tb}norms.{a}", C)
         _default_linear(sd, g, tb + "ff.net.0.proj", 8 * C, C)
@@ -191,7 +192,7 @@ def _memory_block(sd, g, prefix, cfg, max_len=6, layers=4):
         _default_linear(sd, g, p + "pwconv2", C, 4 * C)
 
 
-def make_state_dict(model: str, encoder: str, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+def make_state_dict(model: str, encoder: str, seed: int = 0, use_clstoken: bool = False, pe: str = "ape") -> "OrderedDict[str, torch.Tensor]":
     """model in {'vda', 'v5', 'da2'}; returns fp32 CPU tensors under the reference's key names.
 
     'vda' = video_depth_anything/video_depth.py:35-56 (prefixes ``pretrained.`` / ``head.``)
@@ -205,7 +206,11 @@ def make_state_dict(model: str, encoder: str, seed: int = 0) -> "OrderedDict[str
     _encoder(sd, g, "pretrained.", cfg)
     if model == "vda":
         _dpt_head(sd, g, "head.", cfg)
-        _motion_modules(sd, g, "head.", cfg)
+        _motion_modules(sd, g, "head.", cfg, pe)
+        if use_clstoken:  # dpt.py:92-98; drawn last so the other tensors do not depend on the switch
+            C = cfg["embed_dim"]
+            for i in range(4):
+                _default_linear(sd, g, f"head.readout_projects.{i}.0", C, 2 * C)
     elif model == "v5":
         sd["scale_head.feat.1.weight"] = g.normal((1, 1, 1, 1), 0.5)
         sd["scale_head.feat.1.bias"] = g.normal((1,), 0.5)

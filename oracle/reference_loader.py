@@ -32,13 +32,14 @@ def _install_shims():
         sys.modules["easydict"] = types.SimpleNamespace(EasyDict=EasyDict)
 
 
-def load_vda(encoder: str, state_dict):
-    """Reference VideoDepthAnything (video_depth_anything/video_depth.py:35) with our recipe weights, strict."""
+def load_vda(encoder: str, state_dict, **kw):
+    """Reference VideoDepthAnything (video_depth_anything/video_depth.py:35) with our recipe weights, strict.
+    ``kw``: use_clstoken / pe constructor switches."""
     from .init_recipe import ENCODERS
     _install_shims()
     from video_depth_anything.video_depth import VideoDepthAnything
     cfg = ENCODERS[encoder]
-    m = VideoDepthAnything(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
+    m = VideoDepthAnything(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"], **kw).eval()
     m.load_state_dict(state_dict, strict=True)
     return m
 
@@ -50,6 +51,17 @@ def load_v5(encoder: str, state_dict):
     from models.video_depth_model_v5 import VideoDepthAnything as V5
     cfg = ENCODERS[encoder]
     m = V5(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
+    m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+def load_v4(encoder: str, state_dict):
+    """Reference models/video_depth_model_v4.py:88 VideoDepthAnything (v5 without the 224x224 resize; same keys), strict."""
+    from .init_recipe import ENCODERS
+    _install_shims()
+    from models.video_depth_model_v4 import VideoDepthAnything as V4
+    cfg = ENCODERS[encoder]
+    m = V4(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
     m.load_state_dict(state_dict, strict=True)
     return m
 
@@ -66,12 +78,12 @@ def load_da2(encoder: str, state_dict):
     return m
 
 
-def load_vda_stream(encoder: str, state_dict):
+def load_vda_stream(encoder: str, state_dict, **kw):
     """Reference streaming model (video_depth_anything/video_depth_stream.py:32), same weights / keys as load_vda, strict."""
     from .init_recipe import ENCODERS
     _install_shims()
     from video_depth_anything.video_depth_stream import VideoDepthAnything as VDAStream
     cfg = ENCODERS[encoder]
-    m = VDAStream(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
+    m = VDAStream(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"], **kw).eval()
     m.load_state_dict(state_dict, strict=True)
     return m

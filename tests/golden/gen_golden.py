@@ -29,7 +29,15 @@ VDA_CASES = [
     ("vda_vits_t2_518x518", "vits", 2, 518, 518, 1, 4),   # native 37x37 grid -> pos_embed untouched branch
     ("vda_vitl_t2_56x70", "vitl", 2, 56, 70, 2, 1),
 ]
+# (name, encoder, T, H, W, seed, constructor switches): SURVEY §8f rank 3 — pe='rope' motion modules and the use_clstoken readout
+VDA_SWITCH_CASES = [
+    ("vda_vits_t4_70x84_rope", "vits", 4, 70, 84, 9, {"pe": "rope"}),
+    ("vda_vits_t4_70x84_cls", "vits", 4, 70, 84, 10, {"use_clstoken": True}),
+    ("vda_vitl_t3_56x70_rope_cls", "vitl", 3, 56, 70, 11, {"pe": "rope", "use_clstoken": True}),
+]
+STREAM_SWITCH_CASES = [("stream_vits_n5_56x70_rope_cls", "vits", 5, 56, 70, 12, {"pe": "rope", "use_clstoken": True})]
 V5_CASES = [("v5_vits_s4_60x80", "vits", 4, 60, 80, 3)]
+V4_CASES = [("v4_vits_s4_56x84", "vits", 4, 56, 84, 14)]  # models/video_depth_model_v4.py: network at the native resolution
 # (name, encoder, batch, H(=W), calls, seed, stride): DepthAnythingV2 is stateful -> a sequence of forward() calls on one model
 DA2_CASES = [("da2_vits_b2_70_calls8", "vits", 2, 70, 8, 5, 1), ("da2_vits_b1_518_calls2", "vits", 1, 518, 2, 6, 4), ("da2_vitl_b1_70_calls3", "vitl", 1, 70, 3, 7, 1)]
 # (name, encoder, frames, H, W, seed): streaming inference, one infer_video_depth_one call per frame (window slides after frame 10)
@@ -78,15 +86,50 @@ def gen_stream():
         del m
 
 
+def gen_v4():
+    for name, enc, S, H, W, seed in V4_CASES:
+        sd = make_state_dict("v5", enc, seed)  # v4 and v5 share the module tree / key names
+        m = RL.load_v4(enc, sd)
+        d = make_input("depth", (1, S, H, W), seed)
+        y = m(d)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), out=y.numpy(), meta=np.array([S, H, W, seed]))
+        print(name, tuple(y.shape), float((y - d).abs().mean()))
+        del m
+
+
+def gen_switches():
+    for name, enc, T, H, W, seed, kw in VDA_SWITCH_CASES:
+        sd = make_state_dict("vda", enc, seed, **kw)
+        m = RL.load_vda(enc, sd, **kw)
+        y = m(make_input("rgb", (1, T, 3, H, W), seed))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), depth=y.numpy(), meta=np.array([T, H, W, seed]))
+        print(name, tuple(y.shape), float(y.mean()), float(y.min()))
+        del m
+    for name, enc, N, H, W, seed, kw in STREAM_SWITCH_CASES:
+        sd = make_state_dict("vda", enc, seed, **kw)
+        m = RL.load_vda_stream(enc, sd, **kw)
+        frames = video_frames(N, H, W, seed)
+        outs = [m.infer_video_depth_one(frames[i], input_size=min(H, W), device="cpu", fp32=True) for i in range(N)]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), depths=np.stack(outs).astype(np.float32), meta=np.array([N, H, W, seed]))
+        print(name, np.stack(outs).shape, float(np.stack(outs).mean()))
+        del m
+
+
 def main():
     assert RL.available(), "reference not present"
     torch.set_grad_enabled(False)
+    if len(sys.argv) > 1 and sys.argv[1] == "switches":
+        return gen_switches()
+    if len(sys.argv) > 1 and sys.argv[1] == "v4":
+        return gen_v4()
     if len(sys.argv) > 1 and sys.argv[1] == "da2":
         return gen_da2()
     if len(sys.argv) > 1 and sys.argv[1] == "stream":
         return gen_stream()
     gen_da2()
     gen_stream()
+    gen_switches()
+    gen_v4()
     for name, enc, T, H, W, seed, stride in VDA_CASES:
         sd = make_state_dict("vda", enc, seed)
         m = RL.load_vda(enc, sd)

@@ -241,3 +241,65 @@ def test_streaming_infer_video_depth_one_matches_reference_golden(vdn):
     m.reset_stream()
     d0 = m.infer_video_depth_one(frames[0], input_size=min(H, W), device="cuda")
     _check("stream frame 0 after reset", torch.from_numpy(d0)[None], torch.from_numpy(g["depths"][0])[None])
+
+
+# ------------------------------------------------------------------------------------------ f3: pe='rope' / use_clstoken=True
+def _model_kw(vdn, enc, seed, **kw):
+    cfg = ENCODERS[enc]
+    m = vdn.VideoDepthAnything(encoder=enc, features=cfg["features"], out_channels=cfg["out_channels"], **kw).cuda().eval()
+    sd = make_state_dict("vda", enc, seed, **kw)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+@pytest.mark.parametrize("name,enc,kw", [("vda_vits_t4_70x84_rope", "vits", {"pe": "rope"}), ("vda_vits_t4_70x84_cls", "vits", {"use_clstoken": True}),
+                                         ("vda_vitl_t3_56x70_rope_cls", "vitl", {"pe": "rope", "use_clstoken": True})])
+def test_switches_match_reference_golden(vdn, name, enc, kw):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    T, H, W, seed = [int(v) for v in g["meta"]]
+    m, sd = _model_kw(vdn, enc, seed, **kw)
+    y = m(make_input("rgb", (1, T, 3, H, W), seed).cuda())
+    _check(name, y, torch.from_numpy(g["depth"]))
+    with pytest.raises(RuntimeError):  # strict key check: a default-config state_dict does not fit a switched model
+        m.load_state_dict(make_state_dict("vda", enc, seed))
+
+
+def test_rope_window_of_32_on_the_tensor_core_temporal_kernel(vdn):
+    """T = 32 ViT-L takes the tcgen05 temporal-attention path (q|k row-major, V transposed per tile): RoPE is applied to the q|k buffer."""
+    kw = {"pe": "rope", "use_clstoken": True}
+    m, sd = _model_kw(vdn, "vitl", 13, **kw)
+    x = make_input("rgb", (1, 32, 3, 28, 42), 13)
+    y = m(x.cuda())
+    dev_sd = {k: v.cuda() for k, v in sd.items()}
+    ref = O.vda_forward(dev_sd, x.cuda(), "vitl")
+    _check("rope+cls vitl T=32", y, ref)
+
+
+def test_streaming_rope_cls_matches_reference_golden(vdn):
+    import sys
+    sys.path.insert(0, GOLD)
+    from gen_golden import video_frames
+    g = np.load(os.path.join(GOLD, "stream_vits_n5_56x70_rope_cls.npz"))
+    N, H, W, seed = [int(v) for v in g["meta"]]
+    m, _ = _model_kw(vdn, "vits", seed, pe="rope", use_clstoken=True)
+    frames = video_frames(N, H, W, seed)
+    for i in range(N):
+        d = m.infer_video_depth_one(frames[i], input_size=min(H, W), device="cuda")
+        _check(f"stream rope+cls frame {i}", torch.from_numpy(d)[None], torch.from_numpy(g["depths"][i])[None])
+
+
+# ------------------------------------------------------------------------------------------ f4: v4 refinement model (native resolution)
+def test_v4_refiner_matches_reference_golden(vdn):
+    """models/video_depth_model_v4.py:120-148 = the v5 tree without the 224x224 resize, against the live reference's output."""
+    g = np.load(os.path.join(GOLD, "v4_vits_s4_56x84.npz"))
+    S, H, W, seed = [int(v) for v in g["meta"]]
+    cfg = ENCODERS["vits"]
+    sd = make_state_dict("v5", "vits", seed)
+    m = vdn.VideoDepthRefinerV4(encoder="vits", features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
+    m.load_state_dict(sd)
+    y = m(make_input("depth", (1, S, H, W), seed).cuda())
+    assert y.shape == (1, S, H, W) and y.dtype == torch.float32
+    e = _check("v4_vits_s4_56x84 vs reference", y / 65535.0, torch.from_numpy(g["out"]) / 65535.0, floor_frac=0.05)
+    assert e["max_abs"] <= 1e-3
+    with pytest.raises(RuntimeError):  # patch_embed.py:73-74 through the native-resolution path
+        m(make_input("depth", (1, 2, 60, 84), seed).cuda())

@@ -322,7 +322,12 @@ def test_im2col_3x3_s2(ops):
     assert torch.equal(out.float(), ref)
 
 
-@pytest.mark.parametrize("H,W,Ho,Wo,C", [(19, 19, 37, 37, 64), (37, 37, 74, 74, 256), (10, 12, 20, 24, 64), (40, 48, 70, 84, 32), (5, 6, 5, 6, 8)])
+@pytest.mark.parametrize("H,W,Ho,Wo,C", [(19, 19, 37, 37, 64), (37, 37, 74, 74, 256), (10, 12, 20, 24, 64), (40, 48, 70, 84, 32), (5, 6, 5, 6, 8),
+                                         (60, 296, 105, 518, 128),   # several wo tiles per row (row-staged kernel)
+                                         (33, 400, 12, 90, 64),      # down-scaling: few output pixels per staged tile
+                                         (7, 9, 50, 301, 96),        # large up-scaling, 32-channel chunks
+                                         (21, 1, 40, 1, 64), (1, 17, 1, 40, 64), (9, 11, 1, 1, 64),  # degenerate extents
+                                         (12, 14, 24, 28, 48)])      # C % 32 != 0: gather kernel
 def test_bilinear_nhwc(ops, H, W, Ho, Wo, C):
     od = ops.operand_dtype()
     x = _r16(ops, 2, H, W, C, seed=1)
@@ -331,6 +336,22 @@ def test_bilinear_nhwc(ops, H, W, Ho, Wo, C):
     torch.cuda.synchronize()
     ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
     _close("bilinear nhwc", out, ref)
+
+
+@pytest.mark.parametrize("H,W,Ho,Wo,C", [(37, 37, 74, 74, 64), (20, 296, 35, 518, 32), (12, 14, 24, 28, 24)])
+def test_bilinear_nhwc_relu_variants(ops, H, W, Ho, Wo, C):
+    od = ops.operand_dtype()
+    x = _r16(ops, 2, H, W, C, seed=2)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    out = torch.empty(2, Ho, Wo, C, device="cuda", dtype=od)
+    ops.bilinear_nhwc(x, out, 2, H, W, Ho, Wo, C, relu_out=True)
+    torch.cuda.synchronize()
+    _close("bilinear nhwc relu", out, F.relu(ref))
+    o1, o2 = torch.empty_like(out), torch.empty_like(out)
+    ops.bilinear_nhwc2(x, o1, o2, 2, H, W, Ho, Wo, C)
+    torch.cuda.synchronize()
+    _close("bilinear nhwc2 plain", o1, ref)
+    assert torch.equal(o2, F.relu(o1))
 
 
 def test_bilinear_f32_and_relu(ops):

@@ -131,3 +131,54 @@ def test_stream_steps_match_reference():
         ref = torch.from_numpy(g["depths"][i])
         assert (y - ref).abs().max() / ref.abs().max() < 2e-4, i
     assert len(state["cache"]) == 42
+
+
+# ------------------------------------------------------------------------------------------ f3: constructor switches
+SWITCH_CASES = [("vda_vits_t4_70x84_rope", "vits", {"pe": "rope"}), ("vda_vits_t4_70x84_cls", "vits", {"use_clstoken": True}),
+                ("vda_vitl_t3_56x70_rope_cls", "vitl", {"pe": "rope", "use_clstoken": True})]
+
+
+@pytest.mark.parametrize("name,enc,kw", SWITCH_CASES)
+def test_vda_switches_match_reference(name, enc, kw):
+    """pe='rope' (motion_module.py:236-240,279-282; attention.py:403-429) and use_clstoken=True (dpt.py:92-98,129-132)."""
+    g = _load(name)
+    T, H, W, seed = [int(v) for v in g["meta"]]
+    sd = make_state_dict("vda", enc, seed, **kw)
+    assert any("pos_encoder.pe" in k for k in sd) == (kw.get("pe", "ape") == "ape")
+    assert any("readout_projects" in k for k in sd) == bool(kw.get("use_clstoken"))
+    y = O.vda_forward(sd, make_input("rgb", (1, T, 3, H, W), seed), enc)
+    e = O.depth_errors(y, torch.from_numpy(g["depth"]))
+    assert e["max_rel"] < RTOL, e
+    # the switch changes the function (the golden is not the default model's output)
+    base = {k: v for k, v in make_state_dict("vda", enc, seed).items()}
+    y0 = O.vda_forward(base, make_input("rgb", (1, T, 3, H, W), seed), enc)
+    assert float((y0 - y).abs().mean() / y.abs().mean()) > 5e-3
+
+
+def test_stream_steps_rope_cls_match_reference():
+    """Streaming with pe='rope': a one-frame query makes the reference rotate by freqs_cis[:1] = identity (see temporal_attention)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from gen_golden import video_frames
+    from video_depth_normal_v2_b200 import video as V
+    g = _load("stream_vits_n5_56x70_rope_cls")
+    N, H, W, seed = [int(v) for v in g["meta"]]
+    sd = make_state_dict("vda", "vits", seed, pe="rope", use_clstoken=True)
+    ft = torch.from_numpy(V.preprocess_frames(video_frames(N, H, W, seed), min(H, W)))
+    state = {}
+    for i in range(N):
+        y = O.vda_stream_step(sd, ft[i][None, None], "vits", state)
+        ref = torch.from_numpy(g["depths"][i])
+        assert (y - ref).abs().max() / ref.abs().max() < 2e-4, i
+
+
+def test_v4_forward_matches_reference():
+    """models/video_depth_model_v4.py:120-148 (network at the native resolution): v5_forward(net_size=None)."""
+    g = _load("v4_vits_s4_56x84")
+    S, H, W, seed = [int(v) for v in g["meta"]]
+    sd = make_state_dict("v5", "vits", seed)
+    d = make_input("depth", (1, S, H, W), seed)
+    y = O.v5_forward(sd, d, "vits", net_size=None)
+    ref = torch.from_numpy(g["out"])
+    assert (y - ref).abs().max() / ref.abs().max() < 1e-4
+    assert (O.v5_forward(sd, d, "vits") - ref).abs().max() / ref.abs().max() > 1e-3  # the 224x224 variant is a different function

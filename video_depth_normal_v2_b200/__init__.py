@@ -7,7 +7,7 @@ Host code is Python; every device kernel lives in the in-tree C-ABI library ``li
 from . import ops  # noqa: F401
 from . import torch_ops  # noqa: F401  (registers torch.ops.vdn.*)
 
-_LAZY = {"VideoDepthAnything": "models", "VideoDepthRefinerV5": "models", "ENCODER_CONFIGS": "models", "DepthAnythingV2": "da2"}
+_LAZY = {"VideoDepthAnything": "models", "VideoDepthRefinerV5": "models", "VideoDepthRefinerV4": "models", "ENCODER_CONFIGS": "models", "DepthAnythingV2": "da2"}
 
 
 def __getattr__(name):

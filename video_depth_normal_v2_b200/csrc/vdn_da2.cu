@@ -13,7 +13,7 @@ namespace vdn {
 template <int FMT>
 __global__ void __launch_bounds__(256)
 rope2d_kernel(uint4* __restrict__ x, long long rows, int ld8 /*row pitch in 16-byte units*/, int col8 /*first column / 8*/, int heads,
-              const float* __restrict__ cs, int P, long long rows_per_batch, long long batch_pitch) {
+              const float* __restrict__ cs, int P, long long rows_per_batch, long long batch_pitch, int per_head /*table row = (pos, head)*/) {
   const long long total = rows * heads * 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int v = int(idx & 7);  // 16-byte piece of the 64-wide head: pairs 4v .. 4v+3
@@ -26,8 +26,9 @@ rope2d_kernel(uint4* __restrict__ x, long long rows, int ld8 /*row pitch in 16-b
     uint4* p = x + phys * ld8 + col8 + h * 8 + v;
     uint4 u = *p;
     uint32_t* w = &u.x;
-    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + (long long)pos * 64 + 4 * v));
-    const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + (long long)pos * 64 + 32 + 4 * v));
+    const long long trow = per_head ? (long long)pos * heads + h : (long long)pos;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + trow * 64 + 4 * v));
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + trow * 64 + 32 + 4 * v));
     const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -217,8 +218,20 @@ extern "C" int vdn_rope2d(void* x, int64_t rows, int64_t ld, int32_t col0, int32
   if (rows_per_batch <= 0) { rows_per_batch = rows; batch_pitch = rows; }
   if (rows_per_batch % P != 0 || batch_pitch < rows_per_batch) return set_error("vdn_rope2d: rows_per_batch must be a multiple of P and <= batch_pitch");
   const unsigned grid = blocks_for(rows * heads * 8, 256);
-  if (get_operand_format()) rope2d_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch);
-  else rope2d_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch);
+  if (get_operand_format()) rope2d_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch, 0);
+  else rope2d_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch, 0);
+  count_launch();
+  return check_launch("rope2d_kernel");
+}
+
+extern "C" int vdn_rope_chunks(void* x, int64_t rows, int64_t ld, int32_t col0, int32_t chunks, const float* cos_sin, int32_t P, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !cos_sin) return set_error("vdn_rope_chunks: null pointer");
+  if (ld % 8 != 0 || col0 % 8 != 0 || chunks <= 0 || P <= 0 || rows <= 0) return set_error("vdn_rope_chunks: bad geometry");
+  if (col0 + (int64_t)chunks * 64 > ld) return set_error("vdn_rope_chunks: chunks exceed the row");
+  const unsigned grid = blocks_for(rows * chunks * 8, 256);
+  if (get_operand_format()) rope2d_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, chunks, cos_sin, P, rows, rows, 1);
+  else rope2d_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, chunks, cos_sin, P, rows, rows, 1);
   count_launch();
   return check_launch("rope2d_kernel");
 }

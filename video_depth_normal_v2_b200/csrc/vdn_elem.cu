@@ -234,6 +234,7 @@ groupnorm_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, in
 }
 
 // apply + transpose: one warp per (frame, pixel) row; out row = (b*D + d)*T + f
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_tc_kernel(const void* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w, const float* __restrict__ b,
                           void* __restrict__ out, int Bv, int T, int D, int C, int groups, int fmt) {
@@ -260,13 +261,23 @@ groupnorm_apply_tc_kernel(const void* __restrict__ x, const float* __restrict__ 
       t = unpack16(u.y, fmt); v[2] = t.x; v[3] = t.y;
       t = unpack16(u.z, fmt); v[4] = t.x; v[5] = t.y;
       t = unpack16(u.w, fmt); v[6] = t.x; v[7] = t.y;
+      if (VEC) {  // cg % 8 == 0: the 8 channels of a vector share one group
+        const float2 ms = __ldg(reinterpret_cast<const float2*>(stats) + frame * groups + c0 / cg);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(w + c0)), g1 = __ldg(reinterpret_cast<const float4*>(w + c0) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(b + c0) + 1);
+        const float gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float gb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        const int g = c / cg;
-        const float mean = __ldg(stats + 2 * (frame * groups + g));
-        const float rstd = __ldg(stats + 2 * (frame * groups + g) + 1);
-        v[i] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+        for (int i = 0; i < 8; ++i) v[i] = (v[i] - ms.x) * ms.y * gw[i] + gb[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 + i;
+          const int g = c / cg;
+          const float mean = __ldg(stats + 2 * (frame * groups + g));
+          const float rstd = __ldg(stats + 2 * (frame * groups + g) + 1);
+          v[i] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+        }
       }
       uint4 o;
       o.x = pack16(v[0], v[1], fmt);
@@ -306,6 +317,20 @@ __global__ void write_cls_kernel(float* __restrict__ x, const float* __restrict_
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int bb = idx / C, c = idx - bb * C;
     x[(long long)bb * tokens * C + c] = cls[c] + pos[c];
+  }
+}
+
+// use_clstoken readout input (dpt.py:129-132 / dpt_temporal.py:56-59): out[f*P + p] = [ xn[f*N + 1 + p] | xn[f*N] ], 16-byte vectors
+__global__ void __launch_bounds__(256)
+readout_concat_kernel(const uint4* __restrict__ xn, uint4* __restrict__ out, long long frames, int N, int cv) {
+  const int P = N - 1;
+  const long long total = frames * P * 2 * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = int(idx % (2 * cv));
+    const long long row = idx / (2 * cv);
+    const long long f = row / P;
+    const int p = int(row - f * P);
+    out[idx] = c < cv ? __ldg(xn + (f * N + 1 + p) * cv + c) : __ldg(xn + f * N * cv + (c - cv));
   }
 }
 
@@ -400,6 +425,102 @@ bilinear_nhwc_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4
       }
       orow[wo * cv + c8 + v * cq] = r;
       if (RELU2) orow_relu[wo * cv + c8 + v * cq] = rr;
+    }
+  }
+}
+
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2): one issue slot for two lanes of a lerp.
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 c;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+  return c;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+// Row-staged separable variant (channel chunks of CC = 8 * CV8 channels, CV8 a power of two): block = (wo tile x channel chunk,
+// output row, image).  Phase 1 lerps the two source rows VERTICALLY once per source pixel into fp32 shared memory (two float4
+// planes, conflict-free 16-byte accesses); phase 2 lerps HORIZONTALLY per output pixel.  Against the gather kernel above this
+// converts each source value once per output row instead of once per output pixel and uses packed FFMA2, ~3x fewer issue slots
+// per output byte (that kernel sat at 87 % issue-active, 2.8 TB/s).  Same coordinate arithmetic (ac_coords); the fp32 evaluation
+// order (vertical first) differs from ATen's by fp32 rounding only.
+template <int FMT, int RELU2, int CV8>
+__global__ void __launch_bounds__(256)
+bilinear_rows_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4* __restrict__ o_relu, int H, int W, int Ho, int Wo, int cv,
+                     int tw, int nchunks, int relu_out) {
+  extern __shared__ float4 bil_smem[];
+  const int chunk = blockIdx.x % nchunks;
+  const int tile = blockIdx.x / nchunks;
+  const int ho = blockIdx.y;
+  const long long bimg = blockIdx.z;
+  const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.0f;
+  const float sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.0f;
+  int h0, h1;
+  float lh;
+  ac_coords(ho, sh, H, h0, h1, lh);
+  const int wo_a = tile * tw;
+  const int wo_b = min(wo_a + tw, Wo);
+  int w_lo, w_hi, tmp;
+  float ftmp;
+  ac_coords(wo_a, sw, W, w_lo, tmp, ftmp);
+  ac_coords(wo_b - 1, sw, W, tmp, w_hi, ftmp);
+  const int nin = w_hi - w_lo + 1;
+  float4* plane0 = bil_smem;                 // channels 0-3 of every (pixel, vector)
+  float4* plane1 = bil_smem + nin * CV8;     // channels 4-7
+  const uint4* row0 = xin + ((bimg * H + h0) * (long long)W + w_lo) * cv + chunk * CV8;
+  const uint4* row1 = xin + ((bimg * H + h1) * (long long)W + w_lo) * cv + chunk * CV8;
+  const float2 wa = make_float2(1.0f - lh, 1.0f - lh), wb = make_float2(lh, lh);
+  for (int i = threadIdx.x; i < nin * CV8; i += 256) {
+    const int p = i / CV8, v = i - p * CV8;
+    const uint4 a = __ldg(row0 + p * cv + v);
+    const uint4 c = __ldg(row1 + p * cv + v);
+    float2 r0 = ffma2(T16f<FMT>::unpack(c.x), wb, fmul2(T16f<FMT>::unpack(a.x), wa));
+    float2 r1 = ffma2(T16f<FMT>::unpack(c.y), wb, fmul2(T16f<FMT>::unpack(a.y), wa));
+    float2 r2 = ffma2(T16f<FMT>::unpack(c.z), wb, fmul2(T16f<FMT>::unpack(a.z), wa));
+    float2 r3 = ffma2(T16f<FMT>::unpack(c.w), wb, fmul2(T16f<FMT>::unpack(a.w), wa));
+    plane0[i] = make_float4(r0.x, r0.y, r1.x, r1.y);
+    plane1[i] = make_float4(r2.x, r2.y, r3.x, r3.y);
+  }
+  __syncthreads();
+  uint4* orow = o + (bimg * Ho + ho) * (long long)Wo * cv + chunk * CV8;
+  uint4* orow_relu = RELU2 ? o_relu + (bimg * Ho + ho) * (long long)Wo * cv + chunk * CV8 : nullptr;
+  const int nout = (wo_b - wo_a) * CV8;
+  for (int i = threadIdx.x; i < nout; i += 256) {
+    const int wo = wo_a + i / CV8, v = i % CV8;
+    int w0, w1;
+    float lw;
+    ac_coords(wo, sw, W, w0, w1, lw);
+    const int i0 = (w0 - w_lo) * CV8 + v, i1 = (w1 - w_lo) * CV8 + v;
+    const float4 a0 = plane0[i0], b0 = plane0[i1], a1 = plane1[i0], b1 = plane1[i1];
+    const float2 ua = make_float2(1.0f - lw, 1.0f - lw), ub = make_float2(lw, lw);
+    float2 y0 = ffma2(make_float2(b0.x, b0.y), ub, fmul2(make_float2(a0.x, a0.y), ua));
+    float2 y1 = ffma2(make_float2(b0.z, b0.w), ub, fmul2(make_float2(a0.z, a0.w), ua));
+    float2 y2 = ffma2(make_float2(b1.x, b1.y), ub, fmul2(make_float2(a1.x, a1.y), ua));
+    float2 y3 = ffma2(make_float2(b1.z, b1.w), ub, fmul2(make_float2(a1.z, a1.w), ua));
+    if (relu_out) {
+      y0.x = fmaxf(y0.x, 0.0f); y0.y = fmaxf(y0.y, 0.0f); y1.x = fmaxf(y1.x, 0.0f); y1.y = fmaxf(y1.y, 0.0f);
+      y2.x = fmaxf(y2.x, 0.0f); y2.y = fmaxf(y2.y, 0.0f); y3.x = fmaxf(y3.x, 0.0f); y3.y = fmaxf(y3.y, 0.0f);
+    }
+    uint4 r;
+    r.x = T16f<FMT>::pack(y0.x, y0.y); r.y = T16f<FMT>::pack(y1.x, y1.y); r.z = T16f<FMT>::pack(y2.x, y2.y); r.w = T16f<FMT>::pack(y3.x, y3.y);
+    orow[(long long)wo * cv + v] = r;
+    if (RELU2) {
+      uint4 rr;
+      rr.x = T16f<FMT>::pack(fmaxf(y0.x, 0.0f), fmaxf(y0.y, 0.0f)); rr.y = T16f<FMT>::pack(fmaxf(y1.x, 0.0f), fmaxf(y1.y, 0.0f));
+      rr.z = T16f<FMT>::pack(fmaxf(y2.x, 0.0f), fmaxf(y2.y, 0.0f)); rr.w = T16f<FMT>::pack(fmaxf(y3.x, 0.0f), fmaxf(y3.y, 0.0f));
+      orow_relu[(long long)wo * cv + v] = rr;
     }
   }
 }
@@ -636,7 +757,9 @@ extern "C" int vdn_groupnorm_apply_tc(const void* x, const float* stats, const f
   VDN_STREAM;
   if (!x || !stats || !w || !b || !out) return set_error("vdn_groupnorm_apply_tc: null pointer");
   if (C % 8 != 0 || C % groups != 0) return set_error("vdn_groupnorm_apply_tc: C must be a multiple of 8 and of groups");
-  groupnorm_apply_tc_kernel<<<grid_for((long long)Bv * T * D, 8), 256, 0, stream>>>(x, stats, w, b, out, Bv, T, D, C, groups, get_operand_format());
+  const unsigned grid = grid_for((long long)Bv * T * D, 8);
+  if ((C / groups) % 8 == 0) groupnorm_apply_tc_kernel<true><<<grid, 256, 0, stream>>>(x, stats, w, b, out, Bv, T, D, C, groups, get_operand_format());
+  else groupnorm_apply_tc_kernel<false><<<grid, 256, 0, stream>>>(x, stats, w, b, out, Bv, T, D, C, groups, get_operand_format());
   count_launch();
   return check_launch("groupnorm_apply_tc_kernel");
 }
@@ -659,6 +782,16 @@ extern "C" int vdn_write_cls(float* x, const float* cls, const float* pos, int32
   return check_launch("write_cls_kernel");
 }
 
+extern "C" int vdn_readout_concat(const void* xn, void* out, int64_t frames, int32_t tokens, int32_t C, void* stream_v) {
+  VDN_STREAM;
+  if (!xn || !out) return set_error("vdn_readout_concat: null pointer");
+  if (C % 8 != 0 || tokens < 2 || frames <= 0) return set_error("vdn_readout_concat: C must be a multiple of 8, tokens >= 2");
+  readout_concat_kernel<<<grid_for(frames * (tokens - 1) * 2 * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(xn), reinterpret_cast<uint4*>(out),
+                                                                                              frames, tokens, C / 8);
+  count_launch();
+  return check_launch("readout_concat_kernel");
+}
+
 extern "C" int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream_v) {
   VDN_STREAM;
   if (!x || !out) return set_error("vdn_im2col_3x3_s2: null pointer");
@@ -673,13 +806,33 @@ static int launch_bilinear_nhwc(const void* x, void* out, void* out_relu, int B,
   if (B <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return set_error("vdn_bilinear_nhwc: bad shape");
   if (Ho > 65535 || B > 65535) return set_error("vdn_bilinear_nhwc: Ho and B must fit a grid dimension");
   const int cv = C / 8;
-  const int per_row = Wo * cv;
-  dim3 grid((per_row + 255) / 256, Ho, B);
-  if (grid.x > 8) grid.x = 8;
   const uint4* xi = reinterpret_cast<const uint4*>(x);
   uint4* o = reinterpret_cast<uint4*>(out);
   uint4* orl = reinterpret_cast<uint4*>(out_relu);
   const int fmt = get_operand_format();
+  static const char* env_v1 = getenv("VDN_BILINEAR_V1");
+  const int cv8 = (cv % 8 == 0) ? 8 : (cv % 4 == 0) ? 4 : 0;  // channel chunk of 64 or 32
+  if (cv8 != 0 && env_v1 == nullptr) {
+    // wo tile: at most NIN_MAX source pixels staged per block (fp32, 32 * cv8 bytes each)
+    constexpr int NIN_MAX = 160;
+    const double scale = Wo > 1 ? (double)(W - 1) / (double)(Wo - 1) : 0.0;
+    int tw = scale > 0.0 ? (int)((NIN_MAX - 3) / scale) : Wo;
+    if (tw < 1) tw = 1;
+    if (tw > Wo) tw = Wo;
+    const int ntiles = (Wo + tw - 1) / tw;
+    tw = (Wo + ntiles - 1) / ntiles;
+    const int nchunks = cv / cv8;
+    const size_t smem = (size_t)NIN_MAX * cv8 * 32;
+    dim3 g((unsigned)(ntiles * nchunks), Ho, B);
+#define VDN_BILR(F, R, V) bilinear_rows_kernel<F, R, V><<<g, 256, smem, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, tw, nchunks, relu_out)
+#define VDN_BILR_FR(F, R) do { if (cv8 == 8) VDN_BILR(F, R, 8); else VDN_BILR(F, R, 4); } while (0)
+    if (orl != nullptr) { if (fmt) VDN_BILR_FR(1, 1); else VDN_BILR_FR(0, 1); }
+    else { if (fmt) VDN_BILR_FR(1, 0); else VDN_BILR_FR(0, 0); }
+#undef VDN_BILR_FR
+#undef VDN_BILR
+    count_launch();
+    return check_launch("bilinear_rows_kernel");
+  }
   const int vpt = (cv % 4 == 0) ? 4 : 1;
   dim3 g2((Wo * (cv / vpt) + 255) / 256, Ho, B);
   if (g2.x > 8) g2.x = 8;

@@ -81,8 +81,10 @@ class GraphRunner:
 # ======================================================================================================
 # encoder: DINOv2 get_intermediate_layers (dinov2.py:212-231, 271-321; block.py:82-107)
 # ======================================================================================================
-def encoder_forward(enc: dict, x: torch.Tensor) -> List[torch.Tensor]:
-    """x (Bf, 3, H, W) fp32 -> 4 x [Bf*ph*pw, C] 16-bit (final-norm'ed patch tokens of the tapped blocks, cls dropped)."""
+def encoder_forward(enc: dict, x: torch.Tensor, readout: Optional[list] = None) -> List[torch.Tensor]:
+    """x (Bf, 3, H, W) fp32 -> 4 x [Bf*ph*pw, C] 16-bit (final-norm'ed patch tokens of the tapped blocks, cls dropped).
+    ``readout`` (use_clstoken=True, dpt.py:129-132): the four packed readout_projects; the per-frame [token | cls] -> Linear -> GELU
+    readout has no cross-frame term, so it runs here and the features keep their shape for every consumer (head, window reuse, streaming)."""
     Bf, _, H, W = x.shape
     if H % 14 != 0 or W % 14 != 0:
         raise RuntimeError(f"Input image height {H} / width {W} is not a multiple of patch size 14")  # patch_embed.py:73-74
@@ -115,7 +117,14 @@ def encoder_forward(enc: dict, x: torch.Tensor) -> List[torch.Tensor]:
         ops.gemm(hid, blk["fc2"]["w"], xs, M=rows, N=C, K=4 * C, bias=blk["fc2"]["b"], gamma=blk["ls2"], res=xs)
         if i in enc["taps"]:
             f = _empty((Bf * P, C), od, dev)
-            ops.layernorm(xs, enc["norm_w"], enc["norm_b"], f, 1e-6, drop_first=True, rows_per_batch=N)
+            if readout is None:
+                ops.layernorm(xs, enc["norm_w"], enc["norm_b"], f, 1e-6, drop_first=True, rows_per_batch=N)
+            else:
+                ops.layernorm(xs, enc["norm_w"], enc["norm_b"], xn, 1e-6)  # xn is free until the next block's ln1
+                cat = _empty((Bf * P, 2 * C), od, dev)
+                ops.readout_concat(xn, cat, Bf, N, C)
+                ro = readout[len(feats)]
+                ops.gemm(cat, ro["w"], f, M=Bf * P, N=C, K=2 * C, bias=ro["b"], act=ops.ACT_GELU)
             feats.append(f)
     return feats
 
@@ -147,12 +156,17 @@ def motion_module_forward(mm: dict, x: torch.Tensor, Bv: int, T: int, D: int, re
     else:
         qkv = _empty((rows, 3 * C), od, dev)
     for a in mm["attn"]:
-        ops.layernorm(h, a["ln_w"], a["ln_b"], n16, 1e-5, pe=a["pe"][:T])
+        rope = a["pe"] is None  # pe='rope': rotate the projected q | k columns by the frame index instead of adding a table to the input
+        ops.layernorm(h, a["ln_w"], a["ln_b"], n16, 1e-5, pe=None if rope else a["pe"][:T])
         if tc:
             ops.gemm(n16, a["qkv_w"], qk, M=rows, N=3 * C, K=C, ldc=2 * C, out2=vT, row_map=ops.ROWMAP_QKV_SPLIT, rm=(128, 128, C, 0))
+            if rope:
+                ops.rope_chunks(qk, rows, 2 * C, 0, 2 * C // 64, a["rope"], T)
             ops.temporal_attn_tc(qk, vT, ao, rows, C, 8)
         else:
             ops.gemm(n16, a["qkv_w"], qkv, M=rows, N=3 * C, K=C)
+            if rope:
+                ops.rope_chunks(qkv, rows, 3 * C, 0, 2 * C // 64, a["rope"], T)
             ops.temporal_attn(qkv, ao, Bv * D, T, C, 8)
         ops.gemm(ao, a["out"]["w"], h, M=rows, N=C, K=C, bias=a["out"]["b"], res=h)
     ops.layernorm(h, mm["ffn_w"], mm["ffn_b"], n16, 1e-5)
@@ -395,8 +409,11 @@ def _encoder_shapes(prefix: str, cfg: dict) -> Dict[str, tuple]:
     return s
 
 
-def _head_shapes(prefix: str, C: int, Fe: int, oc: List[int], temporal: bool) -> Dict[str, tuple]:
+def _head_shapes(prefix: str, C: int, Fe: int, oc: List[int], temporal: bool, pe: str = "ape", use_clstoken: bool = False) -> Dict[str, tuple]:
     s = OrderedDict()
+    if use_clstoken:
+        for i in range(4):
+            s[f"{prefix}readout_projects.{i}.0.weight"], s[f"{prefix}readout_projects.{i}.0.bias"] = (C, 2 * C), (C,)
     for i in range(4):
         s[f"{prefix}projects.{i}.weight"], s[f"{prefix}projects.{i}.bias"] = (oc[i], C, 1, 1), (oc[i],)
     s[prefix + "resize_layers.0.weight"], s[prefix + "resize_layers.0.bias"] = (oc[0], oc[0], 4, 4), (oc[0],)
@@ -424,7 +441,8 @@ def _head_shapes(prefix: str, C: int, Fe: int, oc: List[int], temporal: bool) ->
                 ab = f"{tb}attention_blocks.{a}."
                 s[ab + "to_q.weight"] = s[ab + "to_k.weight"] = s[ab + "to_v.weight"] = (Cm, Cm)
                 s[ab + "to_out.0.weight"], s[ab + "to_out.0.bias"] = (Cm, Cm), (Cm,)
-                s[ab + "pos_encoder.pe"] = (1, 32, Cm)
+                if pe == "ape":
+                    s[ab + "pos_encoder.pe"] = (1, 32, Cm)
                 s[f"{tb}norms.{a}.weight"] = s[f"{tb}norms.{a}.bias"] = (Cm,)
             s[tb + "ff.net.0.proj.weight"], s[tb + "ff.net.0.proj.bias"] = (8 * Cm, Cm), (8 * Cm,)
             s[tb + "ff.net.2.weight"], s[tb + "ff.net.2.bias"] = (Cm, 4 * Cm), (Cm,)
@@ -434,29 +452,32 @@ def _head_shapes(prefix: str, C: int, Fe: int, oc: List[int], temporal: bool) ->
 
 
 class VideoDepthAnything(_PackedModule):
-    """Drop-in for video_depth_anything/video_depth.py:35 ``VideoDepthAnything`` (vits / vitl, use_bn=False, use_clstoken=False, pe='ape')."""
+    """Drop-in for video_depth_anything/video_depth.py:35 ``VideoDepthAnything`` (vits / vitl, use_bn=False; use_clstoken and
+    pe in {'ape', 'rope'} as in the reference constructor)."""
 
     def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False, use_clstoken=False, num_frames=32, pe="ape"):
         super().__init__()
         if encoder not in ENCODER_CONFIGS:
             raise KeyError(encoder)  # the reference indexes intermediate_layer_idx[encoder] (video_depth.py:48-51)
-        if use_bn or use_clstoken:
-            raise NotImplementedError("use_bn / use_clstoken are never exercised by the reference (SURVEY.md §8b)")
-        if pe != "ape":
-            raise NotImplementedError("pe='rope' is on the roadmap (SURVEY.md §8f rank 3)")
+        if use_bn:
+            raise NotImplementedError("use_bn is never exercised by the reference (SURVEY.md §8b)")
+        if pe not in ("ape", "rope"):
+            raise NotImplementedError(pe)  # motion_module.py:242-243
         assert num_frames > 0
         self.encoder = encoder
+        self.use_clstoken, self.pe = bool(use_clstoken), pe
         self.num_frames = num_frames
         self.cfg = dict(ENCODER_CONFIGS[encoder], features=features, out_channels=list(out_channels))
         self.intermediate_layer_idx = {k: v["taps"] for k, v in ENCODER_CONFIGS.items()}
 
     def _expected_shapes(self):
         s = _encoder_shapes("pretrained.", self.cfg)
-        s.update(_head_shapes("head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], True))
+        s.update(_head_shapes("head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], True, self.pe, self.use_clstoken))
         return s
 
     def _pack(self, sd, dev, dt):
-        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "head.", self.cfg, dev, dt, True)}
+        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt),
+                "head": packing.pack_head(sd, "head.", self.cfg, dev, dt, True, self.pe, self.use_clstoken)}
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -470,7 +491,7 @@ class VideoDepthAnything(_PackedModule):
         ph, pw = H // 14, W // 14
 
         def run(xd):
-            feats = encoder_forward(w["enc"], xd.reshape(B * T, 3, H, W))
+            feats = encoder_forward(w["enc"], xd.reshape(B * T, 3, H, W), w["head"].get("readout"))
             # F.interpolate(depth, (H, W), align_corners=True) is the identity here (H == 14*ph) and the head's output is already >= 0
             return head_forward(w["head"], feats, B * T, ph, pw, T)
 
@@ -488,7 +509,7 @@ class VideoDepthAnything(_PackedModule):
         """x (F, 3, H, W) fp32 -> 4 x [F*ph*pw, C] tapped, final-norm'ed patch tokens (frame-major)."""
         w = self._weights()
         x = x.to(device=self._dev, dtype=torch.float32).contiguous()
-        feats = self._graphs.run(("encode",) + tuple(x.shape), lambda xd: encoder_forward(w["enc"], xd), [x])
+        feats = self._graphs.run(("encode",) + tuple(x.shape), lambda xd: encoder_forward(w["enc"], xd, w["head"].get("readout")), [x])
         return [f.clone() for f in feats]  # the long-video driver keeps per-frame views of these across windows
 
     @torch.no_grad()
@@ -515,7 +536,7 @@ class VideoDepthAnything(_PackedModule):
         st["id"] += 1
         _, h, wd = x.shape
         ph, pw = h // 14, wd // 14
-        feats = encoder_forward(w["enc"], x.to(device=self._dev, dtype=torch.float32).unsqueeze(0).contiguous())
+        feats = encoder_forward(w["enc"], x.to(device=self._dev, dtype=torch.float32).unsqueeze(0).contiguous(), w["head"].get("readout"))
         new: list = []
         if st["id"] == 0:
             depth = head_forward(w["head"], feats, 1, ph, pw, 1, stream={"cached": None, "new": new})
@@ -573,10 +594,11 @@ class VideoDepthRefinerV5(_PackedModule):
         super().__init__()
         if encoder not in ENCODER_CONFIGS:
             raise KeyError(encoder)
-        if use_bn or use_clstoken:
-            raise NotImplementedError("use_bn / use_clstoken are never exercised by the reference (SURVEY.md §8b)")
-        if pe != "ape":
-            raise NotImplementedError("pe='rope' is on the roadmap (SURVEY.md §8f rank 3)")
+        if use_bn:
+            raise NotImplementedError("use_bn is never exercised by the reference (SURVEY.md §8b)")
+        if pe not in ("ape", "rope"):
+            raise NotImplementedError(pe)
+        self.use_clstoken, self.pe = bool(use_clstoken), pe
         if not use_residual or not input_normal:
             raise NotImplementedError("only use_residual=True, input_normal=True (the reference defaults) are built")
         self.encoder, self.num_frames, self.max_depth = encoder, num_frames, float(max_depth)
@@ -587,12 +609,12 @@ class VideoDepthRefinerV5(_PackedModule):
     def _expected_shapes(self):
         s = _encoder_shapes("pretrained.", self.cfg)
         s["scale_head.feat.1.weight"], s["scale_head.feat.1.bias"] = (1, 1, 1, 1), (1,)
-        s.update(_head_shapes("temporal_head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], True))
+        s.update(_head_shapes("temporal_head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], True, self.pe, self.use_clstoken))
         s["shift_head.0.weight"], s["shift_head.0.bias"] = (1, 1, 1, 1), (1,)
         return s
 
     def _pack(self, sd, dev, dt):
-        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "temporal_head.", self.cfg, dev, dt, True),
+        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "temporal_head.", self.cfg, dev, dt, True, self.pe, self.use_clstoken),
                 "scale_w": float(sd["scale_head.feat.1.weight"].reshape(())), "scale_b": float(sd["scale_head.feat.1.bias"].reshape(())),
                 "shift_w": float(sd["shift_head.0.weight"].reshape(())), "shift_b": float(sd["shift_head.0.bias"].reshape(()))}
 
@@ -604,17 +626,28 @@ class VideoDepthRefinerV5(_PackedModule):
         B, S, H, W = input_depth.shape
         if S > 32:
             raise RuntimeError("temporal attention supports at most 32 frames per window")
-        dev, n, hw = self._dev, B * S, self.NET_SIZE
+        dev, n = self._dev, B * S
+        nh, nw = (self.NET_SIZE, self.NET_SIZE) if self.NET_SIZE else (H, W)  # v4 runs the network at the native resolution
         din = input_depth.to(device=dev, dtype=torch.float32).contiguous()
         inv_max = 1.0 / self.max_depth
         scale = _empty((n,), torch.float32, dev)
         ops.frame_median_scale(din, scale, H * W, inv_max, w["scale_w"], w["scale_b"])          # :164-167
-        r = _empty((n, hw, hw), torch.float32, dev)
-        ops.bilinear_f32(din.view(n, H, W), r, n, H, W, hw, hw)                                  # :169 (scale commutes with the resize)
-        x = _empty((n, 3, hw, hw), torch.float32, dev)
-        ops.v5_net_input(r, scale, x, n, hw, hw, inv_max)                                        # :173-178
-        feats = encoder_forward(w["enc"], x)
-        o = head_forward(w["head"], feats, n, hw // 14, hw // 14, S)  # temporal modules mix the S frames of each of the B sequences
+        if (nh, nw) == (H, W):
+            r = din.view(n, H, W)
+        else:
+            r = _empty((n, nh, nw), torch.float32, dev)
+            ops.bilinear_f32(din.view(n, H, W), r, n, H, W, nh, nw)                              # :169 (scale commutes with the resize)
+        x = _empty((n, 3, nh, nw), torch.float32, dev)
+        ops.v5_net_input(r, scale, x, n, nh, nw, inv_max)                                        # :173-178
+        feats = encoder_forward(w["enc"], x, w["head"].get("readout"))
+        o = head_forward(w["head"], feats, n, nh // 14, nw // 14, S)  # temporal modules mix the S frames of each of the B sequences
         out = _empty((B, S, H, W), torch.float32, dev)
-        ops.v5_residual(din, o, scale, out, n, H, W, hw, hw, w["shift_w"], w["shift_b"], self.max_depth)  # :183-192
+        ops.v5_residual(din, o, scale, out, n, H, W, nh, nw, w["shift_w"], w["shift_b"], self.max_depth)  # :183-192
         return out
+
+
+class VideoDepthRefinerV4(VideoDepthRefinerV5):
+    """Drop-in for models/video_depth_model_v4.py:88 ``VideoDepthAnything``: the v5 module tree (same state_dict keys) with the
+    network evaluated at the input's own resolution (forward :120-148; H and W multiples of 14) instead of 224x224."""
+
+    NET_SIZE = None

@@ -327,6 +327,22 @@ def rope2d(x, rows: int, ld: int, col0: int, heads: int, cos_sin, P: int, rows_p
     return x
 
 
+def rope_chunks(x, rows: int, ld: int, col0: int, chunks: int, cos_sin, P: int):
+    """Temporal RoPE in place on `chunks` 64-wide column chunks of 16-bit rows; row r is frame r % P; cos_sin [P, chunks, 64] fp32."""
+    od = operand_dtype()
+    _check(_run("rope", "hbm", 4.0 * rows * chunks * 64, lib().vdn_rope_chunks, _ptr(x, od, "x"), rows, ld, col0, chunks,
+                _ptr(cos_sin, torch.float32, "cos_sin"), P, _stream()), "vdn_rope_chunks")
+    return x
+
+
+def readout_concat(xn, out, frames: int, tokens: int, C_: int):
+    """[frames*tokens, C] normed tokens (row 0 = cls) -> [frames*(tokens-1), 2C] = [patch token | cls of its frame]."""
+    od = operand_dtype()
+    _check(_run("readout_concat", "hbm", 2.0 * frames * (tokens - 1) * 3 * C_, lib().vdn_readout_concat, _ptr(xn, od, "xn"), _ptr(out, od, "out"),
+                frames, tokens, C_, _stream()), "vdn_readout_concat")
+    return out
+
+
 def add_rowvec(x, vec, alpha: float, out):
     rows, C_ = out.shape[0], out.shape[1]
     _check(_run("add_rowvec", "hbm", (4.0 if x.dtype == torch.float32 else 2.0) * rows * C_ + 4.0 * rows * C_, lib().vdn_add_rowvec, _ptr(x, None, "x"),

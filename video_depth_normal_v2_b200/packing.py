@@ -102,7 +102,20 @@ def encoder_pos_embed(enc: dict, ph: int, pw: int, dev) -> torch.Tensor:
     return enc["pos_cache"][key]
 
 
-def pack_motion_module(sd, prefix: str, C: int, dev, dt) -> dict:
+def temporal_rope_table(C: int, max_len: int = 32, theta: float = 10000.0) -> torch.Tensor:
+    """cos|sin table of the temporal RoPE (precompute_freqs_cis(query_dim, temporal_max_len), motion_module/attention.py:403-408) laid
+    out for vdn_rope_chunks over the q|k columns: [max_len, 2C/64, 64] = per (frame, 64-channel chunk) cos[32] | sin[32]; the k half
+    repeats the q half (one frequency per channel pair of query_dim).  Weights-free, fp64 once."""
+    if C % 64 != 0:
+        raise RuntimeError("pe='rope' needs motion-module widths that are multiples of 64")
+    freqs = 1.0 / (theta ** (torch.arange(0, C, 2, dtype=torch.float32)[: C // 2] / C))  # fp32 like the reference
+    ang = torch.outer(torch.arange(max_len, dtype=torch.float32), freqs)                # [max_len, C/2]
+    cos, sin = ang.cos().reshape(max_len, C // 64, 32), ang.sin().reshape(max_len, C // 64, 32)
+    tab = torch.cat((cos, sin), dim=-1)                                                  # [max_len, C/64, 64]
+    return torch.cat((tab, tab), dim=1).contiguous()                                     # q chunks then k chunks
+
+
+def pack_motion_module(sd, prefix: str, C: int, dev, dt, pe_type: str = "ape") -> dict:
     p = prefix + "temporal_transformer."
     tb = p + "transformer_blocks.0."
     mm = {"C": C, "gn_w": _f32(sd[p + "norm.weight"], dev), "gn_b": _f32(sd[p + "norm.bias"], dev),
@@ -110,14 +123,20 @@ def pack_motion_module(sd, prefix: str, C: int, dev, dt) -> dict:
     for a in range(2):
         ab = f"{tb}attention_blocks.{a}."
         qkv = torch.cat([sd[ab + "to_q.weight"], sd[ab + "to_k.weight"], sd[ab + "to_v.weight"]], dim=0)
-        pe = sd[ab + "pos_encoder.pe"][0].detach().double()
-        mm["attn"].append({
-            "ln_w": _f32(sd[f"{tb}norms.{a}.weight"], dev), "ln_b": _f32(sd[f"{tb}norms.{a}.bias"], dev),
-            "qkv_w": _w16(qkv, dev, dt), "out": pack_linear(sd, ab + "to_out.0", dev, dt),
-            "pe": _f32(sd[ab + "pos_encoder.pe"][0], dev),  # (32, C)
+        blk = {"ln_w": _f32(sd[f"{tb}norms.{a}.weight"], dev), "ln_b": _f32(sd[f"{tb}norms.{a}.bias"], dev),
+               "qkv_w": _w16(qkv, dev, dt), "out": pack_linear(sd, ab + "to_out.0", dev, dt)}
+        if pe_type == "ape":
+            pe = sd[ab + "pos_encoder.pe"][0].detach().double()
+            blk["pe"] = _f32(sd[ab + "pos_encoder.pe"][0], dev)  # (32, C)
             # streaming path: positional part of the bias-free projections, W (n + pe_j) = W n + W pe_j (weights only, fp64 once)
-            "pos_qkv": _f32((pe @ qkv.detach().double().t()).float(), dev),  # (32, 3C)
-        })
+            blk["pos_qkv"] = _f32((pe @ qkv.detach().double().t()).float(), dev)  # (32, 3C)
+        else:
+            blk["pe"] = None
+            blk["rope"] = mm.setdefault("rope_table", temporal_rope_table(C).to(dev))  # (32, 2C/64, 64)
+            # streaming + rope: the reference rotates by freqs_cis[:1] (angle 0) broadcast over all keys (motion_module.py:279-282
+            # with a one-frame query), i.e. no positional term at all
+            blk["pos_qkv"] = torch.zeros((32, 3 * C), dtype=torch.float32, device=dev)
+        mm["attn"].append(blk)
     w1, b1 = sd[tb + "ff.net.0.proj.weight"].detach().float(), sd[tb + "ff.net.0.proj.bias"].detach().float()
     h = w1.shape[0] // 2  # rows [0,h) = value, [h,2h) = gate (GEGLU.chunk(2), motion_module/attention.py:382-384)
     mm["ff1_w"] = _w16(torch.stack([w1[:h], w1[h:]], dim=1).reshape(2 * h, -1), dev, dt)
@@ -127,7 +146,7 @@ def pack_motion_module(sd, prefix: str, C: int, dev, dt) -> dict:
     return mm
 
 
-def pack_head(sd, prefix: str, cfg: dict, dev, dt, temporal: bool) -> dict:
+def pack_head(sd, prefix: str, cfg: dict, dev, dt, temporal: bool, pe_type: str = "ape", use_clstoken: bool = False) -> dict:
     oc, Fe = cfg["out_channels"], cfg["features"]
     s = prefix + "scratch."
     head = {"features": Fe, "oc": list(oc)}
@@ -149,5 +168,7 @@ def pack_head(sd, prefix: str, cfg: dict, dev, dt, temporal: bool) -> dict:
     head["oc2_head_w"] = _f32(sd[s + "output_conv2.2.weight"].reshape(32), dev)
     head["oc2_head_b"] = float(sd[s + "output_conv2.2.bias"].reshape(()).item())
     if temporal:
-        head["mm"] = [pack_motion_module(sd, f"{prefix}motion_modules.{m}.", C, dev, dt) for m, C in enumerate([oc[2], oc[3], Fe, Fe])]
+        head["mm"] = [pack_motion_module(sd, f"{prefix}motion_modules.{m}.", C, dev, dt, pe_type) for m, C in enumerate([oc[2], oc[3], Fe, Fe])]
+    if use_clstoken:  # dpt.py:92-98: Linear(2C -> C) + GELU on [token | cls]
+        head["readout"] = [pack_linear(sd, f"{prefix}readout_projects.{i}.0", dev, dt) for i in range(4)]
     return head
