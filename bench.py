@@ -26,6 +26,7 @@ FRAMES, SIZE, ENCODER = 32, 518, "vitl"
 FEATURES, OUT_CHANNELS = 256, [256, 512, 1024, 1024]
 # reference-equivalent FLOPs per slot-frame (torch flop counter on the reference modules)
 GFLOP_PER_FRAME = 1404.7
+ENCODER_GFLOP_PER_FRAME = 1013.6  # 24 x 42.17 + 1.65
 METRIC = "frames/sec ViT-L 518x518 video"
 
 
@@ -225,6 +226,22 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * FRAMES * args.steps / (ms_total / 1e3)
 
+    # ---------------- encoder alone (north_star: >= 60 % of dense tensor peak on the encoder) ----------------
+    xe = x_dev[0]
+    for _ in range(2):
+        model.encode_frames(xe, clone=False)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        model.encode_frames(xe, clone=False)
+    e1.record()
+    barrier()
+    enc_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    encoder = {"ms_per_window": enc_ms, "gflop_per_frame": ENCODER_GFLOP_PER_FRAME,
+               "tflops": ENCODER_GFLOP_PER_FRAME * 1e9 * FRAMES / (enc_ms / 1e3) / 1e12,
+               "note": "DINOv2 ViT-L, 32 frames 518x518 -> four tapped feature maps (patch embed, 24 blocks, final norms; SURVEY.md §8d: 1013.6 GFLOP/frame), "
+                       "device-resident, per GPU"}
+
     # ---------------- end to end through the public API with host buffers ----------------
     for _ in range(2):
         y_host.copy_(model(x_host))
@@ -342,11 +359,13 @@ def main():
     agg = prof.summary()
     total_prof_ms = sum(a["ms"] for a in agg.values())
     peaks = _peaks()
+    encoder["tensor_frac"] = encoder["tflops"] / peaks["tflops"]
     kernels = {}
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         rate = a["work"] / (a["ms"] / 1e3) if a["ms"] > 0 else 0.0
         kernels[name] = {"launches_per_step": a["launches"] // n_prof, "ms_per_step": a["ms"] / n_prof, "share": a["ms"] / total_prof_ms,
-                         ("tflops" if a["kind"] == "tensor" else "gbs"): rate / (1e12 if a["kind"] == "tensor" else 1e9)}
+                         ("tflops" if a["kind"] == "tensor" else "gbs"): rate / (1e12 if a["kind"] == "tensor" else 1e9),
+                         "frac_of_peak": rate / (peaks["tflops"] * 1e12 if a["kind"] == "tensor" else peaks["hbm_gbs"] * 1e9)}
     top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     tname, ta = top
     if ta["kind"] == "tensor":
@@ -376,12 +395,13 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.operands == "fp16" else "bf16", "data": "synthetic",
-        "config": {"workload": f"VideoDepthAnything {ENCODER} 32-frame clip {SIZE}x{SIZE}, one window forward per step per GPU (BASELINE configs[3]-shaped "
-                               f"video path at the metric's 518x518; DepthAnythingV2 batch-16 image path not built yet)",
+        "config": {"workload": f"VideoDepthAnything {ENCODER} 32-frame clip {SIZE}x{SIZE} with temporal motion-module attention, one window forward per step "
+                               f"per GPU (the video path BASELINE.json's metric names, at its 518x518; configs[1] DepthAnythingV2 batch 16 is the "
+                               f"da2_batch16 block, configs[4] the long_video block)",
                    "frames_per_step_per_gpu": FRAMES, "tokens_per_frame": 1370, "parallelism": f"window-sharded x{world}, no data-path collective",
                    "l2": "activations per step (>2 GB) exceed the 126 MB L2, no explicit flush", "operands": args.operands + " (fp32 accumulate, fp32 residual stream)"},
         "tensor_frac_of_step": (GFLOP_PER_FRAME * 1e9 * FRAMES / (ms_per_step / 1e3)) / 1e12 / peaks["tflops"],
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "long_video": long_video, "da2_batch16": da2, "stream": stream, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "encoder": encoder, "long_video": long_video, "da2_batch16": da2, "stream": stream, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -33,6 +33,8 @@ ENCODERS = {
     # name: embed_dim, depth, heads, taps, features, out_channels   (run_video.py:28-33, video_depth.py:48-51)
     "vits": dict(embed_dim=384, depth=12, heads=6, taps=[2, 5, 8, 11], features=64, out_channels=[48, 96, 192, 384]),
     "vitl": dict(embed_dim=1024, depth=24, heads=16, taps=[4, 11, 17, 23], features=256, out_channels=[256, 512, 1024, 1024]),
+    # DepthAnythingV2 only (depth_anything_v2.py:24-29, dinov2.py:353-364); VideoDepthAnything knows vits / vitl (video_depth.py:48-51)
+    "vitb": dict(embed_dim=768, depth=12, heads=12, taps=[2, 5, 8, 11], features=128, out_channels=[96, 192, 384, 768]),
 }
 POS_GRID = 37  # DINOv2(img_size=518, patch 14) -> 37x37 learned pos-embed (dinov2.py:407-409)
 NUM_FRAMES = 32

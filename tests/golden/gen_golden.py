@@ -39,7 +39,8 @@ STREAM_SWITCH_CASES = [("stream_vits_n5_56x70_rope_cls", "vits", 5, 56, 70, 12, 
 V5_CASES = [("v5_vits_s4_60x80", "vits", 4, 60, 80, 3)]
 V4_CASES = [("v4_vits_s4_56x84", "vits", 4, 56, 84, 14)]  # models/video_depth_model_v4.py: network at the native resolution
 # (name, encoder, batch, H(=W), calls, seed, stride): DepthAnythingV2 is stateful -> a sequence of forward() calls on one model
-DA2_CASES = [("da2_vits_b2_70_calls8", "vits", 2, 70, 8, 5, 1), ("da2_vits_b1_518_calls2", "vits", 1, 518, 2, 6, 4), ("da2_vitl_b1_70_calls3", "vitl", 1, 70, 3, 7, 1)]
+DA2_CASES = [("da2_vits_b2_70_calls8", "vits", 2, 70, 8, 5, 1), ("da2_vits_b1_518_calls2", "vits", 1, 518, 2, 6, 4), ("da2_vitl_b1_70_calls3", "vitl", 1, 70, 3, 7, 1),
+             ("da2_vitb_b2_70_calls3", "vitb", 2, 70, 3, 17, 1)]
 # (name, encoder, frames, H, W, seed): streaming inference, one infer_video_depth_one call per frame (window slides after frame 10)
 STREAM_CASES = [("stream_vits_n16_56x70", "vits", 16, 56, 70, 8)]
 VIDEO_CASES = [("video_vits_n50_56x70", "vits", 50, 56, 70, 4)]
@@ -62,8 +63,10 @@ def da2_inputs(B, H, calls, seed):
     return [make_input("rgb", (B, 1, 3, H, H), seed * 100 + i)[:, 0] for i in range(calls)]
 
 
-def gen_da2():
+def gen_da2(only=None):
     for name, enc, B, H, calls, seed, stride in DA2_CASES:
+        if only is not None and only not in name:
+            continue
         sd = make_state_dict("da2", enc, seed)
         m = RL.load_da2(enc, sd)
         outs = [m(x)[:, ::stride, ::stride].numpy() for x in da2_inputs(B, H, calls, seed)]
@@ -123,7 +126,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "v4":
         return gen_v4()
     if len(sys.argv) > 1 and sys.argv[1] == "da2":
-        return gen_da2()
+        return gen_da2(sys.argv[2] if len(sys.argv) > 2 else None)
     if len(sys.argv) > 1 and sys.argv[1] == "stream":
         return gen_stream()
     gen_da2()

@@ -121,6 +121,8 @@ def test_determinism_and_batch_independence(vdn):
 
 
 def test_api_errors(vdn):
+    with pytest.raises(KeyError):  # video_depth.py:48-51 knows vits / vitl only (vitb exists for DepthAnythingV2)
+        vdn.VideoDepthAnything(encoder="vitb")
     m, sd = _model(vdn, "vits", 0)
     with pytest.raises(RuntimeError, match="multiple of patch size"):
         m(torch.zeros(1, 2, 3, 60, 70).cuda())
@@ -176,7 +178,8 @@ def _da2_inputs(B, H, calls, seed):
     return [make_input("rgb", (B, 1, 3, H, H), seed * 100 + i)[:, 0] for i in range(calls)]
 
 
-@pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl")])
+@pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl"),
+                                      ("da2_vitb_b2_70_calls3", "vitb")])
 def test_da2_stateful_forward_matches_reference_golden(vdn, name, enc):
     """A sequence of forward() calls on one model against the live reference's outputs: empty bank (constant cross-attention
     term), filling bank (cross-attention over 1..6 cached entries) and the ring wrap after 6 entries."""
@@ -303,3 +306,35 @@ def test_v4_refiner_matches_reference_golden(vdn):
     assert e["max_abs"] <= 1e-3
     with pytest.raises(RuntimeError):  # patch_embed.py:73-74 through the native-resolution path
         m(make_input("depth", (1, 2, 60, 84), seed).cuda())
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs[3]: ViT-L 518x924
+def test_vitl_518x924_window_matches_oracle_on_gpu(vdn):
+    """The non-square BASELINE size (37 x 66 patch grid, 2443 tokens, interpolated pos-embed), ViT-L, strict-fp32 oracle on the GPU."""
+    enc, T, H, W = "vitl", 4, 518, 924
+    m, sd = _model(vdn, enc, 15)
+    x = make_input("rgb", (1, T, 3, H, W), 15).cuda()
+    y = m(x)
+    ref = O.vda_forward({k: v.cuda() for k, v in sd.items()}, x, enc)
+    torch.cuda.synchronize()
+    _check("vitl 4x518x924", y, ref)
+
+
+def test_v5_vitl_32x518x924_matches_oracle_on_gpu(vdn):
+    """BASELINE configs[3] as written: video_depth_model_v5, ViT-L, one 32-frame 518x924 depth clip (median scale head, 224x224
+    Sobel-normal network input, temporal DPT head, residual output) and the surface normals of the refined depth."""
+    cfg = ENCODERS["vitl"]
+    sd = make_state_dict("v5", "vitl", 16)
+    m = vdn.VideoDepthRefinerV5(encoder="vitl", features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
+    m.load_state_dict(sd)
+    d = make_input("depth", (1, 32, 518, 924), 16).cuda()
+    y = m(d)
+    ref = O.v5_forward({k: v.cuda() for k, v in sd.items()}, d, "vitl")
+    torch.cuda.synchronize()
+    e = _check("v5 vitl 32x518x924", y / 65535.0, ref / 65535.0, floor_frac=0.05)
+    assert e["max_abs"] <= 1e-3
+    n = torch.empty((32, 3, 518, 924), device="cuda")
+    vdn.ops.sobel_normals((y[0] / 65535.0).contiguous(), n, 32, 518, 924)
+    ang = O.normal_angle_deg(n.cpu(), O.sobel_normals((ref[0] / 65535.0)[:, None]).cpu())
+    print(f"v5 vitl 32x518x924 sobel normals of the refined depth: max angle {ang:.4f} deg")
+    assert ang <= MAX_ANGLE

@@ -89,7 +89,8 @@ def _da2_inputs(B, H, calls, seed):
     return [make_input("rgb", (B, 1, 3, H, H), seed * 100 + i)[:, 0] for i in range(calls)]
 
 
-@pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl")])
+@pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl"),
+                                      ("da2_vitb_b2_70_calls3", "vitb")])
 def test_da2_stateful_forward_matches_reference(name, enc):
     """A sequence of forward() calls on one model (memory bank filling up, then wrapping at 6 entries)."""
     g = _load(name)

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import ops, packing
-from .models import ENCODER_CONFIGS, _PackedModule, _empty, _encoder_shapes, _head_shapes, encoder_forward, head_forward
+from .models import DA2_ENCODER_CONFIGS as ENCODER_CONFIGS, _PackedModule, _empty, _encoder_shapes, _head_shapes, encoder_forward, head_forward
 
 NUM_MEM_ATTENTION_LAYERS = 4  # depth_anything_v2.py:31
 
@@ -133,7 +133,7 @@ class _MemoryState:
 
 
 class DepthAnythingV2(_PackedModule):
-    """Drop-in for depth_anything_v2/depth_anything_v2.py:12 (encoder vits / vitl; use_bn=False, use_clstoken=False)."""
+    """Drop-in for depth_anything_v2/depth_anything_v2.py:12 (encoder vits / vitb / vitl; use_bn=False, use_clstoken=False)."""
 
     def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False, use_clstoken=False, max_memory_length=6):
         super().__init__()

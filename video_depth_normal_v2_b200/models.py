@@ -26,6 +26,8 @@ ENCODER_CONFIGS = {
     "vits": dict(embed_dim=384, depth=12, heads=6, taps=[2, 5, 8, 11]),
     "vitl": dict(embed_dim=1024, depth=24, heads=16, taps=[4, 11, 17, 23]),
 }
+# depth_anything_v2.py:24-29 also lists vitb (dinov2.py:353-364); vitg (SwiGLU FFN, embed_dim 1536) is not built
+DA2_ENCODER_CONFIGS = dict(ENCODER_CONFIGS, vitb=dict(embed_dim=768, depth=12, heads=12, taps=[2, 5, 8, 11]))
 
 # video_depth.py:29-33 — "infer settings, do not change"
 INFER_LEN = 32
@@ -505,12 +507,13 @@ class VideoDepthAnything(_PackedModule):
     # --- the two halves of forward(), exposed for the long-video driver: the encoder is per-frame (dinov2.py:212-321 has no
     # cross-frame op), so the features of the 10 key frames a window shares with its predecessor are computed once.
     @torch.no_grad()
-    def encode_frames(self, x: torch.Tensor) -> List[torch.Tensor]:
-        """x (F, 3, H, W) fp32 -> 4 x [F*ph*pw, C] tapped, final-norm'ed patch tokens (frame-major)."""
+    def encode_frames(self, x: torch.Tensor, clone: bool = True) -> List[torch.Tensor]:
+        """x (F, 3, H, W) fp32 -> 4 x [F*ph*pw, C] tapped, final-norm'ed patch tokens (frame-major).  ``clone=False`` returns the
+        replayed graph's own output buffers (valid until the next call with the same shape)."""
         w = self._weights()
         x = x.to(device=self._dev, dtype=torch.float32).contiguous()
         feats = self._graphs.run(("encode",) + tuple(x.shape), lambda xd: encoder_forward(w["enc"], xd, w["head"].get("readout")), [x])
-        return [f.clone() for f in feats]  # the long-video driver keeps per-frame views of these across windows
+        return [f.clone() for f in feats] if clone else list(feats)  # the long-video driver keeps per-frame views of these across windows
 
     @torch.no_grad()
     def head_from_features(self, feats: List[torch.Tensor], T: int, ph: int, pw: int) -> torch.Tensor:
