@@ -106,6 +106,12 @@ int vdn_temporal_attn_tc(const void* qk, int64_t ld_qk, const void* vT, void* ou
    the positional part (Wq pe_j | Wk pe_j | Wv pe_j); out [D, C] = softmax((q+pq)(k+pk)^T / sqrt(dh)) (v+pv) per (pixel, head) */
 int vdn_stream_temporal_attn(const void* const* qkv_entries, int32_t L, int64_t ld, const float* pos, void* out, int32_t D, int32_t C, int32_t heads,
                              void* stream);
+/* the same attention with the cached projections in a slot pool [slots, D, ld] and a DEVICE-side slot table (int32, entry j = slot of
+   cached frame j, < 0 = `staging`, this frame's projection): launch parameters are frame-independent, so the streaming step replays
+   as one CUDA graph.  vdn_ring_store copies `staging` into slot table[slot_index] of the pool (the cache insertion, also in the graph). */
+int vdn_stream_temporal_attn_ring(const void* pool, const void* staging, const int32_t* slot_table, int32_t L, int64_t ld, const float* pos,
+                                  void* out, int32_t D, int32_t C, int32_t heads, void* stream);
+int vdn_ring_store(const void* staging, void* pool, const int32_t* slot_table, int32_t slot_index, int64_t slot_elems, void* stream);
 
 /* ---- normalisation ----------------------------------------------------------------------------- */
 /* LayerNorm over C of fp32 rows -> 16-bit.  out row = map(row):

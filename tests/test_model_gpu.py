@@ -338,3 +338,20 @@ def test_v5_vitl_32x518x924_matches_oracle_on_gpu(vdn):
     ang = O.normal_angle_deg(n.cpu(), O.sobel_normals((ref[0] / 65535.0)[:, None]).cpu())
     print(f"v5 vitl 32x518x924 sobel normals of the refined depth: max angle {ang:.4f} deg")
     assert ang <= MAX_ANGLE
+
+
+def test_streaming_vitl_matches_oracle_on_gpu(vdn):
+    """ViT-L streaming (head_dim 128 / 32 motion modules -> vectorised streaming attention, ring slots, graph replay from the third
+    frame on) against the oracle's restatement of video_depth_stream.py, 6 frames."""
+    m, sd = _model(vdn, "vitl", 18)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    state = {}
+    for i in range(6):
+        x = make_input("rgb", (1, 1, 3, 56, 70), 180 + i).cuda()
+        d = m.stream_step(x[0, 0])
+        ref = O.vda_stream_step(sd_gpu, x, "vitl", state)
+        _check(f"vitl stream frame {i}", d[None], ref.reshape(1, 56, 70))
+    m.reset_stream()
+    d0 = m.stream_step(make_input("rgb", (1, 1, 3, 56, 70), 180).cuda()[0, 0])
+    state = {}
+    _check("vitl stream frame 0 after reset", d0[None], O.vda_stream_step(sd_gpu, make_input("rgb", (1, 1, 3, 56, 70), 180).cuda(), "vitl", state).reshape(1, 56, 70))

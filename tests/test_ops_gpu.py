@@ -461,3 +461,44 @@ def test_device_preprocess_matches_cv2_transform(ops, H, W, size):
     ops.preprocess_u8(torch.from_numpy(frames).cuda(), out, h, w)
     torch.cuda.synchronize()
     assert float((out.cpu() - ref).abs().max()) < 2e-4  # values span ~[-2.1, 2.6]; fp32 rounding of the 16 taps times 1/std
+
+
+# ----------------------------------------------------------------------------------------------- streaming temporal attention
+@pytest.mark.parametrize("D,C,L", [(37, 256, 32), (50, 1024, 32), (19, 512, 5), (23, 256, 1), (11, 192, 7), (40, 1024, 17)])
+def test_stream_temporal_attn_list_and_ring(ops, D, C, L):
+    """One new frame against L-1 cached frames (motion_module.py:252-269 restated on cached projections): the pointer-list form and
+    the slot-pool form (device-side slot table) against a plain fp32 evaluation.  head_dim 32 / 64 / 128 take the vectorised kernel,
+    192 / 8 = 24 the scalar one."""
+    od = ops.operand_dtype()
+    heads, dh = 8, C // 8
+    entries = [_r16(ops, D, 3 * C, seed=10 + j) for j in range(L)]
+    pos = _f32(32, 3 * C, seed=3) * 0.5
+    out = torch.empty(D, C, device="cuda", dtype=od)
+    ops.stream_temporal_attn(entries, pos, out, D, C, heads)
+    torch.cuda.synchronize()
+    x = torch.stack([e.float() for e in entries]) + pos[:L, None, :]          # (L, D, 3C)
+    q = x[L - 1, :, :C].reshape(D, heads, 1, dh)
+    k = x[:, :, C:2 * C].reshape(L, D, heads, dh).permute(1, 2, 0, 3)
+    v = x[:, :, 2 * C:].reshape(L, D, heads, dh).permute(1, 2, 0, 3)
+    att = ((q @ k.transpose(-1, -2)) * dh ** -0.5).softmax(-1)
+    ref = (att @ v).reshape(D, C)
+    _close("stream temporal attn (list)", out, ref)
+    # ring form: cached entries scattered over pool slots, this frame in the staging buffer
+    slots = 40
+    pool = torch.zeros(slots, D, 3 * C, device="cuda", dtype=od)
+    perm = torch.randperm(slots, generator=torch.Generator().manual_seed(L))[: L - 1].tolist()
+    for j, s_ in enumerate(perm):
+        pool[s_].copy_(entries[j])
+    table = torch.tensor(perm + [-1] * (32 - (L - 1)) + [39 if 39 not in perm else -1], dtype=torch.int32).cuda()
+    out2 = torch.empty_like(out)
+    ops.stream_temporal_attn_ring(pool, entries[L - 1], table, L, pos, out2, D, C, heads)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    before = pool.clone()
+    ops.ring_store(entries[L - 1], pool, table, 32)
+    torch.cuda.synchronize()
+    tgt = int(table[32])
+    if tgt >= 0:
+        assert torch.equal(pool[tgt], entries[L - 1])
+        before[tgt] = entries[L - 1]
+    assert torch.equal(pool, before)

@@ -42,6 +42,8 @@ SIGNATURES = {
     "vdn_flash_attn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdn_flash_attn_ex": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_stream_temporal_attn": (c_int, [C.POINTER(c_void_p), c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdn_stream_temporal_attn_ring": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdn_ring_store": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "vdn_temporal_attn_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "vdn_temporal_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -446,7 +446,29 @@ struct StreamAttnParams {
   const float* pos;         // [32, 3C] fp32: row j = (Wq pe_j | Wk pe_j | Wv pe_j)
   void* out;                // [D, C] 16-bit
   int D, C, heads, L, ld, fmt;
+  // ring mode (table != nullptr): entry j lives in slot table[j] of `pool` ([slots, D, ld]) or, for table[j] < 0, in `staging`
+  // (this frame's projection).  The slot table is DEVICE memory, so the launch parameters do not change from frame to frame and
+  // the whole streaming step can be replayed as one CUDA graph.
+  const uint16_t* pool;
+  const uint16_t* staging;
+  const int* table;
+  long long slot_stride;
 };
+
+__device__ __forceinline__ const uint16_t* stream_entry(const StreamAttnParams& p, int j) {
+  if (p.table == nullptr) return p.qkv[j];
+  const int s = __ldg(p.table + j);
+  return s < 0 ? p.staging : p.pool + (long long)s * p.slot_stride;
+}
+
+// ring mode: staging -> pool[table[slot_index]] (16-byte vectors), the cache insertion of the frame inside the replayed graph
+__global__ void __launch_bounds__(256) ring_store_kernel(const uint4* __restrict__ staging, uint4* __restrict__ pool, const int* __restrict__ table,
+                                                         int slot_index, long long nvec) {
+  const int s = __ldg(table + slot_index);
+  if (s < 0) return;
+  uint4* dst = pool + (long long)s * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) dst[i] = staging[i];
+}
 
 __global__ void __launch_bounds__(256) stream_temporal_attn_kernel(const StreamAttnParams p) {
   const int lane = threadIdx.x & 31;
@@ -463,15 +485,16 @@ __global__ void __launch_bounds__(256) stream_temporal_attn_kernel(const StreamA
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = lane + 32 * i;
-      q[i] = c < dh ? load16(p.qkv[L - 1], d * p.ld + c0 + c, p.fmt) + __ldg(p.pos + (long long)(L - 1) * 3 * p.C + c0 + c) : 0.0f;
+      q[i] = c < dh ? load16(stream_entry(p, L - 1), d * p.ld + c0 + c, p.fmt) + __ldg(p.pos + (long long)(L - 1) * 3 * p.C + c0 + c) : 0.0f;
     }
     float sj = -INFINITY;  // lane j keeps score j
     for (int j = 0; j < L; ++j) {
       float acc = 0.0f;
+      const uint16_t* ej = stream_entry(p, j);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = lane + 32 * i;
-        if (c < dh) acc = fmaf(q[i], load16(p.qkv[j], d * p.ld + p.C + c0 + c, p.fmt) + __ldg(p.pos + (long long)j * 3 * p.C + p.C + c0 + c), acc);
+        if (c < dh) acc = fmaf(q[i], load16(ej, d * p.ld + p.C + c0 + c, p.fmt) + __ldg(p.pos + (long long)j * 3 * p.C + p.C + c0 + c), acc);
       }
       acc = warp_sum(acc) * scale;
       if (lane == j) sj = acc;
@@ -482,10 +505,11 @@ __global__ void __launch_bounds__(256) stream_temporal_attn_kernel(const StreamA
     float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int j = 0; j < L; ++j) {
       const float w = __shfl_sync(0xffffffffu, pj, j);
+      const uint16_t* ej = stream_entry(p, j);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = lane + 32 * i;
-        if (c < dh) o[i] = fmaf(w, load16(p.qkv[j], d * p.ld + 2 * p.C + c0 + c, p.fmt) + __ldg(p.pos + (long long)j * 3 * p.C + 2 * p.C + c0 + c), o[i]);
+        if (c < dh) o[i] = fmaf(w, load16(ej, d * p.ld + 2 * p.C + c0 + c, p.fmt) + __ldg(p.pos + (long long)j * 3 * p.C + 2 * p.C + c0 + c), o[i]);
       }
     }
 #pragma unroll
@@ -494,6 +518,157 @@ __global__ void __launch_bounds__(256) stream_temporal_attn_kernel(const StreamA
       if (c < dh) store16(p.out, d * p.C + c0 + c, o[i], p.fmt);
     }
   }
+}
+
+// Vectorised form for head_dim 32 / 64 / 128 (ViT-L motion modules).  The scalar kernel above reads 2 bytes per lane per load and
+// re-reads the fp32 positional table from global memory for every (pixel, head): 0.7 TB/s.  Here a block serves one head, keeps that
+// head's positional k / v slices in shared memory, and each warp walks its (pixel, head) with 16-byte loads: LPE = DH/8 lanes share
+// one cached entry, 32/LPE entries are in flight per warp; scores meet in shared memory, the output is reduced across the entry
+// groups with shuffles.
+template <int DH, int FMT>
+__global__ void __launch_bounds__(256) stream_temporal_attn_vec_kernel(const StreamAttnParams p) {
+  constexpr int LPE = DH / 8;   // lanes per entry (one 16-byte vector of 8 channels each)
+  constexpr int G = 32 / LPE;   // entries in flight per warp
+  extern __shared__ float sta_smem[];
+  float* pk = sta_smem;                 // [32][DH]
+  float* pv = sta_smem + 32 * DH;       // [32][DH]
+  float* sc = sta_smem + 64 * DH;       // [8 warps][32]
+  const int h = blockIdx.y;
+  const int L = p.L, C = p.C;
+  for (int i = threadIdx.x; i < L * DH; i += blockDim.x) {
+    const int j = i / DH, c = i - j * DH;
+    pk[i] = __ldg(p.pos + (long long)j * 3 * C + C + h * DH + c);
+    pv[i] = __ldg(p.pos + (long long)j * 3 * C + 2 * C + h * DH + c);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / LPE, v8 = lane % LPE;
+  const float scale = rsqrtf((float)DH);
+  float* myscores = sc + warp * 32;
+  const int c_off = h * DH + v8 * 8;
+  for (int d = blockIdx.x * 8 + warp; d < p.D; d += gridDim.x * 8) {
+    const long long row = (long long)d * p.ld;
+    float q[8];
+    {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(stream_entry(p, L - 1) + row + c_off));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(L - 1) * 3 * C + c_off));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(L - 1) * 3 * C + c_off) + 1);
+      float2 t;
+      t = T16f<FMT>::unpack(u.x); q[0] = t.x + a.x; q[1] = t.y + a.y;
+      t = T16f<FMT>::unpack(u.y); q[2] = t.x + a.z; q[3] = t.y + a.w;
+      t = T16f<FMT>::unpack(u.z); q[4] = t.x + b.x; q[5] = t.y + b.y;
+      t = T16f<FMT>::unpack(u.w); q[6] = t.x + b.z; q[7] = t.y + b.w;
+    }
+    // batches of 4 entry groups: the four 16-byte loads of a batch are issued before the first dot product (the loop is otherwise
+    // one exposed global-load latency per group)
+    for (int jb = 0; jb < L; jb += 4 * G) {
+      uint4 u[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = jb + t * G + grp;
+        u[t] = j < L ? __ldg(reinterpret_cast<const uint4*>(stream_entry(p, j) + row + C + c_off)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = jb + t * G + grp;
+        const bool valid = j < L;
+        float acc = 0.0f;
+        if (valid) {
+          const float4 a = *reinterpret_cast<const float4*>(pk + j * DH + v8 * 8);
+          const float4 b = *reinterpret_cast<const float4*>(pk + j * DH + v8 * 8 + 4);
+          float2 f;
+          f = T16f<FMT>::unpack(u[t].x); acc = fmaf(q[0], f.x + a.x, acc); acc = fmaf(q[1], f.y + a.y, acc);
+          f = T16f<FMT>::unpack(u[t].y); acc = fmaf(q[2], f.x + a.z, acc); acc = fmaf(q[3], f.y + a.w, acc);
+          f = T16f<FMT>::unpack(u[t].z); acc = fmaf(q[4], f.x + b.x, acc); acc = fmaf(q[5], f.y + b.y, acc);
+          f = T16f<FMT>::unpack(u[t].w); acc = fmaf(q[6], f.x + b.z, acc); acc = fmaf(q[7], f.y + b.w, acc);
+        }
+#pragma unroll
+        for (int o = LPE / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (valid && v8 == 0) myscores[j] = acc * scale;
+      }
+    }
+    __syncwarp();
+    const float sj = lane < L ? myscores[lane] : -INFINITY;
+    const float mx = warp_max(sj);
+    const float e = lane < L ? __expf(sj - mx) : 0.0f;
+    const float pj = e / warp_sum(e);
+    float o8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    for (int jb = 0; jb < L; jb += 4 * G) {
+      uint4 u[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = jb + t * G + grp;
+        u[t] = j < L ? __ldg(reinterpret_cast<const uint4*>(stream_entry(p, j) + row + 2 * C + c_off)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = jb + t * G + grp;
+        const bool valid = j < L;
+        const float w = __shfl_sync(0xffffffffu, pj, valid ? j : 0);
+        if (valid) {
+          const float4 a = *reinterpret_cast<const float4*>(pv + j * DH + v8 * 8);
+          const float4 b = *reinterpret_cast<const float4*>(pv + j * DH + v8 * 8 + 4);
+          float2 f;
+          f = T16f<FMT>::unpack(u[t].x); o8[0] = fmaf(w, f.x + a.x, o8[0]); o8[1] = fmaf(w, f.y + a.y, o8[1]);
+          f = T16f<FMT>::unpack(u[t].y); o8[2] = fmaf(w, f.x + a.z, o8[2]); o8[3] = fmaf(w, f.y + a.w, o8[3]);
+          f = T16f<FMT>::unpack(u[t].z); o8[4] = fmaf(w, f.x + b.x, o8[4]); o8[5] = fmaf(w, f.y + b.y, o8[5]);
+          f = T16f<FMT>::unpack(u[t].w); o8[6] = fmaf(w, f.x + b.z, o8[6]); o8[7] = fmaf(w, f.y + b.w, o8[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPE; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] += __shfl_xor_sync(0xffffffffu, o8[i], o);
+    }
+    if (grp == 0) {
+      uint4 r;
+      r.x = T16f<FMT>::pack(o8[0], o8[1]); r.y = T16f<FMT>::pack(o8[2], o8[3]);
+      r.z = T16f<FMT>::pack(o8[4], o8[5]); r.w = T16f<FMT>::pack(o8[6], o8[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (long long)d * C + c_off) = r;
+    }
+    __syncwarp();  // myscores is rewritten by the next pixel
+  }
+}
+
+template <int DH>
+static int launch_stream_vec(const StreamAttnParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)(64 * DH + 8 * 32) * sizeof(float);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    cudaFuncSetAttribute(stream_temporal_attn_vec_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(stream_temporal_attn_vec_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  int bx = (p.D + 7) / 8;
+  const int cap = (num_sms() * 8 + p.heads - 1) / p.heads;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)p.heads);
+  if (p.fmt) stream_temporal_attn_vec_kernel<DH, 1><<<grid, 256, smem, stream>>>(p);
+  else stream_temporal_attn_vec_kernel<DH, 0><<<grid, 256, smem, stream>>>(p);
+  count_launch();
+  return check_launch("stream_temporal_attn_vec_kernel");
+}
+
+// all entries 16-byte addressable (rows ld * 2 bytes, channel offsets multiples of 8) and a head_dim the vector kernel is built for
+static bool stream_vec_ok(const StreamAttnParams& p) {
+  const int dh = p.C / p.heads;
+  static const char* env = getenv("VDN_STREAM_ATTN_V1");
+  return env == nullptr && (dh == 32 || dh == 64 || dh == 128) && p.ld % 8 == 0 && p.C % 8 == 0;
+}
+
+static int launch_stream_attn(const StreamAttnParams& p, cudaStream_t stream) {
+  if (stream_vec_ok(p)) {
+    const int dh = p.C / p.heads;
+    if (dh == 32) return launch_stream_vec<32>(p, stream);
+    if (dh == 64) return launch_stream_vec<64>(p, stream);
+    return launch_stream_vec<128>(p, stream);
+  }
+  long long blocks = ((long long)p.D * p.heads + 7) / 8;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  stream_temporal_attn_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  count_launch();
+  return check_launch("stream_temporal_attn_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -801,11 +976,37 @@ extern "C" int vdn_stream_temporal_attn(const void* const* qkv_entries, int32_t 
     p.qkv[j] = reinterpret_cast<const uint16_t*>(qkv_entries[j]);
   }
   p.pos = pos; p.out = out; p.D = D; p.C = C; p.heads = heads; p.L = L; p.ld = (int)ld; p.fmt = get_operand_format();
-  long long blocks = ((long long)D * heads + 7) / 8;
-  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
-  stream_temporal_attn_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  for (int j = 0; j < L; ++j)
+    if ((reinterpret_cast<uintptr_t>(p.qkv[j]) & 15) != 0) return set_error("vdn_stream_temporal_attn: entries must be 16-byte aligned");
+  return launch_stream_attn(p, stream);
+}
+
+extern "C" int vdn_stream_temporal_attn_ring(const void* pool, const void* staging, const int32_t* slot_table, int32_t L, int64_t ld, const float* pos,
+                                             void* out, int32_t D, int32_t C, int32_t heads, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!pool || !staging || !slot_table || !pos || !out) return set_error("vdn_stream_temporal_attn_ring: null pointer");
+  if (L < 1 || L > 32) return set_error("vdn_stream_temporal_attn_ring: L must be in [1, 32]");
+  if (heads <= 0 || C % heads != 0 || C / heads > 128 || ld < 3 * C) return set_error("vdn_stream_temporal_attn_ring: head_dim must be <= 128 and ld >= 3*C");
+  StreamAttnParams p{};
+  p.pos = pos; p.out = out; p.D = D; p.C = C; p.heads = heads; p.L = L; p.ld = (int)ld; p.fmt = get_operand_format();
+  p.pool = reinterpret_cast<const uint16_t*>(pool);
+  p.staging = reinterpret_cast<const uint16_t*>(staging);
+  p.table = slot_table;
+  p.slot_stride = (long long)D * ld;
+  if (((reinterpret_cast<uintptr_t>(pool) | reinterpret_cast<uintptr_t>(staging)) & 15) != 0) return set_error("vdn_stream_temporal_attn_ring: buffers must be 16-byte aligned");
+  return launch_stream_attn(p, stream);
+}
+
+extern "C" int vdn_ring_store(const void* staging, void* pool, const int32_t* slot_table, int32_t slot_index, int64_t slot_elems, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!staging || !pool || !slot_table) return set_error("vdn_ring_store: null pointer");
+  if (slot_elems <= 0 || slot_elems % 8 != 0 || slot_index < 0) return set_error("vdn_ring_store: slot_elems must be a positive multiple of 8");
+  const long long nvec = slot_elems / 8;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  ring_store_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(staging), reinterpret_cast<uint4*>(pool), slot_table, slot_index, nvec);
   count_launch();
-  return check_launch("stream_temporal_attn_kernel");
+  return check_launch("ring_store_kernel");
 }
 
 extern "C" int vdn_temporal_attn_tc(const void* qk, int64_t ld_qk, const void* vT, void* out, int64_t rows, int32_t C, int32_t heads, void* stream_v) {

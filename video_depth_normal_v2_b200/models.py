@@ -183,7 +183,11 @@ def motion_module_forward(mm: dict, x: torch.Tensor, Bv: int, T: int, D: int, re
     return (y, y_relu) if relu_copy else y
 
 
-def motion_module_stream(mm: dict, x: torch.Tensor, D: int, cached: Optional[list], new_cache: list):
+RING_NEW_SLOT = 32   # index in the slot table of the pool slot that receives this frame's projections
+RING_SLOTS = 44      # the reference's cache list holds at most 42 frames (video_depth_stream.py:150-158) + the incoming one
+
+
+def motion_module_stream(mm: dict, x: torch.Tensor, D: int, cached: Optional[list], new_cache: list, ring: Optional[dict] = None):
     """One new frame through a motion module with cached history (motion_module.py:102-136 with cached_hidden_state_list,
     TemporalAttention.forward :252-259).  x: [1, D, C] 16-bit NHWC.  ``cached``: per attention block the list of earlier frames'
     cached projections (oldest first); ``new_cache`` receives this frame's two projections.  The reference caches the normed hidden
@@ -200,11 +204,19 @@ def motion_module_stream(mm: dict, x: torch.Tensor, D: int, cached: Optional[lis
     ao = _empty((D, C), od, dev)
     for i, a in enumerate(mm["attn"]):
         ops.layernorm(h, a["ln_w"], a["ln_b"], n16, 1e-5)  # the positional term is applied in the attention kernel
-        proj = _empty((D, 3 * C), od, dev)                 # (Wq n | Wk n | Wv n) of this frame: what gets cached
-        ops.gemm(n16, a["qkv_w"], proj, M=D, N=3 * C, K=C)
-        new_cache.append(proj)
-        entries = (cached[i] if cached is not None else []) + [proj]
-        ops.stream_temporal_attn(entries, a["pos_qkv"], ao, D, C, 8)
+        if ring is not None:
+            # graph-replayable form: this frame's projection goes to a fixed staging buffer, the cached ones are addressed through
+            # the device-side slot table, and the cache insertion (staging -> pool[new slot]) is a kernel of the same graph
+            proj, pool = ring["staging"][i], ring["pool"][i]
+            ops.gemm(n16, a["qkv_w"], proj, M=D, N=3 * C, K=C)
+            ops.stream_temporal_attn_ring(pool, proj, ring["table"], ring["L"], a["pos_qkv"], ao, D, C, 8)
+            ops.ring_store(proj, pool, ring["table"], RING_NEW_SLOT)
+        else:
+            proj = _empty((D, 3 * C), od, dev)             # (Wq n | Wk n | Wv n) of this frame: what gets cached
+            ops.gemm(n16, a["qkv_w"], proj, M=D, N=3 * C, K=C)
+            new_cache.append(proj)
+            entries = (cached[i] if cached is not None else []) + [proj]
+            ops.stream_temporal_attn(entries, a["pos_qkv"], ao, D, C, 8)
         ops.gemm(ao, a["out"]["w"], h, M=D, N=C, K=C, bias=a["out"]["b"], res=h)
     ops.layernorm(h, mm["ffn_w"], mm["ffn_b"], n16, 1e-5)
     g = _empty((D, 4 * C), od, dev)
@@ -287,6 +299,9 @@ def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: in
     ops.gemm(col, head["resize3"]["w"], layer4, M=Bf * H4 * W4, N=oc[3], K=9 * oc[3], bias=head["resize3"]["b"])
     # ---- temporal mixing on layer_3 / layer_4 (dpt_temporal.py:81-84)
     def mm_stream(m, x, D):
+        if "ring" in stream:  # {"ring": per motion module {"pool": [2], "staging": [2]}, "table": int32[33] device, "L": entries}
+            r = dict(stream["ring"][m], table=stream["table"], L=stream["L"])
+            return motion_module_stream(head["mm"][m], x, D, None, [], ring=r)
         cached = stream["cached"][m] if stream["cached"] is not None else None
         return motion_module_stream(head["mm"][m], x, D, cached, stream["new"])
 
@@ -528,32 +543,69 @@ class VideoDepthAnything(_PackedModule):
     def reset_stream(self):
         self._stream = None
 
+    def _stream_ring(self, ph: int, pw: int) -> dict:
+        """Slot pools for the cached per-frame projections of the 4 motion modules x 2 attention blocks at this patch grid, the
+        staging buffers of the incoming frame and the device-side slot table (persistent: the stream graph holds their addresses)."""
+        rings = self.__dict__.setdefault("_rings", {})
+        key = (ph, pw, ops.operand_dtype(), self._dev)
+        if key not in rings:
+            od, dev = ops.operand_dtype(), self._dev
+            oc, Fe = self.cfg["out_channels"], self.cfg["features"]
+            H4, W4 = (ph - 1) // 2 + 1, (pw - 1) // 2 + 1
+            geo = [(ph * pw, oc[2]), (H4 * W4, oc[3]), (ph * pw, Fe), (4 * ph * pw, Fe)]  # (pixels, channels) of mm0..mm3
+            rings[key] = {"mods": [{"pool": [torch.empty((RING_SLOTS, D, 3 * C), dtype=od, device=dev) for _ in range(2)],
+                                    "staging": [torch.empty((D, 3 * C), dtype=od, device=dev) for _ in range(2)]} for D, C in geo],
+                          "table": torch.full((RING_NEW_SLOT + 1,), -1, dtype=torch.int32, device=dev)}
+        return rings[key]
+
     @torch.no_grad()
     def stream_step(self, x: torch.Tensor) -> torch.Tensor:
         """One pre-processed frame x (3, h, w) fp32 -> depth (h, w) fp32 on the device, attending to the cached history:
-        frame 0, the second-oldest kept frame and the last 29 frames (video_depth_stream.py:130-158)."""
+        frame 0, the second-oldest kept frame and the last 29 frames (video_depth_stream.py:130-158).  The cache list holds pool
+        slot numbers; from the second frame on the whole step (encoder, head, cache insertion) replays as one CUDA graph whose
+        only per-frame input besides the image is the 33-entry device slot table."""
         w = self._weights()
         st = getattr(self, "_stream", None)
-        if st is None:
-            st = self._stream = {"id": -1, "cache": []}
-        st["id"] += 1
         _, h, wd = x.shape
         ph, pw = h // 14, wd // 14
-        feats = encoder_forward(w["enc"], x.to(device=self._dev, dtype=torch.float32).unsqueeze(0).contiguous(), w["head"].get("readout"))
-        new: list = []
+        ring = self._stream_ring(ph, pw)
+        if st is None:
+            st = self._stream = {"id": -1, "cache": [], "free": list(range(RING_SLOTS - 1, -1, -1)), "grid": (ph, pw)}
+        elif st["grid"] != (ph, pw):
+            raise RuntimeError("frame size changed mid-stream")
+        st["id"] += 1
+        xd = x.to(device=self._dev, dtype=torch.float32).unsqueeze(0).contiguous()
+        slot = st["free"].pop()
         if st["id"] == 0:
+            # the encoder of one frame has fixed shapes and touches no cache: CUDA-graph replay
+            feats = self.encode_frames(xd, clone=False)
+            new: list = []
             depth = head_forward(w["head"], feats, 1, ph, pw, 1, stream={"cached": None, "new": new})
-            st["cache"] = [new] * INFER_LEN  # "copy multiple cache to simulate the windows"
+            for m in range(4):
+                for a in range(2):
+                    ring["mods"][m]["pool"][a][slot].copy_(new[2 * m + a])
+            st["cache"] = [slot] * INFER_LEN  # "copy multiple cache to simulate the windows"
+            depth = depth[0]
         else:
             cl = st["cache"]
             cur = cl[0:2] + cl[-INFER_LEN + 3:]
-            cached = [[[fr[2 * m + a] for fr in cur] for a in range(2)] for m in range(4)]
-            depth = head_forward(w["head"], feats, 1, ph, pw, 1, stream={"cached": cached, "new": new})
-            st["cache"] = cl + [new]
+            table = cur + [-1] * (RING_NEW_SLOT - len(cur)) + [slot]  # entry len(cur) = -1 = this frame (staging)
+            ring["table"].copy_(torch.tensor(table, dtype=torch.int32))
+            L = len(cur) + 1
+
+            def run(xs):
+                feats = encoder_forward(w["enc"], xs, w["head"].get("readout"))
+                return head_forward(w["head"], feats, 1, ph, pw, 1, stream={"ring": ring["mods"], "table": ring["table"], "L": L})
+
+            depth = self._graphs.run(("stream", ph, pw, L), run, [xd])[0].clone()
+            st["cache"] = cl + [slot]
         gap = (INFER_LEN - OVERLAP) * 2 - 1 - (OVERLAP - INTERP_LEN)
         if st["id"] + INFER_LEN > gap + 1:
+            dropped = st["cache"][1]
             st["cache"] = st["cache"][:1] + st["cache"][2:]
-        return depth[0]
+            if dropped not in st["cache"]:
+                st["free"].append(dropped)
+        return depth
 
     @torch.no_grad()
     def infer_video_depth_one(self, frame, input_size=518, device="cuda", fp32=False):

@@ -187,6 +187,24 @@ def stream_temporal_attn(entries, pos: torch.Tensor, out: torch.Tensor, D: int, 
     return out
 
 
+def stream_temporal_attn_ring(pool: torch.Tensor, staging: torch.Tensor, table: torch.Tensor, L: int, pos: torch.Tensor, out: torch.Tensor, D: int,
+                              C_: int, heads: int):
+    """Ring form: pool [slots, D, 3C], staging [D, 3C] (this frame), table int32 device tensor (entry j = slot of cached frame j, < 0 = staging)."""
+    od = operand_dtype()
+    _check(_run("stream_temporal_attn", "hbm", 2.0 * L * D * 2 * C_ + 4.0 * D * C_, lib().vdn_stream_temporal_attn_ring, _ptr(pool, od, "pool"),
+                _ptr(staging, od, "staging"), _ptr(table, torch.int32, "table"), L, staging.shape[-1], _ptr(pos, torch.float32, "pos"), _ptr(out, od, "out"),
+                D, C_, heads, _stream()), "vdn_stream_temporal_attn_ring")
+    return out
+
+
+def ring_store(staging: torch.Tensor, pool: torch.Tensor, table: torch.Tensor, slot_index: int):
+    """pool[table[slot_index]] = staging (device-side slot lookup; a negative slot skips the store)."""
+    od = operand_dtype()
+    _check(_run("ring_store", "hbm", 4.0 * staging.numel(), lib().vdn_ring_store, _ptr(staging, od, "staging"), _ptr(pool, od, "pool"),
+                _ptr(table, torch.int32, "table"), slot_index, staging.numel(), _stream()), "vdn_ring_store")
+    return pool
+
+
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor, eps: float, drop_first: bool = False, rows_per_batch: int = 0,
               pe: Optional[torch.Tensor] = None):
     rows, C_ = x.shape[0], x.shape[1]
