@@ -25,7 +25,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
 
 // MAXN: how many values the row-max pass covers (the split layout can re-read the whole 128-wide row so both halves agree on m)
 template <int NS, int POLY, int MAXN>
-__global__ void k(float* out, long long* cyc, float seed) {
+__global__ void k(float* out, long long* cyc, float seed, int skew) {
   float s[NS];
   float extra[MAXN > NS ? MAXN - NS : 1];
 #pragma unroll
@@ -37,6 +37,10 @@ __global__ void k(float* out, long long* cyc, float seed) {
   uint32_t acc = 0;
   __syncthreads();
   long long t0 = clock64();
+  if (skew > 0) {  // de-synchronise the warps of a sub-partition (in the real kernel they never run in lockstep)
+    const long long until = t0 + (long long)((threadIdx.x >> 7) * skew);
+    while (clock64() < until) {}
+  }
   for (int it = 0; it < ITERS; ++it) {
     float mx0 = -1e30f, mx1 = -1e30f;
 #pragma unroll
@@ -73,17 +77,17 @@ __global__ void k(float* out, long long* cyc, float seed) {
 }
 
 template <int NS, int POLY, int MAXN>
-void run(const char* name, int wps) {
+void run(const char* name, int wps, int skew = 0) {
   float* out; long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
   int threads = wps * 128;
-  k<NS, POLY, MAXN><<<148, threads>>>(out, cyc, 1e-3f);
+  k<NS, POLY, MAXN><<<148, threads>>>(out, cyc, 1e-3f, skew);
   cudaDeviceSynchronize();
-  k<NS, POLY, MAXN><<<148, threads>>>(out, cyc, 1e-3f);
+  k<NS, POLY, MAXN><<<148, threads>>>(out, cyc, 1e-3f, skew);
   long long h[148];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
   double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
-  printf("%-44s warps/SMSP=%d scores/thread=%3d poly=%d/8  cycles per %d score-columns per SMSP = %8.1f\n", name, wps, NS, POLY, wps * NS, avg / ITERS);
+  printf("%-44s warps/SMSP=%d scores/thread=%3d poly=%d/8 skew=%4d  cycles per %d score-columns per SMSP = %8.1f\n", name, wps, NS, POLY, skew, wps * NS, avg / ITERS);
   cudaFree(out); cudaFree(cyc);
 }
 
@@ -100,6 +104,13 @@ int main() {
   run<64, 1, 128>("half row per thread, full-row max", 4);
   run<64, 2, 128>("half row per thread, full-row max", 4);
   run<64, 3, 128>("half row per thread, full-row max", 4);
+  for (int skew : {200, 500, 900, 1300}) {
+    run<128, 2, 128>("row per thread (shipped), skewed start", 2, skew);
+    run<128, 0, 128>("row per thread, skewed start", 2, skew);
+    run<64, 2, 64>("half row per thread, half-row max, skewed", 4, skew);
+    run<64, 2, 128>("half row per thread, full-row max, skewed", 4, skew);
+    run<64, 0, 64>("half row per thread, half-row max, skewed", 4, skew);
+  }
   run<32, 2, 32>("quarter row per thread", 8);
   run<32, 3, 32>("quarter row per thread", 8);
   printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
