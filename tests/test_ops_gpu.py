@@ -252,7 +252,7 @@ def test_temporal_attention_tcgen05(ops, D, C):
 
 
 # ----------------------------------------------------------------------------------------------- norms / layout
-@pytest.mark.parametrize("rows,C", [(1370 * 2, 384), (1000, 1024), (77, 64), (300, 192), (64, 256)])
+@pytest.mark.parametrize("rows,C", [(1370 * 2, 384), (1000, 1024), (77, 64), (300, 192), (64, 256), (333, 768), (4097, 1024), (9001, 256)])
 def test_layernorm(ops, rows, C):
     x, w, b = _f32(rows, C, scale=3.0, seed=1) + 0.5, _f32(C, seed=2), _f32(C, seed=3)
     out = torch.empty(rows, C, device="cuda", dtype=ops.operand_dtype())
@@ -266,8 +266,8 @@ def test_layernorm(ops, rows, C):
     _close("layernorm+pe", out, ref)
 
 
-def test_layernorm_drop_cls(ops):
-    B, N, C = 3, 31, 384
+@pytest.mark.parametrize("B,N,C", [(3, 31, 384), (5, 1370, 1024), (2, 2, 256), (4, 17, 192), (7, 258, 768)])
+def test_layernorm_drop_cls(ops, B, N, C):
     x, w, b = _f32(B * N, C, seed=1), _f32(C, seed=2), _f32(C, seed=3)
     out = torch.empty(B * (N - 1), C, device="cuda", dtype=ops.operand_dtype())
     ops.layernorm(x, w, b, out, 1e-6, drop_first=True, rows_per_batch=N)

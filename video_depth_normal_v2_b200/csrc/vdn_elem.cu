@@ -86,21 +86,26 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
   }
 }
 
-// Plain rows (no row map, no positional term), C = 128 * NV: two rows per warp in flight (all 2 x NV 16-byte loads are issued
-// before the first reduction), 32-bit index arithmetic, streaming loads — the ViT blocks' 48 LayerNorms per window.
-template <int NV, int FMT>
+// C = 128 * NV: two rows per warp in flight (all 2 x NV 16-byte loads are issued before the first reduction), 32-bit index
+// arithmetic, streaming loads — the ViT blocks' 48 LayerNorms per window.  PE adds the positional table row (row % pe_len) to the
+// output (motion-module attention inputs), DROP iterates over OUTPUT rows and skips the first row of every batch of rpb source rows
+// (the tapped features without their cls token): both used to take the generic kernel at less than half this kernel's rate.
+template <int NV, int FMT, bool PE, bool DROP>
 __global__ void __launch_bounds__(256)
 layernorm_rows2_kernel(const float4* __restrict__ x, const float4* __restrict__ w, const float4* __restrict__ b, uint2* __restrict__ out, int rows,
-                       float eps) {
+                       float eps, const float4* __restrict__ pe, int pe_len, int rpb) {
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   constexpr float invC = 1.0f / (float)(NV * 128);
-  for (int row = warp0; row < rows; row += 2 * nwarps) {
+  for (int row = warp0; row < rows; row += 2 * nwarps) {   // `rows` / `row` count output rows
     const int row2 = row + nwarps;
     const bool has2 = row2 < rows;
-    const float4* xa = x + (long long)row * (NV * 32);
-    const float4* xb = x + (long long)(has2 ? row2 : row) * (NV * 32);
+    const int rb = has2 ? row2 : row;
+    const int sa_row = DROP ? row + row / (rpb - 1) + 1 : row;   // source rows
+    const int sb_row = DROP ? rb + rb / (rpb - 1) + 1 : rb;
+    const float4* xa = x + (long long)sa_row * (NV * 32);
+    const float4* xb = x + (long long)sb_row * (NV * 32);
     float4 va[NV], vb[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) va[i] = __ldcs(xa + lane + 32 * i);
@@ -131,34 +136,54 @@ layernorm_rows2_kernel(const float4* __restrict__ x, const float4* __restrict__ 
       qa += __shfl_xor_sync(0xffffffffu, qa, o);
       qb += __shfl_xor_sync(0xffffffffu, qb, o);
     }
-    const float ra = rsqrtf(qa * invC + eps), rb = rsqrtf(qb * invC + eps);
+    const float ra = rsqrtf(qa * invC + eps), rb_ = rsqrtf(qb * invC + eps);
     uint2* oa = out + (long long)row * (NV * 32);
     uint2* ob = out + (long long)row2 * (NV * 32);
+    const float4* pa = PE ? pe + (long long)(sa_row % pe_len) * (NV * 32) : nullptr;
+    const float4* pb = PE ? pe + (long long)(sb_row % pe_len) * (NV * 32) : nullptr;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float4 g = __ldg(w + lane + 32 * i);
       const float4 be = __ldg(b + lane + 32 * i);
+      float4 ya, yb;
+      ya.x = (va[i].x - ma) * ra * g.x + be.x; ya.y = (va[i].y - ma) * ra * g.y + be.y;
+      ya.z = (va[i].z - ma) * ra * g.z + be.z; ya.w = (va[i].w - ma) * ra * g.w + be.w;
+      yb.x = (vb[i].x - mb) * rb_ * g.x + be.x; yb.y = (vb[i].y - mb) * rb_ * g.y + be.y;
+      yb.z = (vb[i].z - mb) * rb_ * g.z + be.z; yb.w = (vb[i].w - mb) * rb_ * g.w + be.w;
+      if (PE) {
+        const float4 p0 = __ldg(pa + lane + 32 * i), p1 = __ldg(pb + lane + 32 * i);
+        ya.x += p0.x; ya.y += p0.y; ya.z += p0.z; ya.w += p0.w;
+        yb.x += p1.x; yb.y += p1.y; yb.z += p1.z; yb.w += p1.w;
+      }
       uint2 u;
-      u.x = T16f<FMT>::pack((va[i].x - ma) * ra * g.x + be.x, (va[i].y - ma) * ra * g.y + be.y);
-      u.y = T16f<FMT>::pack((va[i].z - ma) * ra * g.z + be.z, (va[i].w - ma) * ra * g.w + be.w);
+      u.x = T16f<FMT>::pack(ya.x, ya.y);
+      u.y = T16f<FMT>::pack(ya.z, ya.w);
       oa[lane + 32 * i] = u;
       if (has2) {
-        u.x = T16f<FMT>::pack((vb[i].x - mb) * rb * g.x + be.x, (vb[i].y - mb) * rb * g.y + be.y);
-        u.y = T16f<FMT>::pack((vb[i].z - mb) * rb * g.z + be.z, (vb[i].w - mb) * rb * g.w + be.w);
+        u.x = T16f<FMT>::pack(yb.x, yb.y);
+        u.y = T16f<FMT>::pack(yb.z, yb.w);
         ob[lane + 32 * i] = u;
       }
     }
   }
 }
 
+// rows = output rows; pe / drop select the variant
 template <int NV>
-static void launch_layernorm_rows2(const float* x, const float* w, const float* b, void* out, long long rows, float eps, cudaStream_t stream) {
+static void launch_layernorm_rows2(const float* x, const float* w, const float* b, void* out, long long rows, float eps, const float* pe, int pe_len,
+                                   int drop_rpb, cudaStream_t stream) {
   const unsigned grid = grid_for((rows + 1) / 2, 8);
   const float4* x4 = reinterpret_cast<const float4*>(x);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   const float4* b4 = reinterpret_cast<const float4*>(b);
-  if (get_operand_format()) layernorm_rows2_kernel<NV, 1><<<grid, 256, 0, stream>>>(x4, w4, b4, reinterpret_cast<uint2*>(out), (int)rows, eps);
-  else layernorm_rows2_kernel<NV, 0><<<grid, 256, 0, stream>>>(x4, w4, b4, reinterpret_cast<uint2*>(out), (int)rows, eps);
+  const float4* p4 = reinterpret_cast<const float4*>(pe);
+  uint2* o2 = reinterpret_cast<uint2*>(out);
+#define VDN_LN2(F, P, D) layernorm_rows2_kernel<NV, F, P, D><<<grid, 256, 0, stream>>>(x4, w4, b4, o2, (int)rows, eps, p4, pe_len, drop_rpb)
+  const int fmt = get_operand_format();
+  if (pe != nullptr) { if (fmt) VDN_LN2(1, true, false); else VDN_LN2(0, true, false); }
+  else if (drop_rpb > 0) { if (fmt) VDN_LN2(1, false, true); else VDN_LN2(0, false, true); }
+  else { if (fmt) VDN_LN2(1, false, false); else VDN_LN2(0, false, false); }
+#undef VDN_LN2
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -732,10 +757,14 @@ extern "C" int vdn_layernorm(const float* x, const float* w, const float* b, voi
   if (drop_first && (rows_per_batch < 2 || rows % rows_per_batch != 0)) return set_error("vdn_layernorm: bad rows_per_batch");
   if (pe && pe_len <= 0) return set_error("vdn_layernorm: bad pe_len");
   static const char* env = getenv("VDN_LN_V1");
-  const bool plain = !drop_first && pe == nullptr && rows < 0x3fffffffLL && env == nullptr;
-  if (plain && C == 1024) launch_layernorm_rows2<8>(x, w, b, out, rows, eps, stream);
-  else if (plain && C == 384) launch_layernorm_rows2<3>(x, w, b, out, rows, eps, stream);
-  else if (plain && C == 256) launch_layernorm_rows2<2>(x, w, b, out, rows, eps, stream);
+  // the two-rows-per-warp kernel: plain, + positional table, or drop-first (not both at once); output rows fit 32 bits
+  const bool fast = !(drop_first && pe != nullptr) && rows < 0x3fffffffLL && env == nullptr;
+  const long long out_rows = drop_first ? rows / rows_per_batch * (rows_per_batch - 1) : rows;
+  const int rpb = drop_first ? rows_per_batch : 0;
+  if (fast && C == 1024) launch_layernorm_rows2<8>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
+  else if (fast && C == 768) launch_layernorm_rows2<6>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
+  else if (fast && C == 384) launch_layernorm_rows2<3>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
+  else if (fast && C == 256) launch_layernorm_rows2<2>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
   else layernorm_kernel<<<grid_for(rows, 8), 256, 0, stream>>>(x, w, b, out, rows, C, eps, drop_first, rows_per_batch, pe, pe_len, get_operand_format());
   count_launch();
   return check_launch("layernorm_kernel");
