@@ -1,5 +1,5 @@
 """Stand-alone timing of the DPT-head bilinear upsamples (align_corners=True, NHWC 16-bit) at the ViT-L 518x518 shapes, 32 frames.
-usage: run_bilinear.py [substring of the case name]   (VDN_BILINEAR_V1=1 selects the older gather kernel)"""
+usage: run_bilinear.py [substring of the case name]   (VDN_BILINEAR_RUN=N overrides the run length per thread)"""
 import sys, torch
 sys.path.insert(0, ".")
 from video_depth_normal_v2_b200 import ops

@@ -323,11 +323,11 @@ def test_im2col_3x3_s2(ops):
 
 
 @pytest.mark.parametrize("H,W,Ho,Wo,C", [(19, 19, 37, 37, 64), (37, 37, 74, 74, 256), (10, 12, 20, 24, 64), (40, 48, 70, 84, 32), (5, 6, 5, 6, 8),
-                                         (60, 296, 105, 518, 128),   # several wo tiles per row (row-staged kernel)
-                                         (33, 400, 12, 90, 64),      # down-scaling: few output pixels per staged tile
-                                         (7, 9, 50, 301, 96),        # large up-scaling, 32-channel chunks
+                                         (60, 296, 105, 518, 128),   # several runs per row
+                                         (33, 400, 12, 90, 64),      # down-scaling: every step crosses source pixels
+                                         (7, 9, 50, 301, 96),        # large up-scaling: long stretches between two source pixels
                                          (21, 1, 40, 1, 64), (1, 17, 1, 40, 64), (9, 11, 1, 1, 64),  # degenerate extents
-                                         (12, 14, 24, 28, 48)])      # C % 32 != 0: gather kernel
+                                         (12, 14, 24, 28, 48)])      # channel vectors that do not fill a warp
 def test_bilinear_nhwc(ops, H, W, Ho, Wo, C):
     od = ops.operand_dtype()
     x = _r16(ops, 2, H, W, C, seed=1)

@@ -392,68 +392,6 @@ __device__ __forceinline__ void ac_coords(int dst, float scale, int in_size, int
   l1 = src - (float)i0;
 }
 
-// grid (x-chunks of one output row, Ho, B): row coordinates are block-uniform, only 32-bit index arithmetic per thread
-// (the flat 64-bit div/mod version was instruction-bound at ~30 % of HBM bandwidth).  Each thread produces 8 channels of one
-// output pixel from four 16-byte loads (neighbouring pixels hit L1/L2) and writes one or two 16-byte results.
-// VPT 16-byte channel vectors of one output pixel per thread: the coordinate / weight arithmetic is per pixel, and with one vector
-// per thread the kernel was issue-bound (87 % issue-active, 3.1 TB/s at 128 channels).
-template <int FMT, int RELU2, int VPT>
-__global__ void __launch_bounds__(256)
-bilinear_nhwc_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4* __restrict__ o_relu, int H, int W, int Ho, int Wo, int cv,
-                     int relu_out) {
-  const int ho = blockIdx.y;
-  const long long bimg = blockIdx.z;
-  const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.0f;
-  const float sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.0f;
-  int h0, h1;
-  float lh;
-  ac_coords(ho, sh, H, h0, h1, lh);
-  const uint4* row0 = xin + (bimg * H + h0) * (long long)W * cv;
-  const uint4* row1 = xin + (bimg * H + h1) * (long long)W * cv;
-  uint4* orow = o + (bimg * Ho + ho) * (long long)Wo * cv;
-  uint4* orow_relu = RELU2 ? o_relu + (bimg * Ho + ho) * (long long)Wo * cv : nullptr;
-  const int cq = cv / VPT;          // threads per pixel
-  const int per_row = Wo * cq;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
-    const int wo = i / cq;
-    const int c8 = i - wo * cq;     // this thread's vectors: c8, c8 + cq, c8 + 2 cq, ...
-    int w0, w1;
-    float lw;
-    ac_coords(wo, sw, W, w0, w1, lw);
-    const float w00 = (1.0f - lh) * (1.0f - lw), w01 = (1.0f - lh) * lw, w10 = lh * (1.0f - lw), w11 = lh * lw;
-    const uint4* pa4 = row0 + w0 * cv + c8;
-    const uint4* pb4 = row0 + w1 * cv + c8;
-    const uint4* pc4 = row1 + w0 * cv + c8;
-    const uint4* pd4 = row1 + w1 * cv + c8;
-    uint4 a[VPT], b[VPT], c[VPT], d[VPT];
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      a[v] = __ldg(pa4 + v * cq);
-      b[v] = __ldg(pb4 + v * cq);
-      c[v] = __ldg(pc4 + v * cq);
-      d[v] = __ldg(pd4 + v * cq);
-    }
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      const uint32_t* pa = &a[v].x; const uint32_t* pb = &b[v].x; const uint32_t* pc = &c[v].x; const uint32_t* pd = &d[v].x;
-      uint4 r, rr;
-      uint32_t* pr = &r.x;
-      uint32_t* prr = &rr.x;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = T16f<FMT>::unpack(pa[k]), fb = T16f<FMT>::unpack(pb[k]), fc = T16f<FMT>::unpack(pc[k]), fd = T16f<FMT>::unpack(pd[k]);
-        float y0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
-        float y1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
-        if (relu_out) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
-        pr[k] = T16f<FMT>::pack(y0, y1);
-        if (RELU2) prr[k] = T16f<FMT>::pack(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f));
-      }
-      orow[wo * cv + c8 + v * cq] = r;
-      if (RELU2) orow_relu[wo * cv + c8 + v * cq] = rr;
-    }
-  }
-}
-
 // Packed fp32 pairs (sm_100 FFMA2 / FMUL2): one issue slot for two lanes of a lerp.
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   unsigned long long ra, rb, rc;
@@ -475,19 +413,20 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
-// Row-staged separable variant (channel chunks of CC = 8 * CV8 channels, CV8 a power of two): block = (wo tile x channel chunk,
-// output row, image).  Phase 1 lerps the two source rows VERTICALLY once per source pixel into fp32 shared memory (two float4
-// planes, conflict-free 16-byte accesses); phase 2 lerps HORIZONTALLY per output pixel.  Against the gather kernel above this
-// converts each source value once per output row instead of once per output pixel and uses packed FFMA2, ~3x fewer issue slots
-// per output byte (that kernel sat at 87 % issue-active, 2.8 TB/s).  Same coordinate arithmetic (ac_coords); the fp32 evaluation
-// order (vertical first) differs from ATen's by fp32 rounding only.
-template <int FMT, int RELU2, int CV8>
-__global__ void __launch_bounds__(256)
-bilinear_rows_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4* __restrict__ o_relu, int H, int W, int Ho, int Wo, int cv,
-                     int tw, int nchunks, int relu_out) {
-  extern __shared__ float4 bil_smem[];
-  const int chunk = blockIdx.x % nchunks;
-  const int tile = blockIdx.x / nchunks;
+// A thread owns one 16-byte channel vector over a run of L consecutive output pixels of one output row and keeps the two
+// vertically-lerped source columns it is between in registers (fp32, packed FFMA2); when the run crosses a source pixel the right
+// column becomes the left one and one new column is loaded (two 16-byte loads, L1/L2 hits).  No shared memory, no barrier;
+// consecutive threads are consecutive channel vectors, so every access of a warp is one contiguous run of up to 512 bytes.
+// Same coordinate arithmetic as ATen (ac_coords); the evaluation order (vertical first) differs from ATen's by fp32 rounding only.
+// History: a gather kernel (four 16-byte loads and a full 4-tap blend per output vector) was issue-bound at 2.8 TB/s; a row-staged
+// variant through shared memory reached 4.1-4.9 TB/s alone but stalled on its own shared-memory traffic; this one 4.2-5.7 TB/s.
+template <int FMT, int RELU2>
+__global__ void __launch_bounds__(128)
+bilinear_slide_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4* __restrict__ o_relu, int H, int W, int Ho, int Wo, int cv, int L,
+                      int nseg, int relu_out) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= nseg * cv) return;
+  const int seg = t / cv, v = t - seg * cv;
   const int ho = blockIdx.y;
   const long long bimg = blockIdx.z;
   const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.0f;
@@ -495,57 +434,61 @@ bilinear_rows_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4
   int h0, h1;
   float lh;
   ac_coords(ho, sh, H, h0, h1, lh);
-  const int wo_a = tile * tw;
-  const int wo_b = min(wo_a + tw, Wo);
-  int w_lo, w_hi, tmp;
-  float ftmp;
-  ac_coords(wo_a, sw, W, w_lo, tmp, ftmp);
-  ac_coords(wo_b - 1, sw, W, tmp, w_hi, ftmp);
-  const int nin = w_hi - w_lo + 1;
-  float4* plane0 = bil_smem;                 // channels 0-3 of every (pixel, vector)
-  float4* plane1 = bil_smem + nin * CV8;     // channels 4-7
-  const uint4* row0 = xin + ((bimg * H + h0) * (long long)W + w_lo) * cv + chunk * CV8;
-  const uint4* row1 = xin + ((bimg * H + h1) * (long long)W + w_lo) * cv + chunk * CV8;
+  const uint4* row0 = xin + (bimg * H + h0) * (long long)W * cv + v;
+  const uint4* row1 = xin + (bimg * H + h1) * (long long)W * cv + v;
   const float2 wa = make_float2(1.0f - lh, 1.0f - lh), wb = make_float2(lh, lh);
-  for (int i = threadIdx.x; i < nin * CV8; i += 256) {
-    const int p = i / CV8, v = i - p * CV8;
-    const uint4 a = __ldg(row0 + p * cv + v);
-    const uint4 c = __ldg(row1 + p * cv + v);
-    float2 r0 = ffma2(T16f<FMT>::unpack(c.x), wb, fmul2(T16f<FMT>::unpack(a.x), wa));
-    float2 r1 = ffma2(T16f<FMT>::unpack(c.y), wb, fmul2(T16f<FMT>::unpack(a.y), wa));
-    float2 r2 = ffma2(T16f<FMT>::unpack(c.z), wb, fmul2(T16f<FMT>::unpack(a.z), wa));
-    float2 r3 = ffma2(T16f<FMT>::unpack(c.w), wb, fmul2(T16f<FMT>::unpack(a.w), wa));
-    plane0[i] = make_float4(r0.x, r0.y, r1.x, r1.y);
-    plane1[i] = make_float4(r2.x, r2.y, r3.x, r3.y);
-  }
-  __syncthreads();
-  uint4* orow = o + (bimg * Ho + ho) * (long long)Wo * cv + chunk * CV8;
-  uint4* orow_relu = RELU2 ? o_relu + (bimg * Ho + ho) * (long long)Wo * cv + chunk * CV8 : nullptr;
-  const int nout = (wo_b - wo_a) * CV8;
-  for (int i = threadIdx.x; i < nout; i += 256) {
-    const int wo = wo_a + i / CV8, v = i % CV8;
+  auto loadcol = [&](int w, float2 (&c)[4]) {
+    const uint4 a = __ldg(row0 + (long long)w * cv);
+    const uint4 b = __ldg(row1 + (long long)w * cv);
+    c[0] = ffma2(T16f<FMT>::unpack(b.x), wb, fmul2(T16f<FMT>::unpack(a.x), wa));
+    c[1] = ffma2(T16f<FMT>::unpack(b.y), wb, fmul2(T16f<FMT>::unpack(a.y), wa));
+    c[2] = ffma2(T16f<FMT>::unpack(b.z), wb, fmul2(T16f<FMT>::unpack(a.z), wa));
+    c[3] = ffma2(T16f<FMT>::unpack(b.w), wb, fmul2(T16f<FMT>::unpack(a.w), wa));
+  };
+  const int wo_a = seg * L;
+  const int wo_b = min(wo_a + L, Wo);
+  uint4* orow = o + (bimg * Ho + ho) * (long long)Wo * cv + v;
+  uint4* orow_relu = RELU2 ? o_relu + (bimg * Ho + ho) * (long long)Wo * cv + v : nullptr;
+  float2 A[4], B[4];
+  int cur0 = -1, cur1 = -1;
+  for (int wo = wo_a; wo < wo_b; ++wo) {
     int w0, w1;
     float lw;
     ac_coords(wo, sw, W, w0, w1, lw);
-    const int i0 = (w0 - w_lo) * CV8 + v, i1 = (w1 - w_lo) * CV8 + v;
-    const float4 a0 = plane0[i0], b0 = plane0[i1], a1 = plane1[i0], b1 = plane1[i1];
+    if (w0 != cur0) {
+      if (w0 == cur1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) A[k] = B[k];
+      } else {
+        loadcol(w0, A);
+      }
+      cur0 = w0;
+    }
+    if (w1 != cur1) {
+      if (w1 == cur0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) B[k] = A[k];
+      } else {
+        loadcol(w1, B);
+      }
+      cur1 = w1;
+    }
     const float2 ua = make_float2(1.0f - lw, 1.0f - lw), ub = make_float2(lw, lw);
-    float2 y0 = ffma2(make_float2(b0.x, b0.y), ub, fmul2(make_float2(a0.x, a0.y), ua));
-    float2 y1 = ffma2(make_float2(b0.z, b0.w), ub, fmul2(make_float2(a0.z, a0.w), ua));
-    float2 y2 = ffma2(make_float2(b1.x, b1.y), ub, fmul2(make_float2(a1.x, a1.y), ua));
-    float2 y3 = ffma2(make_float2(b1.z, b1.w), ub, fmul2(make_float2(a1.z, a1.w), ua));
-    if (relu_out) {
-      y0.x = fmaxf(y0.x, 0.0f); y0.y = fmaxf(y0.y, 0.0f); y1.x = fmaxf(y1.x, 0.0f); y1.y = fmaxf(y1.y, 0.0f);
-      y2.x = fmaxf(y2.x, 0.0f); y2.y = fmaxf(y2.y, 0.0f); y3.x = fmaxf(y3.x, 0.0f); y3.y = fmaxf(y3.y, 0.0f);
+    float2 y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      y[k] = ffma2(B[k], ub, fmul2(A[k], ua));
+      if (relu_out) { y[k].x = fmaxf(y[k].x, 0.0f); y[k].y = fmaxf(y[k].y, 0.0f); }
     }
     uint4 r;
-    r.x = T16f<FMT>::pack(y0.x, y0.y); r.y = T16f<FMT>::pack(y1.x, y1.y); r.z = T16f<FMT>::pack(y2.x, y2.y); r.w = T16f<FMT>::pack(y3.x, y3.y);
-    orow[(long long)wo * cv + v] = r;
+    r.x = T16f<FMT>::pack(y[0].x, y[0].y); r.y = T16f<FMT>::pack(y[1].x, y[1].y);
+    r.z = T16f<FMT>::pack(y[2].x, y[2].y); r.w = T16f<FMT>::pack(y[3].x, y[3].y);
+    orow[(long long)wo * cv] = r;
     if (RELU2) {
       uint4 rr;
-      rr.x = T16f<FMT>::pack(fmaxf(y0.x, 0.0f), fmaxf(y0.y, 0.0f)); rr.y = T16f<FMT>::pack(fmaxf(y1.x, 0.0f), fmaxf(y1.y, 0.0f));
-      rr.z = T16f<FMT>::pack(fmaxf(y2.x, 0.0f), fmaxf(y2.y, 0.0f)); rr.w = T16f<FMT>::pack(fmaxf(y3.x, 0.0f), fmaxf(y3.y, 0.0f));
-      orow_relu[(long long)wo * cv + v] = rr;
+      rr.x = T16f<FMT>::pack(fmaxf(y[0].x, 0.0f), fmaxf(y[0].y, 0.0f)); rr.y = T16f<FMT>::pack(fmaxf(y[1].x, 0.0f), fmaxf(y[1].y, 0.0f));
+      rr.z = T16f<FMT>::pack(fmaxf(y[2].x, 0.0f), fmaxf(y[2].y, 0.0f)); rr.w = T16f<FMT>::pack(fmaxf(y[3].x, 0.0f), fmaxf(y[3].y, 0.0f));
+      orow_relu[(long long)wo * cv] = rr;
     }
   }
 }
@@ -839,43 +782,23 @@ static int launch_bilinear_nhwc(const void* x, void* out, void* out_relu, int B,
   uint4* o = reinterpret_cast<uint4*>(out);
   uint4* orl = reinterpret_cast<uint4*>(out_relu);
   const int fmt = get_operand_format();
-  static const char* env_v1 = getenv("VDN_BILINEAR_V1");
-  const int cv8 = (cv % 8 == 0) ? 8 : (cv % 4 == 0) ? 4 : 0;  // channel chunk of 64 or 32
-  if (cv8 != 0 && env_v1 == nullptr) {
-    // wo tile: at most NIN_MAX source pixels staged per block (fp32, 32 * cv8 bytes each)
-    constexpr int NIN_MAX = 160;
-    const double scale = Wo > 1 ? (double)(W - 1) / (double)(Wo - 1) : 0.0;
-    int tw = scale > 0.0 ? (int)((NIN_MAX - 3) / scale) : Wo;
-    if (tw < 1) tw = 1;
-    if (tw > Wo) tw = Wo;
-    const int ntiles = (Wo + tw - 1) / tw;
-    tw = (Wo + ntiles - 1) / ntiles;
-    const int nchunks = cv / cv8;
-    const size_t smem = (size_t)NIN_MAX * cv8 * 32;
-    dim3 g((unsigned)(ntiles * nchunks), Ho, B);
-#define VDN_BILR(F, R, V) bilinear_rows_kernel<F, R, V><<<g, 256, smem, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, tw, nchunks, relu_out)
-#define VDN_BILR_FR(F, R) do { if (cv8 == 8) VDN_BILR(F, R, 8); else VDN_BILR(F, R, 4); } while (0)
-    if (orl != nullptr) { if (fmt) VDN_BILR_FR(1, 1); else VDN_BILR_FR(0, 1); }
-    else { if (fmt) VDN_BILR_FR(1, 0); else VDN_BILR_FR(0, 0); }
-#undef VDN_BILR_FR
-#undef VDN_BILR
-    count_launch();
-    return check_launch("bilinear_rows_kernel");
-  }
-  const int vpt = (cv % 4 == 0) ? 4 : 1;
-  dim3 g2((Wo * (cv / vpt) + 255) / 256, Ho, B);
-  if (g2.x > 8) g2.x = 8;
-#define VDN_BIL(F, R, V) bilinear_nhwc_kernel<F, R, V><<<g2, 256, 0, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, relu_out)
-  if (orl != nullptr) {
-    if (fmt) { if (vpt == 4) VDN_BIL(1, 1, 4); else VDN_BIL(1, 1, 1); }
-    else { if (vpt == 4) VDN_BIL(0, 1, 4); else VDN_BIL(0, 1, 1); }
-  } else {
-    if (fmt) { if (vpt == 4) VDN_BIL(1, 0, 4); else VDN_BIL(1, 0, 1); }
-    else { if (vpt == 4) VDN_BIL(0, 0, 4); else VDN_BIL(0, 0, 1); }
-  }
-#undef VDN_BIL
+  static const char* env_run = getenv("VDN_BILINEAR_RUN");  // run length override (output pixels per thread)
+  const int want = env_run && atoi(env_run) > 0 ? atoi(env_run) : (cv % 32 == 0 ? 16 : 64);  // measured: short runs win when a warp is one run
+  // the number of runs is rounded so that a row's threads fill whole 128-thread blocks
+  int mult = 1;
+  while ((mult * cv) % 128 != 0 && mult < 8) mult <<= 1;
+  int nseg = (Wo + want - 1) / want;
+  nseg = (nseg + mult - 1) / mult * mult;
+  if (nseg > Wo) nseg = Wo;
+  const int L = (Wo + nseg - 1) / nseg;
+  nseg = (Wo + L - 1) / L;
+  dim3 g((unsigned)((nseg * cv + 127) / 128), Ho, B);
+#define VDN_BILS(F, R) bilinear_slide_kernel<F, R><<<g, 128, 0, stream>>>(xi, o, orl, H, W, Ho, Wo, cv, L, nseg, relu_out)
+  if (orl != nullptr) { if (fmt) VDN_BILS(1, 1); else VDN_BILS(0, 1); }
+  else { if (fmt) VDN_BILS(1, 0); else VDN_BILS(0, 0); }
+#undef VDN_BILS
   count_launch();
-  return check_launch("bilinear_nhwc_kernel");
+  return check_launch("bilinear_slide_kernel");
 }
 
 extern "C" int vdn_bilinear_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, int32_t relu_out,
