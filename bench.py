@@ -323,9 +323,8 @@ def main():
     da2 = None
     if args.da2_batch > 0:
         from video_depth_normal_v2_b200 import DepthAnythingV2
-        from oracle.init_recipe import make_state_dict  # weights only (seeded recipe); the oracle itself is not called here
         m2 = DepthAnythingV2(encoder=ENCODER, features=FEATURES, out_channels=OUT_CHANNELS).to(dev).eval()
-        m2.load_state_dict(make_state_dict("da2", ENCODER, 0))
+        m2.load_state_dict(synthetic_state_dict(m2, 0))
         xb = torch.randn((args.da2_batch, 3, SIZE, SIZE), generator=torch.Generator().manual_seed(7 + rank)).to(dev)
         m2(xb)                      # call 0: empty bank
         barrier()
