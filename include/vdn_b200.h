@@ -131,9 +131,12 @@ int vdn_groupnorm_apply_tc(const void* x, const float* stats, const float* w, co
 int vdn_patch_im2col(const float* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Kp, void* stream);
 /* x[b, 0, :] = cls + pos[0]  for every frame (dinov2.py:219-220) */
 int vdn_write_cls(float* x, const float* cls, const float* pos, int32_t B, int32_t tokens, int32_t C, void* stream);
-/* use_clstoken readout input (dpt.py:129-132, dpt_temporal.py:56-59): normed tokens xn [frames*tokens, C] (row 0 of a frame = cls) ->
-   out [frames*(tokens-1), 2C] = [patch token | that frame's cls token], the operand of readout_projects[i] (Linear 2C->C + GELU) */
-int vdn_readout_concat(const void* xn, void* out, int64_t frames, int32_t tokens, int32_t C, void* stream);
+/* use_clstoken readout input (dpt.py:129-132, dpt_temporal.py:56-59): out [frames*P, 2C] = [patch token | that frame's cls token], the
+   operand of readout_projects[i] (Linear 2C->C + GELU).  Token p of frame f is row f*tok_frame_pitch + p of `tok`, the cls token of
+   frame f row f*cls_frame_pitch of `cls` (rows of C 16-bit elements).  Video models: both point into the normed token matrix
+   [frames*(P+1), C] (tok = row 1, pitches P+1); DepthAnythingV2's last tap takes its tokens from the memory block's output. */
+int vdn_readout_concat(const void* tok, int64_t tok_frame_pitch, const void* cls, int64_t cls_frame_pitch, void* out, int64_t frames, int32_t P,
+                       int32_t C, void* stream);
 /* im2col for the 3x3 stride-2 pad-1 conv (dpt.py:84-89): NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] */
 int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* bilinear resize, align_corners=True, NHWC 16-bit (F.interpolate at util/blocks.py:155-157, dpt_temporal.py:104-106).

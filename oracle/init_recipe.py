@@ -223,6 +223,10 @@ def make_state_dict(model: str, encoder: str, seed: int = 0, use_clstoken: bool 
     elif model == "da2":
         _memory_block(sd, g, "memory_block.", cfg)
         _dpt_head(sd, g, "depth_head.", cfg)
+        if use_clstoken:
+            C = cfg["embed_dim"]
+            for i in range(4):
+                _default_linear(sd, g, f"depth_head.readout_projects.{i}.0", C, 2 * C)
     else:
         raise ValueError(model)
     return sd

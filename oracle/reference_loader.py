@@ -66,14 +66,14 @@ def load_v4(encoder: str, state_dict):
     return m
 
 
-def load_da2(encoder: str, state_dict):
+def load_da2(encoder: str, state_dict, **kw):
     """Reference depth_anything_v2/depth_anything_v2.py:12 DepthAnythingV2 (the fork with the SAM2-style memory block), strict.
     Run it on CPU tensors via forward(): image2tensor / RoPEAttention move data to CUDA when a GPU is visible."""
     from .init_recipe import ENCODERS
     _install_shims()
     from depth_anything_v2.depth_anything_v2 import DepthAnythingV2
     cfg = ENCODERS[encoder]
-    m = DepthAnythingV2(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"]).eval()
+    m = DepthAnythingV2(encoder=encoder, features=cfg["features"], out_channels=cfg["out_channels"], **kw).eval()
     m.load_state_dict(state_dict, strict=True)
     return m
 

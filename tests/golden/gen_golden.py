@@ -40,7 +40,8 @@ V5_CASES = [("v5_vits_s4_60x80", "vits", 4, 60, 80, 3)]
 V4_CASES = [("v4_vits_s4_56x84", "vits", 4, 56, 84, 14)]  # models/video_depth_model_v4.py: network at the native resolution
 # (name, encoder, batch, H(=W), calls, seed, stride): DepthAnythingV2 is stateful -> a sequence of forward() calls on one model
 DA2_CASES = [("da2_vits_b2_70_calls8", "vits", 2, 70, 8, 5, 1), ("da2_vits_b1_518_calls2", "vits", 1, 518, 2, 6, 4), ("da2_vitl_b1_70_calls3", "vitl", 1, 70, 3, 7, 1),
-             ("da2_vitb_b2_70_calls3", "vitb", 2, 70, 3, 17, 1)]
+             ("da2_vitb_b2_70_calls3", "vitb", 2, 70, 3, 17, 1),
+             ("da2_vits_b2_70_calls3_cls", "vits", 2, 70, 3, 19, 1)]  # name ending in _cls: use_clstoken=True
 # (name, encoder, frames, H, W, seed): streaming inference, one infer_video_depth_one call per frame (window slides after frame 10)
 STREAM_CASES = [("stream_vits_n16_56x70", "vits", 16, 56, 70, 8)]
 VIDEO_CASES = [("video_vits_n50_56x70", "vits", 50, 56, 70, 4)]
@@ -67,8 +68,9 @@ def gen_da2(only=None):
     for name, enc, B, H, calls, seed, stride in DA2_CASES:
         if only is not None and only not in name:
             continue
-        sd = make_state_dict("da2", enc, seed)
-        m = RL.load_da2(enc, sd)
+        kw = {"use_clstoken": True} if name.endswith("_cls") else {}
+        sd = make_state_dict("da2", enc, seed, **kw)
+        m = RL.load_da2(enc, sd, **kw)
         outs = [m(x)[:, ::stride, ::stride].numpy() for x in da2_inputs(B, H, calls, seed)]
         m.clear_memory()
         again = m(da2_inputs(B, H, calls, seed)[0])[:, ::stride, ::stride].numpy()  # clear_memory() really resets the state

@@ -179,15 +179,16 @@ def _da2_inputs(B, H, calls, seed):
 
 
 @pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl"),
-                                      ("da2_vitb_b2_70_calls3", "vitb")])
+                                      ("da2_vitb_b2_70_calls3", "vitb"), ("da2_vits_b2_70_calls3_cls", "vits")])
 def test_da2_stateful_forward_matches_reference_golden(vdn, name, enc):
     """A sequence of forward() calls on one model against the live reference's outputs: empty bank (constant cross-attention
     term), filling bank (cross-attention over 1..6 cached entries) and the ring wrap after 6 entries."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     B, H, calls, seed, stride = [int(v) for v in g["meta"]]
     cfg = ENCODERS[enc]
-    m = vdn.DepthAnythingV2(encoder=enc, features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
-    m.load_state_dict(make_state_dict("da2", enc, seed))
+    cls = name.endswith("_cls")  # use_clstoken=True: readout of the last tap after the memory block
+    m = vdn.DepthAnythingV2(encoder=enc, features=cfg["features"], out_channels=cfg["out_channels"], use_clstoken=cls).cuda().eval()
+    m.load_state_dict(make_state_dict("da2", enc, seed, use_clstoken=cls))
     xs = _da2_inputs(B, H, calls, seed)
     for i, x in enumerate(xs):
         y = m(x.cuda())

@@ -90,12 +90,12 @@ def _da2_inputs(B, H, calls, seed):
 
 
 @pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl"),
-                                      ("da2_vitb_b2_70_calls3", "vitb")])
+                                      ("da2_vitb_b2_70_calls3", "vitb"), ("da2_vits_b2_70_calls3_cls", "vits")])
 def test_da2_stateful_forward_matches_reference(name, enc):
     """A sequence of forward() calls on one model (memory bank filling up, then wrapping at 6 entries)."""
     g = _load(name)
     B, H, calls, seed, stride = [int(v) for v in g["meta"]]
-    sd = make_state_dict("da2", enc, seed)
+    sd = make_state_dict("da2", enc, seed, use_clstoken=name.endswith("_cls"))
     bank = []
     for i, x in enumerate(_da2_inputs(B, H, calls, seed)):
         y = O.da2_forward(sd, x, enc, bank)

@@ -68,7 +68,7 @@ SIGNATURES = {
     "vdn_v5_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "vdn_rope2d": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "vdn_rope_chunks": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "vdn_readout_concat": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "vdn_readout_concat": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "vdn_add_rowvec": (c_int, [c_void_p, c_int, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p]),
     "vdn_add_rowscalar": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vdn_dwconv7_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),

@@ -354,17 +354,17 @@ __global__ void write_cls_kernel(float* __restrict__ x, const float* __restrict_
   }
 }
 
-// use_clstoken readout input (dpt.py:129-132 / dpt_temporal.py:56-59): out[f*P + p] = [ xn[f*N + 1 + p] | xn[f*N] ], 16-byte vectors
+// use_clstoken readout input (dpt.py:129-132 / dpt_temporal.py:56-59): out[f*P + p] = [ tok[f*tok_pitch + p] | cls[f*cls_pitch] ], 16-byte vectors
 __global__ void __launch_bounds__(256)
-readout_concat_kernel(const uint4* __restrict__ xn, uint4* __restrict__ out, long long frames, int N, int cv) {
-  const int P = N - 1;
+readout_concat_kernel(const uint4* __restrict__ tok, long long tok_pitch, const uint4* __restrict__ cls, long long cls_pitch, uint4* __restrict__ out,
+                      long long frames, int P, int cv) {
   const long long total = frames * P * 2 * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int c = int(idx % (2 * cv));
     const long long row = idx / (2 * cv);
     const long long f = row / P;
     const int p = int(row - f * P);
-    out[idx] = c < cv ? __ldg(xn + (f * N + 1 + p) * cv + c) : __ldg(xn + f * N * cv + (c - cv));
+    out[idx] = c < cv ? __ldg(tok + (f * tok_pitch + p) * cv + c) : __ldg(cls + f * cls_pitch * cv + (c - cv));
   }
 }
 
@@ -764,12 +764,15 @@ extern "C" int vdn_write_cls(float* x, const float* cls, const float* pos, int32
   return check_launch("write_cls_kernel");
 }
 
-extern "C" int vdn_readout_concat(const void* xn, void* out, int64_t frames, int32_t tokens, int32_t C, void* stream_v) {
+extern "C" int vdn_readout_concat(const void* tok, int64_t tok_frame_pitch, const void* cls, int64_t cls_frame_pitch, void* out, int64_t frames,
+                                  int32_t P, int32_t C, void* stream_v) {
   VDN_STREAM;
-  if (!xn || !out) return set_error("vdn_readout_concat: null pointer");
-  if (C % 8 != 0 || tokens < 2 || frames <= 0) return set_error("vdn_readout_concat: C must be a multiple of 8, tokens >= 2");
-  readout_concat_kernel<<<grid_for(frames * (tokens - 1) * 2 * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(xn), reinterpret_cast<uint4*>(out),
-                                                                                              frames, tokens, C / 8);
+  if (!tok || !cls || !out) return set_error("vdn_readout_concat: null pointer");
+  if (C % 8 != 0 || P < 1 || frames <= 0 || tok_frame_pitch < P || cls_frame_pitch < 1) return set_error("vdn_readout_concat: C must be a multiple of 8, pitches >= extents");
+  if (((reinterpret_cast<uintptr_t>(tok) | reinterpret_cast<uintptr_t>(cls) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return set_error("vdn_readout_concat: 16-byte alignment");
+  readout_concat_kernel<<<grid_for(frames * P * 2 * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(tok), tok_frame_pitch,
+                                                                                    reinterpret_cast<const uint4*>(cls), cls_frame_pitch,
+                                                                                    reinterpret_cast<uint4*>(out), frames, P, C / 8);
   count_launch();
   return check_launch("readout_concat_kernel");
 }

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import ops, packing
-from .models import DA2_ENCODER_CONFIGS as ENCODER_CONFIGS, _PackedModule, _empty, _encoder_shapes, _head_shapes, encoder_forward, head_forward
+from .models import DA2_ENCODER_CONFIGS as ENCODER_CONFIGS, _PackedModule, _empty, _encoder_shapes, _head_shapes, encoder_forward, head_forward, readout_apply
 
 NUM_MEM_ATTENTION_LAYERS = 4  # depth_anything_v2.py:31
 
@@ -133,14 +133,15 @@ class _MemoryState:
 
 
 class DepthAnythingV2(_PackedModule):
-    """Drop-in for depth_anything_v2/depth_anything_v2.py:12 (encoder vits / vitb / vitl; use_bn=False, use_clstoken=False)."""
+    """Drop-in for depth_anything_v2/depth_anything_v2.py:12 (encoder vits / vitb / vitl; use_bn=False)."""
 
     def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False, use_clstoken=False, max_memory_length=6):
         super().__init__()
         if encoder not in ENCODER_CONFIGS:
             raise KeyError(encoder)
-        if use_bn or use_clstoken:
-            raise NotImplementedError("use_bn / use_clstoken are never exercised by the reference (SURVEY.md §8b)")
+        if use_bn:
+            raise NotImplementedError("use_bn is never exercised by the reference (SURVEY.md §8b)")
+        self.use_clstoken = bool(use_clstoken)
         self.encoder, self.max_memory_length = encoder, int(max_memory_length)
         self.cfg = dict(ENCODER_CONFIGS[encoder], features=features, out_channels=list(out_channels))
         self.intermediate_layer_idx = {k: v["taps"] for k, v in ENCODER_CONFIGS.items()}
@@ -149,12 +150,12 @@ class DepthAnythingV2(_PackedModule):
     def _expected_shapes(self):
         s = _encoder_shapes("pretrained.", self.cfg)
         s.update(_memory_block_shapes("memory_block.", self.cfg["embed_dim"], self.max_memory_length))
-        s.update(_head_shapes("depth_head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], False))
+        s.update(_head_shapes("depth_head.", self.cfg["embed_dim"], self.cfg["features"], self.cfg["out_channels"], False, "ape", self.use_clstoken))
         return s
 
     def _pack(self, sd, dev, dt):
         self._mem = None
-        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "depth_head.", self.cfg, dev, dt, False),
+        return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "depth_head.", self.cfg, dev, dt, False, "ape", self.use_clstoken),
                 "mb": pack_memory_block(sd, "memory_block.", self.cfg["embed_dim"], dev, dt)}
 
     def clear_memory(self):
@@ -250,10 +251,19 @@ class DepthAnythingV2(_PackedModule):
         if self._mem is not None and (self._mem.B != B or self._mem.P != P):
             raise RuntimeError("batch size / resolution changed while the memory bank is not empty: call clear_memory() first")
         x = x.to(device=self._dev, dtype=torch.float32)
-        feats = encoder_forward(w["enc"], x)
-        feats[3] = self._memory_attention(w["mb"], feats[3], B, P, side)
+        readout = w["head"].get("readout")
+        feats = encoder_forward(w["enc"], x, readout, defer_last_readout=True)
+        f3m = self._memory_attention(w["mb"], feats[3], B, P, side)
+        if readout is not None:
+            # use_clstoken: the last tap's readout sees the memory block's tokens and the encoder's cls token (depth_anything_v2.py:49-51)
+            C = self.cfg["embed_dim"]
+            f3 = _empty((B * P, C), ops.operand_dtype(), x.device)
+            readout_apply(readout[3], f3m, 0, P, feats[4], P + 1, f3, B, P, C)
+            feats = feats[:3] + [f3]
+        else:
+            feats[3] = f3m
         depth = head_forward(w["head"], feats, B, side, side, None)  # [B, H, W], already through output_conv2's ReLUs
-        self._update_memory(w["mb"], feats[3], depth, B, side)
+        self._update_memory(w["mb"], f3m, depth, B, side)
         return depth
 
     @torch.no_grad()

@@ -83,10 +83,12 @@ class GraphRunner:
 # ======================================================================================================
 # encoder: DINOv2 get_intermediate_layers (dinov2.py:212-231, 271-321; block.py:82-107)
 # ======================================================================================================
-def encoder_forward(enc: dict, x: torch.Tensor, readout: Optional[list] = None) -> List[torch.Tensor]:
+def encoder_forward(enc: dict, x: torch.Tensor, readout: Optional[list] = None, defer_last_readout: bool = False) -> List[torch.Tensor]:
     """x (Bf, 3, H, W) fp32 -> 4 x [Bf*ph*pw, C] 16-bit (final-norm'ed patch tokens of the tapped blocks, cls dropped).
     ``readout`` (use_clstoken=True, dpt.py:129-132): the four packed readout_projects; the per-frame [token | cls] -> Linear -> GELU
-    readout has no cross-frame term, so it runs here and the features keep their shape for every consumer (head, window reuse, streaming)."""
+    readout has no cross-frame term, so it runs here and the features keep their shape for every consumer (head, window reuse, streaming).
+    ``defer_last_readout`` (DepthAnythingV2: the last tap goes through the memory block first, depth_anything_v2.py:49-51): the last
+    feature is returned without its readout and a fifth element is appended, the normed token matrix [Bf*N, C] holding its cls rows."""
     Bf, _, H, W = x.shape
     if H % 14 != 0 or W % 14 != 0:
         raise RuntimeError(f"Input image height {H} / width {W} is not a multiple of patch size 14")  # patch_embed.py:73-74
@@ -119,16 +121,26 @@ def encoder_forward(enc: dict, x: torch.Tensor, readout: Optional[list] = None) 
         ops.gemm(hid, blk["fc2"]["w"], xs, M=rows, N=C, K=4 * C, bias=blk["fc2"]["b"], gamma=blk["ls2"], res=xs)
         if i in enc["taps"]:
             f = _empty((Bf * P, C), od, dev)
-            if readout is None:
+            last_deferred = readout is not None and defer_last_readout and len(feats) == 3
+            if readout is None or last_deferred:
                 ops.layernorm(xs, enc["norm_w"], enc["norm_b"], f, 1e-6, drop_first=True, rows_per_batch=N)
+                if last_deferred:
+                    ops.layernorm(xs, enc["norm_w"], enc["norm_b"], xn, 1e-6)  # the last tap is the last block: xn stays untouched
             else:
                 ops.layernorm(xs, enc["norm_w"], enc["norm_b"], xn, 1e-6)  # xn is free until the next block's ln1
-                cat = _empty((Bf * P, 2 * C), od, dev)
-                ops.readout_concat(xn, cat, Bf, N, C)
-                ro = readout[len(feats)]
-                ops.gemm(cat, ro["w"], f, M=Bf * P, N=C, K=2 * C, bias=ro["b"], act=ops.ACT_GELU)
+                readout_apply(readout[len(feats)], xn, 1, N, xn, N, f, Bf, P, C)
             feats.append(f)
+    if readout is not None and defer_last_readout:
+        feats.append(xn)
     return feats
+
+
+def readout_apply(ro: dict, tok: torch.Tensor, tok_row0: int, tok_pitch: int, cls: torch.Tensor, cls_pitch: int, out: torch.Tensor, Bf: int, P: int, C: int):
+    """readout_projects[i](cat(token, cls)) = GELU(Linear(2C -> C)) (dpt.py:129-132)."""
+    cat = _empty((Bf * P, 2 * C), ops.operand_dtype(), tok.device)
+    ops.readout_concat(tok, tok_row0, tok_pitch, cls, cls_pitch, cat, Bf, P, C)
+    ops.gemm(cat, ro["w"], out, M=Bf * P, N=C, K=2 * C, bias=ro["b"], act=ops.ACT_GELU)
+    return out
 
 
 # ======================================================================================================

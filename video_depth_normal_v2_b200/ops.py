@@ -353,11 +353,13 @@ def rope_chunks(x, rows: int, ld: int, col0: int, chunks: int, cos_sin, P: int):
     return x
 
 
-def readout_concat(xn, out, frames: int, tokens: int, C_: int):
-    """[frames*tokens, C] normed tokens (row 0 = cls) -> [frames*(tokens-1), 2C] = [patch token | cls of its frame]."""
+def readout_concat(tok, tok_row0: int, tok_frame_pitch: int, cls, cls_frame_pitch: int, out, frames: int, P: int, C_: int):
+    """out [frames*P, 2C] = [patch token | cls of its frame]; token p of frame f = row tok_row0 + f*tok_frame_pitch + p of ``tok``
+    ([rows, C]), cls of frame f = row f*cls_frame_pitch of ``cls``."""
     od = operand_dtype()
-    _check(_run("readout_concat", "hbm", 2.0 * frames * (tokens - 1) * 3 * C_, lib().vdn_readout_concat, _ptr(xn, od, "xn"), _ptr(out, od, "out"),
-                frames, tokens, C_, _stream()), "vdn_readout_concat")
+    esz = 2
+    _check(_run("readout_concat", "hbm", 2.0 * frames * P * 3 * C_, lib().vdn_readout_concat, _ptr(tok, od, "tok") + tok_row0 * C_ * esz, tok_frame_pitch,
+                _ptr(cls, od, "cls"), cls_frame_pitch, _ptr(out, od, "out"), frames, P, C_, _stream()), "vdn_readout_concat")
     return out
 
 
