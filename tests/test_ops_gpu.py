@@ -502,3 +502,69 @@ def test_stream_temporal_attn_list_and_ring(ops, D, C, L):
         assert torch.equal(pool[tgt], entries[L - 1])
         before[tgt] = entries[L - 1]
     assert torch.equal(pool, before)
+
+
+# ----------------------------------------------------------------------------------------------- guard bands (compute-sanitizer is closed on this pool)
+def _guarded(shape, dtype, pad=4096):
+    """A tensor of `shape` carved out of a larger buffer with sentinel bytes on both sides; returns (view, check)."""
+    n = 1
+    for d in shape:
+        n *= d
+    esz = torch.empty((), dtype=dtype).element_size()
+    raw = torch.full((2 * pad + n * esz,), 0x5A, dtype=torch.uint8, device="cuda")
+    view = raw[pad:pad + n * esz].view(dtype).view(*shape)
+
+    def check(name):
+        torch.cuda.synchronize()
+        assert bool((raw[:pad] == 0x5A).all()) and bool((raw[pad + n * esz:] == 0x5A).all()), f"{name}: wrote outside its output"
+    return view, check
+
+
+def test_outputs_stay_inside_their_buffers(ops):
+    """Odd extents for every bandwidth-bound kernel touched this round: nothing may be written before or after the output tensor."""
+    od = ops.operand_dtype()
+    # bilinear (ragged last run, channel vectors that do not fill a warp)
+    for (H, W, Ho, Wo, C) in [(7, 9, 13, 31, 24), (19, 19, 37, 37, 256), (5, 300, 9, 518, 128)]:
+        x = _r16(ops, 2, H, W, C, seed=1)
+        out, chk = _guarded((2, Ho, Wo, C), od)
+        ops.bilinear_nhwc(x, out, 2, H, W, Ho, Wo, C)
+        chk("bilinear_nhwc")
+        o1, c1 = _guarded((2, Ho, Wo, C), od)
+        o2, c2 = _guarded((2, Ho, Wo, C), od)
+        ops.bilinear_nhwc2(x, o1, o2, 2, H, W, Ho, Wo, C)
+        c1("bilinear_nhwc2 out"); c2("bilinear_nhwc2 relu")
+    # LayerNorm: odd row counts through the two-rows-per-warp kernel (plain, pe, drop-first) and the generic one
+    for rows, C in [(2049, 1024), (777, 256), (13, 768), (9, 192)]:
+        x, w, b = _f32(rows, C, seed=1), _f32(C, seed=2), _f32(C, seed=3)
+        out, chk = _guarded((rows, C), od)
+        ops.layernorm(x, w, b, out, 1e-6)
+        chk("layernorm")
+        ops.layernorm(x, w, b, out, 1e-6, pe=_f32(5, C, seed=4))
+        chk("layernorm+pe")
+    x, w, b = _f32(3 * 33, 1024, seed=1), _f32(1024, seed=2), _f32(1024, seed=3)
+    out, chk = _guarded((3 * 32, 1024), od)
+    ops.layernorm(x, w, b, out, 1e-6, drop_first=True, rows_per_batch=33)
+    chk("layernorm drop-first")
+    # patch im2col (+ the zeroed padding columns) and the readout concat
+    img = _f32(3, 3, 28, 42, seed=1)
+    out, chk = _guarded((3 * 6, 592), od)
+    ops.patch_im2col(img, out, 3, 28, 42, 592)
+    chk("patch_im2col")
+    xn = _r16(ops, 3 * 7, 64, seed=2)
+    out, chk = _guarded((3 * 6, 128), od)
+    ops.readout_concat(xn, 1, 7, xn, 7, out, 3, 6, 64)
+    chk("readout_concat")
+    ref = torch.cat((xn.view(3, 7, 64)[:, 1:], xn.view(3, 7, 64)[:, :1].expand(3, 6, 64)), -1).reshape(18, 128)
+    assert torch.equal(out, ref)
+    # GroupNorm apply (vectorised path) and the streaming attention output
+    Bv, T, D, C = 1, 3, 11, 256
+    x = _r16(ops, Bv * T, D, C, seed=3)
+    stats = torch.empty(Bv * T * 32 * 2, device="cuda")
+    ops.groupnorm_stats(x, stats, Bv * T, D, C, 32, 1e-6)
+    out, chk = _guarded((Bv * D * T, C), od)
+    ops.groupnorm_apply_tc(x, stats, _f32(C, seed=4), _f32(C, seed=5), out, Bv, T, D, C, 32)
+    chk("groupnorm_apply_tc")
+    entries = [_r16(ops, 9, 3 * 256, seed=20 + j) for j in range(7)]
+    out, chk = _guarded((9, 256), od)
+    ops.stream_temporal_attn(entries, _f32(32, 3 * 256, seed=6), out, 9, 256, 8)
+    chk("stream_temporal_attn")
