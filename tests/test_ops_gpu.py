@@ -568,3 +568,41 @@ def test_outputs_stay_inside_their_buffers(ops):
     out, chk = _guarded((9, 256), od)
     ops.stream_temporal_attn(entries, _f32(32, 3 * 256, seed=6), out, 9, 256, 8)
     chk("stream_temporal_attn")
+
+
+# ----------------------------------------------------------------------------------------------- many M tiles (odd count, ragged last tile)
+@pytest.mark.parametrize("M", [128 * 40 + 17, 128 * 33])
+def test_gemm_many_m_tiles(ops, M):
+    """Wide GEMMs over many M tiles (41 = odd, last one ragged; 33): the plain / GELU / in-place accumulate TMA epilogues and the QKV
+    split.  Also the shapes the 2-CTA cluster variant (VDN_GEMM_CLUSTER=1) is dispatched for."""
+    od = ops.operand_dtype()
+    K, N = 320, 768
+    a, w = _r16(ops, M, K, seed=1), _r16(ops, N, K, scale=K ** -0.5, seed=2)
+    bias, gamma = _f32(N, seed=3), _f32(N, seed=4)
+    ref = a.float() @ w.float().T + bias
+    out = torch.empty(M, N, device="cuda", dtype=od)
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias)
+    torch.cuda.synchronize()
+    _close("gemm plain", out, ref)
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias, act=ops.ACT_GELU)
+    torch.cuda.synchronize()
+    _close("gemm gelu", out, F.gelu(ref))
+    x0 = _f32(M, N, seed=5)
+    x = x0.clone()
+    ops.gemm(a, w, x, M=M, N=N, K=K, bias=bias, gamma=gamma, res=x)
+    torch.cuda.synchronize()
+    _close("gemm in-place accumulate", x, x0 + gamma * ref, rtol=2e-4, atol_frac=2e-5)
+    # QKV split: C = 256 (4 heads), tokens per frame chosen so that frames straddle M tiles
+    C, heads = 256, 4
+    tokens = M // 3
+    Mq = tokens * 3
+    wq, bq = _r16(ops, 3 * C, K, scale=K ** -0.5, seed=6), _f32(3 * C, seed=7)
+    npad = (tokens + 7) // 8 * 8
+    qk = torch.empty(Mq, 2 * C, device="cuda", dtype=od)
+    vT = torch.zeros(3 * heads, 64, npad, device="cuda", dtype=od)
+    ops.gemm(a[:Mq].contiguous(), wq, qk, M=Mq, N=3 * C, K=K, bias=bq, ldc=2 * C, out2=vT, row_map=ops.ROWMAP_QKV_SPLIT, rm=(tokens, npad, C, 0))
+    torch.cuda.synchronize()
+    qkv = a[:Mq].float() @ wq.float().T + bq
+    _close("qkv split q|k", qk, qkv[:, :2 * C])
+    v_ref = qkv[:, 2 * C:].reshape(3, tokens, heads, 64).permute(0, 2, 3, 1).reshape(3 * heads, 64, tokens)
+    _close("qkv split vT", vT[:, :, :tokens], v_ref)

@@ -80,9 +80,9 @@ template <int BLOCK_N, int EPI = EPI_PLAIN, int HALO = 0>
 struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
-  static constexpr int kStageBytes = HALO ? kStageBytesB : kStageBytesA + kStageBytesB;  // HALO: the ring holds B (per-tap) tiles only
+  static constexpr int kStageBytes = HALO == 1 ? kStageBytesB : kStageBytesA + kStageBytesB;  // HALO: the ring holds B (per-tap) tiles only
   static constexpr int kStagingBytes = (EPI == EPI_TMA || EPI == EPI_QKV) ? kNumEpiWarps * kStagingBytesPerWarp : 0;
-  static constexpr int kARingBytes = HALO ? kHaloAStages * kHaloABytes : 0;
+  static constexpr int kARingBytes = HALO == 1 ? kHaloAStages * kHaloABytes : 0;
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kARingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -297,13 +297,16 @@ __device__ __forceinline__ void epi_head(const GemmKParams& p, const RowCtx& rc,
 template <int BLOCK_N, int EPI, int FMT, int HALO = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-               const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmBh, const GemmKParams p) {
+  // HALO == 2: plain GEMM on clusters of two CTAs that work on two M tiles of the same N block in lockstep; each CTA loads half of
+  // the B (weight) tile and multicasts it to both (tmBh: box of BLOCK_N / 2 rows), halving the L2 -> SM traffic of B.
+  constexpr bool CL = HALO == 2;
   using Cfg = GemmCfg<BLOCK_N, EPI, HALO>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (HALO ? Cfg::kARingBytes : kStages * Cfg::kStageBytesA);
+  uint8_t* smem_b = smem + (HALO == 1 ? Cfg::kARingBytes : kStages * Cfg::kStageBytesA);
   constexpr int kRingBytes = Cfg::kARingBytes + kStages * Cfg::kStageBytes;
   uint8_t* smem_stg = smem + kRingBytes;  // EPI_TMA staging (1024-byte aligned: stage sizes are multiples of 1 KB)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes + Cfg::kStagingBytes);
@@ -327,12 +330,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == EPI_TMA || EPI == EPI_QKV) tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL ? 2 : 1);  // cluster: a stage is free once the MMAs of both CTAs have read it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kNumEpiWarps * 32);
-      if constexpr (HALO) {
+      if constexpr (HALO == 1) {
         mbar_init(&a_full[i], 1);
         mbar_init(&a_empty[i], 1);
       }
@@ -342,16 +345,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into it
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // work iteration: whole tiles, or (cluster) pairs of M tiles of one N block, this CTA taking the tile of its rank
+  const int cta_rank = CL ? (int)cluster_ctarank() : 0;
+  const int it0 = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int it_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int it_end = CL ? ((p.num_m_tiles + 1) / 2) * p.num_n_blocks : num_tiles;
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     // Producer and issuer warps run their (warp-uniform) loops with all lanes and elect one lane per issue: under a plain
     // `if (lane == 0)` the compiler cannot prove descriptors / coordinates uniform and wraps every tcgen05.mma and TMA in an
     // R2UR + ELECT + BRA.U.ANY waterfall (~80 cycles per MMA, longer than a 128x64x16 MMA itself).
-    if constexpr (HALO) {
+    if constexpr (HALO == 1) {
       int stage = 0, astage = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -392,9 +401,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_blk = tile % p.num_n_blocks;
-      const int m_tile = tile / p.num_n_blocks;
+    for (int it = it0; it < it_end; it += it_step) {
+      const int n_blk = it % p.num_n_blocks;
+      const int m_tile = CL ? 2 * (it / p.num_n_blocks) + cta_rank : it / p.num_n_blocks;
       int img = 0, h0 = 0, w0 = 0;
       if (p.conv) {
         const int tw_i = m_tile % p.tiles_w;
@@ -416,7 +425,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], k * BLOCK_K, m_tile * BLOCK_M);
           }
-          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], k * BLOCK_K, n_blk * BLOCK_N);
+          if constexpr (CL)
+            tma_load_2d_mc(smem_b + stage * Cfg::kStageBytesB + cta_rank * (Cfg::kStageBytesB / 2), &tmBh, &full_bar[stage], k * BLOCK_K,
+                           n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2), (uint16_t)0b11);
+          else
+            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], k * BLOCK_K, n_blk * BLOCK_N);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -431,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc = make_idesc(FMT ? 1u : 0u, BLOCK_M, BLOCK_N);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
-    if constexpr (HALO) {
+    if constexpr (HALO == 1) {
       int stage = 0, astage = 0;
       uint32_t phase = 0, aphase = 0;
       int local = 0;
@@ -475,7 +488,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int it = it0; it < it_end; it += it_step, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -492,7 +505,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
             umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+          if constexpr (CL) umma_commit_mc(&empty_bar[stage], (uint16_t)0b11);  // ... in both CTAs: the peer's multicast writes here too
+          else umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
           if (k == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -514,11 +528,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c_end = (c_begin + kChunksPerHalf < kChunks) ? c_begin + kChunksPerHalf : kChunks;
     const int row_in_tile = quarter * 32 + lane;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int it = it0; it < it_end; it += it_step, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int n_blk = tile % p.num_n_blocks;
-      const int m_tile = tile / p.num_n_blocks;
+      const int n_blk = it % p.num_n_blocks;
+      const int m_tile = CL ? 2 * (it / p.num_n_blocks) + cta_rank : it / p.num_n_blocks;  // cluster: may be one past the last M tile (all rows invalid)
       // ---- row context ----
       RowCtx rc;
       long long row;
@@ -732,7 +746,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL) cluster_sync_all();  // the peer may still signal this CTA's barriers / fill its stages until it is done, too
+  else __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -743,7 +758,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int EPI, int FMT, int HALO = 0>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p, cudaStream_t stream,
+                       const CUtensorMap* tmBh = nullptr) {
   using Cfg = GemmCfg<BLOCK_N, EPI, HALO>;
   static bool configured = false;
   if (!configured) {
@@ -751,11 +767,42 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
     configured = true;
   }
-  const int num_tiles = p.num_m_tiles * p.num_n_blocks;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N, EPI, FMT, HALO><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
-  count_launch();
-  return check_launch("gemm_tc_kernel");
+  if constexpr (HALO == 2) {
+    // clusters of two CTAs, each pair working through (M-tile pair, N block) items
+    const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_blocks;
+    int clusters = num_sms() / 2;
+    if (pairs < clusters) clusters = pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tc_kernel<BLOCK_N, EPI, FMT, HALO>, &cfg) != cudaSuccess || max_clusters <= 0) {
+        cudaGetLastError();
+        max_clusters = 0;
+      }
+    }
+    if (max_clusters > 0 && clusters > max_clusters) cfg.gridDim = dim3(2 * max_clusters);  // every cluster must be co-resident with its peer only, but keep the grid persistent
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, EPI, FMT, HALO>, tmA, tmB, tmC, *tmBh, p);
+    if (e != cudaSuccess) return set_error(std::string("cudaLaunchKernelEx(gemm cluster): ") + cudaGetErrorString(e));
+    count_launch();
+    return check_launch("gemm_tc_kernel(cluster)");
+  } else {
+    const int num_tiles = p.num_m_tiles * p.num_n_blocks;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    gemm_tc_kernel<BLOCK_N, EPI, FMT, HALO><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmB, p);
+    count_launch();
+    return check_launch("gemm_tc_kernel");
+  }
 }
 
 template <int EPI, int FMT>
@@ -959,6 +1006,20 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     const uint64_t strides[1] = {(uint64_t)d->ldc * es};
     const uint32_t box[2] = {32u, 32u};
     if (make_tensor_map_ex(&tmC, d->out, d->out_f32 ? 2 : fmt, d->out_f32 ? 128 : 64, 2, dims, strides, box)) return 1;
+  }
+  {
+    // 2-CTA clusters with B multicast (VDN_GEMM_CLUSTER=0 disables): plain wide GEMMs with many M tiles.  Measured on the ViT-L block
+    // GEMMs: qkv 234 -> 227 us, fc1 316 -> 308 us, proj / fc2 unchanged; +1 % on the whole step.
+    static const char* env = getenv("VDN_GEMM_CLUSTER");
+    if ((env == nullptr || atoi(env) != 0) && !d->conv && block_n == 256 && (epi == EPI_TMA || epi == EPI_QKV) && p.num_m_tiles >= 32 && d->N % 256 == 0) {
+      CUtensorMap tmBh;
+      const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+      const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
+      const uint32_t box[2] = {(uint32_t)BLOCK_K, 128u};
+      if (make_tensor_map(&tmBh, d->w, fmt, 2, dims, strides, box)) return 1;
+      if (epi == EPI_TMA) return fmt ? launch_gemm<256, EPI_TMA, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_TMA, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
+      return fmt ? launch_gemm<256, EPI_QKV, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_QKV, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
+    }
   }
   if (halo) return fmt ? launch_halo_epi<1>(epi, block_n, tmA, tmB, tmC, p, stream) : launch_halo_epi<0>(epi, block_n, tmA, tmB, tmC, p, stream);
   return fmt ? launch_gemm_epi<1>(epi, block_n, tmA, tmB, tmC, p, stream) : launch_gemm_epi<0>(epi, block_n, tmA, tmB, tmC, p, stream);
