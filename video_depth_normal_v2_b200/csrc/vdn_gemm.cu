@@ -79,7 +79,7 @@ constexpr int kHaloAStages = 2;
 template <int BLOCK_N, int EPI = EPI_PLAIN, int HALO = 0>
 struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytesB = (HALO == 3 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // pair form: each CTA stages half of the B tile
   static constexpr int kStageBytes = HALO == 1 ? kStageBytesB : kStageBytesA + kStageBytesB;  // HALO: the ring holds B (per-tap) tiles only
   static constexpr int kStagingBytes = (EPI == EPI_TMA || EPI == EPI_QKV) ? kNumEpiWarps * kStagingBytesPerWarp : 0;
   static constexpr int kARingBytes = HALO == 1 ? kHaloAStages * kHaloABytes : 0;
@@ -300,7 +300,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmBh, const GemmKParams p) {
   // HALO == 2: plain GEMM on clusters of two CTAs that work on two M tiles of the same N block in lockstep; each CTA loads half of
   // the B (weight) tile and multicasts it to both (tmBh: box of BLOCK_N / 2 rows), halving the L2 -> SM traffic of B.
-  constexpr bool CL = HALO == 2;
+  // HALO == 3: the pair form - ONE tcgen05.mma.cta_group::2 of M = 256 per K step, issued by the leader CTA: each CTA stages its
+  // own A tile and HALF of the B tile (no duplication in shared memory), the peer's loads signal the leader's full barrier, the
+  // leader's commits release the stages and publish the accumulators in both CTAs, both epilogues report to the leader.
+  constexpr bool CL = HALO == 2 || HALO == 3;
+  constexpr bool PAIR = HALO == 3;
   using Cfg = GemmCfg<BLOCK_N, EPI, HALO>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -330,11 +334,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == EPI_TMA || EPI == EPI_QKV) tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL ? 2 : 1);  // cluster: a stage is free once the MMAs of both CTAs have read it
+      mbar_init(&empty_bar[i], (CL && !PAIR) ? 2 : 1);  // cluster: a stage is free once the MMAs of both CTAs have read it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kNumEpiWarps * 32);
+      mbar_init(&tmem_empty_bar[i], (PAIR ? 2 : 1) * kNumEpiWarps * 32);  // pair: the leader hears from both epilogues
       if constexpr (HALO == 1) {
         mbar_init(&a_full[i], 1);
         mbar_init(&a_empty[i], 1);
@@ -342,7 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   } else if (warp_idx == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_alloc_2sm(tmem_ptr_smem, Cfg::kTmemCols);
+    else tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
   }
   tc_fence_before();
   if constexpr (CL) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into it
@@ -415,6 +420,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int k = 0; k < p.num_k_blocks; ++k) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if constexpr (PAIR) {
+          if (elect_one()) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // both CTAs' A tile + B half
+            const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2sm(smem_a + stage * Cfg::kStageBytesA, &tmA, lead_bar, k * BLOCK_K, m_tile * BLOCK_M);
+            tma_load_2d_2sm(smem_b + stage * Cfg::kStageBytesB, &tmBh, lead_bar, k * BLOCK_K, n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2));
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (p.conv) {
@@ -489,6 +508,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int local = 0;
     for (int it = it0; it < it_end; it += it_step, ++local) {
+      if (PAIR && cta_rank != 0) break;  // the leader's MMAs cover both CTAs
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -497,6 +517,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int k = 0; k < p.num_k_blocks; ++k) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if constexpr (PAIR) {
+          if (elect_one()) {
+            constexpr uint32_t idesc2 = make_idesc(FMT ? 1u : 0u, 2 * BLOCK_M, BLOCK_N);
+            const uint64_t da = make_sdesc_sw128(a_addr + stage * Cfg::kStageBytesA);
+            const uint64_t db = make_sdesc_sw128(b_addr + stage * Cfg::kStageBytesB);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / 16; ++kk) umma_f16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc2, (k | kk) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage], (uint16_t)0b11);
+            if (k == p.num_k_blocks - 1) umma_commit_2sm(&tmem_full_bar[acc], (uint16_t)0b11);
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         if (elect_one()) {
           const uint64_t da = make_sdesc_sw128(a_addr + stage * Cfg::kStageBytesA);
           const uint64_t db = make_sdesc_sw128(b_addr + stage * Cfg::kStageBytesB);
@@ -664,7 +701,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty_bar[acc]), 0));
+        else mbar_arrive(&tmem_empty_bar[acc]);
         continue;
       }
       uint32_t accr[32];
@@ -737,7 +775,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c + 1 < c_end) chunk(c + 1, rb1);
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty_bar[acc]), 0));
+      else mbar_arrive(&tmem_empty_bar[acc]);
     }
     if constexpr (EPI == EPI_TMA || EPI == EPI_QKV) {
       if (elect_one()) tma_store_wait_all();  // staging memory and the global writes must outlive the bulk copies
@@ -750,7 +789,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -767,7 +807,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
     configured = true;
   }
-  if constexpr (HALO == 2) {
+  if constexpr (HALO >= 2) {
     // clusters of two CTAs, each pair working through (M-tile pair, N block) items
     const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_blocks;
     int clusters = num_sms() / 2;
@@ -1017,6 +1057,14 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
       const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
       const uint32_t box[2] = {(uint32_t)BLOCK_K, 128u};
       if (make_tensor_map(&tmBh, d->w, fmt, 2, dims, strides, box)) return 1;
+      // pair form (2-SM MMA, half of B per CTA): measured proj 108.6 -> 102.6 us, fc2 302.8 -> 291.5 us, but fc1 (GELU epilogue)
+      // 302 -> 306 us - the two epilogues of a pair gate one accumulator stage.  Default: the in-place fp32 accumulate GEMMs only.
+      // VDN_GEMM_PAIR=0 never, =2 every TMA-epilogue GEMM.
+      static const char* env_pair = getenv("VDN_GEMM_PAIR");
+      const int pair_mode = env_pair ? atoi(env_pair) : 1;
+      const bool accumulate = d->out_f32 && d->res != nullptr;
+      if (epi == EPI_TMA && (pair_mode == 2 || (pair_mode == 1 && accumulate)))
+        return fmt ? launch_gemm<256, EPI_TMA, 1, 3>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_TMA, 0, 3>(tmA, tmB, tmC, p, stream, &tmBh);
       if (epi == EPI_TMA) return fmt ? launch_gemm<256, EPI_TMA, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_TMA, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
       return fmt ? launch_gemm<256, EPI_QKV, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_QKV, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
     }
