@@ -1058,14 +1058,15 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
       const uint32_t box[2] = {(uint32_t)BLOCK_K, 128u};
       if (make_tensor_map(&tmBh, d->w, fmt, 2, dims, strides, box)) return 1;
       // pair form (2-SM MMA, half of B per CTA): measured proj 108.6 -> 102.6 us, fc2 302.8 -> 291.5 us, but fc1 (GELU epilogue)
-      // 302 -> 306 us - the two epilogues of a pair gate one accumulator stage.  Default: the in-place fp32 accumulate GEMMs only.
-      // VDN_GEMM_PAIR=0 never, =2 every TMA-epilogue GEMM.
+      // 302 -> 306 us - the two epilogues of a pair gate one accumulator stage; the QKV split GEMM 225 -> 211 us.  Default: the
+      // in-place fp32 accumulate GEMMs and the QKV split.  VDN_GEMM_PAIR=0 never, =2 also every other TMA-epilogue GEMM.
       static const char* env_pair = getenv("VDN_GEMM_PAIR");
       const int pair_mode = env_pair ? atoi(env_pair) : 1;
       const bool accumulate = d->out_f32 && d->res != nullptr;
       if (epi == EPI_TMA && (pair_mode == 2 || (pair_mode == 1 && accumulate)))
         return fmt ? launch_gemm<256, EPI_TMA, 1, 3>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_TMA, 0, 3>(tmA, tmB, tmC, p, stream, &tmBh);
       if (epi == EPI_TMA) return fmt ? launch_gemm<256, EPI_TMA, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_TMA, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
+      if (pair_mode != 0) return fmt ? launch_gemm<256, EPI_QKV, 1, 3>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_QKV, 0, 3>(tmA, tmB, tmC, p, stream, &tmBh);
       return fmt ? launch_gemm<256, EPI_QKV, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_QKV, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
     }
   }
