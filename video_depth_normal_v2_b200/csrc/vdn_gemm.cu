@@ -424,7 +424,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elect_one()) {
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // both CTAs' A tile + B half
             const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_2sm(smem_a + stage * Cfg::kStageBytesA, &tmA, lead_bar, k * BLOCK_K, m_tile * BLOCK_M);
+            if (p.conv) {  // this CTA's spatial tile, shifted by the tap (OOB rows / columns / images are zero-filled)
+              const int tap = k / p.cin_blocks;
+              const int kc = k - tap * p.cin_blocks;
+              const int r = tap / 3, s_ = tap - r * 3;
+              tma_load_4d_2sm(smem_a + stage * Cfg::kStageBytesA, &tmA, lead_bar, kc * BLOCK_K, w0 + s_ - 1, h0 + r - 1, img);
+            } else {
+              tma_load_2d_2sm(smem_a + stage * Cfg::kStageBytesA, &tmA, lead_bar, k * BLOCK_K, m_tile * BLOCK_M);
+            }
             tma_load_2d_2sm(smem_b + stage * Cfg::kStageBytesB, &tmBh, lead_bar, k * BLOCK_K, n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2));
           }
           __syncwarp();
@@ -580,7 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = t2 / p.tiles_h;
         const int hh = th_i * p.TH + row_in_tile / p.TW;
         const int ww = tw_i * p.TW + row_in_tile % p.TW;
-        rc.valid = (hh < p.H) && (ww < p.W);
+        rc.valid = (hh < p.H) && (ww < p.W) && (m_tile < p.num_m_tiles);  // cluster forms: the odd tile out of the last pair is empty
         row = ((long long)img * p.H + hh) * p.W + ww;
       } else {
         row = (long long)m_tile * BLOCK_M + row_in_tile;
@@ -1048,26 +1055,32 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     if (make_tensor_map_ex(&tmC, d->out, d->out_f32 ? 2 : fmt, d->out_f32 ? 128 : 64, 2, dims, strides, box)) return 1;
   }
   {
-    // 2-CTA clusters with B multicast (VDN_GEMM_CLUSTER=0 disables): plain wide GEMMs with many M tiles.  Measured on the ViT-L block
-    // GEMMs: qkv 234 -> 227 us, fc1 316 -> 308 us, proj / fc2 unchanged; +1 % on the whole step.
+    // 2-CTA clusters (VDN_GEMM_CLUSTER=0 disables): wide GEMMs / 256-wide convolutions with many M tiles.
+    //  - multicast form (HALO == 2): two M = 128 MMAs, each CTA loads half of the weight tile and multicasts it to both.
+    //    qkv 234 -> 227 us, fc1 316 -> 308 us.
+    //  - pair form (HALO == 3): one 2-SM MMA of M = 256, each CTA stages only half of the weight tile.  proj 108.6 -> 102.6 us,
+    //    fc2 302.8 -> 291.5 us, qkv 225 -> 211 us, but fc1 (GELU epilogue) 302 -> 306 us: the two epilogues of a pair gate one
+    //    accumulator stage.  Default: QKV split, in-place fp32 accumulate, 256-wide convolutions.  VDN_GEMM_PAIR=0 never,
+    //    =2 also every other TMA-epilogue GEMM.
     static const char* env = getenv("VDN_GEMM_CLUSTER");
-    if ((env == nullptr || atoi(env) != 0) && !d->conv && block_n == 256 && (epi == EPI_TMA || epi == EPI_QKV) && p.num_m_tiles >= 32 && d->N % 256 == 0) {
+    static const char* env_pair = getenv("VDN_GEMM_PAIR");
+    const int pair_mode = env_pair ? atoi(env_pair) : 1;
+    static const char* env_cp = getenv("VDN_CONV_PAIR");
+    const bool conv_pair = env_cp == nullptr || atoi(env_cp) != 0;
+    const bool wide = (env == nullptr || atoi(env) != 0) && block_n == 256 && p.num_m_tiles >= 32 && d->N % 256 == 0 && !halo;
+    if (wide && ((!d->conv && (epi == EPI_TMA || epi == EPI_QKV)) || (d->conv && pair_mode != 0 && conv_pair && (epi == EPI_PLAIN || epi == EPI_RES)))) {
       CUtensorMap tmBh;
-      const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+      const uint64_t kw = d->conv ? (uint64_t)p.num_k_blocks * BLOCK_K : (uint64_t)d->K;
+      const uint64_t dims[2] = {kw, (uint64_t)d->N};
       const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
       const uint32_t box[2] = {(uint32_t)BLOCK_K, 128u};
       if (make_tensor_map(&tmBh, d->w, fmt, 2, dims, strides, box)) return 1;
-      // pair form (2-SM MMA, half of B per CTA): measured proj 108.6 -> 102.6 us, fc2 302.8 -> 291.5 us, but fc1 (GELU epilogue)
-      // 302 -> 306 us - the two epilogues of a pair gate one accumulator stage; the QKV split GEMM 225 -> 211 us.  Default: the
-      // in-place fp32 accumulate GEMMs and the QKV split.  VDN_GEMM_PAIR=0 never, =2 also every other TMA-epilogue GEMM.
-      static const char* env_pair = getenv("VDN_GEMM_PAIR");
-      const int pair_mode = env_pair ? atoi(env_pair) : 1;
+#define VDN_CL(E, H) (fmt ? launch_gemm<256, E, 1, H>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, E, 0, H>(tmA, tmB, tmC, p, stream, &tmBh))
+      if (d->conv) return epi == EPI_RES ? VDN_CL(EPI_RES, 3) : VDN_CL(EPI_PLAIN, 3);
       const bool accumulate = d->out_f32 && d->res != nullptr;
-      if (epi == EPI_TMA && (pair_mode == 2 || (pair_mode == 1 && accumulate)))
-        return fmt ? launch_gemm<256, EPI_TMA, 1, 3>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_TMA, 0, 3>(tmA, tmB, tmC, p, stream, &tmBh);
-      if (epi == EPI_TMA) return fmt ? launch_gemm<256, EPI_TMA, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_TMA, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
-      if (pair_mode != 0) return fmt ? launch_gemm<256, EPI_QKV, 1, 3>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_QKV, 0, 3>(tmA, tmB, tmC, p, stream, &tmBh);
-      return fmt ? launch_gemm<256, EPI_QKV, 1, 2>(tmA, tmB, tmC, p, stream, &tmBh) : launch_gemm<256, EPI_QKV, 0, 2>(tmA, tmB, tmC, p, stream, &tmBh);
+      if (epi == EPI_TMA) return (pair_mode == 2 || (pair_mode == 1 && accumulate)) ? VDN_CL(EPI_TMA, 3) : VDN_CL(EPI_TMA, 2);
+      return pair_mode != 0 ? VDN_CL(EPI_QKV, 3) : VDN_CL(EPI_QKV, 2);
+#undef VDN_CL
     }
   }
   if (halo) return fmt ? launch_halo_epi<1>(epi, block_n, tmA, tmB, tmC, p, stream) : launch_halo_epi<0>(epi, block_n, tmA, tmB, tmC, p, stream);
