@@ -167,6 +167,16 @@ int vdn_affine_clamp(const float* x, float* out, int64_t n, const float* scale_s
 /* out = pre*(1-w) + max(post*scale+shift,0)*w */
 int vdn_crossfade(const float* pre, const float* post, float* out, int64_t n, const float* scale_shift, float w, void* stream);
 
+/* One launch for every output frame a window owns (video_depth.py:131-152 + utils/util.py:65-74): cur = raw depth [32, n] of window k,
+ * prev_tail = raw depth [8, n] of window k-1's slots 24..31, ss_cur / ss_prev = device (scale, shift) of windows k / k-1 (ss_prev NULL:
+ * the predecessor is window 0, which is never re-scaled).  out [count, n] = slots first_slot .. first_slot+count-1:
+ * slot < 10 -> pre*(1-w_j) + max(cur*s+t, 0)*w_j with pre = max(prev_tail[j]*s'+t', 0), j = slot-2, w = (0, 1/7, .., 6/7, 1);
+ * slot >= 10 -> max(cur*s+t, 0).  is_first (window 0): plain copy. */
+int vdn_window_finalize(const float* cur, const float* prev_tail, const float* ss_cur, const float* ss_prev, float* out, int64_t n,
+                        int32_t first_slot, int32_t count, int32_t is_first, void* stream);
+/* keys [3, n] = slots (0, 1, 12) of cur [32, n]: what the sequential scale/shift chain needs from a window (video_depth.py:121-129,148-152) */
+int vdn_window_keys(const float* cur, float* keys, int64_t n, void* stream);
+
 /* ---- depth -> normals (utils/normal_utils.py:4-52): reflect-pad Sobel/8, n = normalize(-Ix,-Iy,1) ------- */
 int vdn_sobel_normals(const float* depth, float* normals, int32_t N, int32_t H, int32_t W, int32_t channels_out, void* stream);
 

@@ -1,9 +1,10 @@
-"""TEST INFRASTRUCTURE — import the live reference (build container only).
+"""TEST INFRASTRUCTURE — import the reference's own modules.
 
-``/root/reference`` exists only in the build container; the GPU box never has it, so nothing under
-``tests -m gpu``, ``smoke()`` or ``bench.py`` may call this.  It is used by ``tests/golden/gen_golden.py``
-to produce the committed fixtures and by the ``not gpu`` tests that re-check the oracle against the
-live reference when it is present (they skip otherwise).  SURVEY.md Appendix A.
+``/root/reference`` exists only in the build container; there it is used by ``tests/golden/gen_golden.py`` to produce the
+committed fixtures and by the ``not gpu`` tests that re-check the oracle against the live reference (they skip otherwise).
+On the GPU box the only copy is ``oracle/_ref`` (unmodified files placed there by ``oracle/vendor_ref.py``, git-ignored), and
+the only caller is the CPU arm of ``bench.py`` (``oracle/cpu_arm.py``, a subprocess without a visible GPU): nothing under
+``tests -m gpu`` or ``smoke()`` reads either location.  SURVEY.md Appendix A.
 """
 from __future__ import annotations
 
@@ -11,7 +12,8 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VDN_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("VDN_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/video_depth_anything") else _VENDORED)
 
 
 def available() -> bool:

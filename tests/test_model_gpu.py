@@ -108,6 +108,52 @@ def test_full_size_vitl_window_matches_oracle_on_gpu(vdn):
     _check("vitl 8x518x518", y, ref)
 
 
+def test_timed_shape_vitl_32x518_matches_oracle_on_gpu(vdn):
+    """The exact shape bench.py times (ViT-L, one window of 32 frames at 518x518): the pair-form GEMMs at M = 43840 and the tcgen05
+    temporal-attention kernel (T == 32), end to end against the fp32 oracle on the same GPU; then the same window through the
+    captured CUDA graph (third call = replay) must reproduce the eager result bit for bit."""
+    enc, T, H, W = "vitl", 32, 518, 518
+    m, sd = _model(vdn, enc, 17)
+    x = make_input("rgb", (1, T, 3, H, W), 17).cuda()
+    y = m(x).clone()
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    ref = O.vda_forward(sd_gpu, x, enc)
+    torch.cuda.synchronize()
+    _check("vitl 32x518x518 (timed shape)", y, ref)
+    del ref, sd_gpu
+    torch.cuda.empty_cache()
+    y2 = m(x).clone()
+    y3 = m(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2) and torch.equal(y, y3)
+
+
+def test_long_video_pipeline_vitl_518_matches_window_forward(vdn):
+    """The long-video path bench.py times (raw uint8 frames -> device pre-processing -> encoder-feature reuse -> head -> fused
+    alignment kernel -> pinned host result) on ViT-L 518x518, 3 windows: against the same clip with every window forwarded in
+    full (no feature reuse) and aligned by the oracle's restatement of the reference loop."""
+    from video_depth_normal_v2_b200 import video as V
+    enc, n, S = "vitl", 60, 518
+    m, sd = _model(vdn, enc, 19)
+    rng = np.random.RandomState(5)
+    base = rng.randint(0, 255, (8, S, S, 3), dtype=np.uint8)
+    frames = np.stack([np.roll(base[i % 8], 3 * i, axis=1) for i in range(n)])
+    st = {}
+    out, _ = m.infer_video_depth(frames, 30, input_size=S, device="cuda", stats=st)
+    assert out.shape == (n, S, S) and st["encoded_frames"] == n and st["windows"] == 3
+    wins = V.window_schedule(n)
+    x = torch.empty((n, 3, S, S), dtype=torch.float32, device="cuda")
+    vdn.ops.preprocess_u8(torch.from_numpy(frames).cuda(), x, S, S)
+    depth_list = []
+    for w in wins:
+        d = m(x[torch.tensor(w, device="cuda")].unsqueeze(0))[0]
+        depth_list += [f.cpu().numpy() for f in d]
+    exp = O.align_windows(depth_list, n)
+    err = np.abs(out - exp).max() / max(1.0, np.abs(exp).max())
+    print(f"long-video pipeline vs per-window forward + reference alignment: max err / max {err:.3e}")
+    assert err < 1e-5
+
+
 def test_determinism_and_batch_independence(vdn):
     """Size-independent properties: repeated runs are bit-identical; frames of different clips in a batch do not interact."""
     m, sd = _model(vdn, "vits", 8)
@@ -212,6 +258,24 @@ def test_da2_batch16_vitl_518_matches_oracle(vdn):
         y = m(x.cuda())
         ref = O.da2_forward(sd_gpu, x.cuda(), enc, bank)
         _check(f"da2 vitl 2x518 call {i}", y, ref)
+
+
+def test_da2_timed_shape_batch16_vitl_518_matches_oracle(vdn):
+    """BASELINE configs[1] at its stated size: DepthAnythingV2 ViT-L, 518x518, batch 16, three stateful calls (empty bank, one and
+    two entries) against the fp32 oracle on the same GPU."""
+    enc = "vitl"
+    cfg = ENCODERS[enc]
+    sd = make_state_dict("da2", enc, 13)
+    m = vdn.DepthAnythingV2(encoder=enc, features=cfg["features"], out_channels=cfg["out_channels"]).cuda().eval()
+    m.load_state_dict(sd)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    bank = []
+    for i, x in enumerate(_da2_inputs(3, 518, 16, 13)):
+        y = m(x.cuda()).clone()
+        ref = O.da2_forward(sd_gpu, x.cuda(), enc, bank)
+        _check(f"da2 vitl 16x518 call {i}", y, ref)
+        del ref
+        torch.cuda.empty_cache()
 
 
 def test_da2_infer_image_shape_and_state(vdn):

@@ -145,6 +145,28 @@ def test_conv3x3_depth_head(ops, Ci):
     _close("conv3x3 head", out, ref, rtol=1e-4, atol_frac=1e-5)
 
 
+def test_output_conv2_stage_at_518(ops):
+    """Stage-wise check of the head's last stage at the BASELINE size (dpt_temporal.py:108-111: the reference forces this stage to
+    fp32): bilinear 296 -> 518 of a 128-channel map, 3x3 128 -> 32 + ReLU + 1x1 32 -> 1 + ReLU, against fp32 PyTorch on the same
+    16-bit-rounded operands."""
+    od = ops.operand_dtype()
+    B, Hi, Ho, Ci = 2, 296, 518, 128
+    x = (_r16(ops, B, Hi, Hi, Ci, seed=1).float().abs() * 0.5).to(od)
+    w = _f32(32, Ci, 3, 3, scale=(9 * Ci) ** -0.5, seed=2).to(od)
+    bias, hw = _f32(32, seed=3) * 0.1, _f32(32, seed=4).abs()
+    up = torch.empty(B, Ho, Ho, Ci, device="cuda", dtype=od)
+    ops.bilinear_nhwc(x, up, B, Hi, Hi, Ho, Ho, Ci)
+    out = torch.empty(B, Ho, Ho, device="cuda", dtype=torch.float32)
+    ops.gemm(up, _pack_conv3x3(w.float(), od), out, M=B * Ho * Ho, N=32, K=Ci, conv=(B, Ho, Ho), bias=bias, head_w=hw, head_b=0.05)
+    ref_up = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Ho), mode="bilinear", align_corners=True)
+    mid = F.relu(F.conv2d(ref_up, w.float(), bias, padding=1))
+    ref = F.relu((mid * hw.view(1, 32, 1, 1)).sum(1) + 0.05)
+    torch.cuda.synchronize()
+    rel = ((out - ref).abs() / ref.clamp_min(1e-3 * float(ref.max()))).max()
+    print(f"output_conv2 stage at 518: max-rel {float(rel):.3e}")
+    assert float(rel) < 2e-3
+
+
 @pytest.mark.parametrize("s,Co", [(4, 48), (2, 96), (4, 256)])
 def test_gemm_pixel_shuffle_convtranspose(ops, s, Co):
     od = ops.operand_dtype()
@@ -400,6 +422,29 @@ def test_alignment_kernels(ops):
     torch.cuda.synchronize()
     assert torch.allclose(out, (p * -0.7 + 0.4).clamp_min(0), atol=1e-6)
     assert torch.allclose(out2, t * (1 - 3.0 / 7.0) + (p * -0.7 + 0.4).clamp_min(0) * (3.0 / 7.0), atol=1e-6)
+
+
+@pytest.mark.parametrize("H,W", [(70, 84), (45, 67)])  # 45*67 is odd: the scalar (non-float4) form
+def test_window_finalize_matches_the_reference_alignment_loop(ops, H, W):
+    """vdn_window_finalize / vdn_window_keys (one launch per window) against the oracle's restatement of video_depth.py:118-154:
+    three windows pushed through video.WindowAligner vs oracle.align_windows on the same per-window depth maps."""
+    from oracle import vdn_oracle as O
+    from video_depth_normal_v2_b200 import video as V
+    n = 60
+    wins = V.window_schedule(n)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    ds = [(torch.rand(32, H, W, device="cuda", generator=g) * (1.0 + 0.3 * k) - 0.1 * k).contiguous() for k in range(len(wins))]
+    al = V.WindowAligner(len(wins), H, W, torch.device("cuda"), n_frames=n)
+    for d in ds:
+        al.push(d)
+    got = al.result(n).cpu().numpy()
+    exp = O.align_windows([m for d in ds for m in d.cpu().numpy()], n)
+    assert np.abs(got - exp).max() < 1e-5 * max(1.0, np.abs(exp).max()), float(np.abs(got - exp).max())
+    keys = torch.empty(3, H, W, device="cuda")
+    ops.window_keys(ds[1], keys)
+    assert torch.equal(keys, torch.stack([ds[1][0], ds[1][1], ds[1][12]]))
+    with pytest.raises(RuntimeError, match="cross-fade"):
+        ops.window_finalize(ds[1], None, torch.ones(2, device="cuda"), None, torch.empty(4, H, W, device="cuda"), 2, 4, False)
 
 
 def test_sobel_normals(ops):

@@ -62,6 +62,8 @@ SIGNATURES = {
     "vdn_lsq_solve": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vdn_affine_clamp": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "vdn_crossfade": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p]),
+    "vdn_window_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "vdn_window_keys": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vdn_sobel_normals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vdn_frame_median_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_float, c_void_p]),
     "vdn_v5_net_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),

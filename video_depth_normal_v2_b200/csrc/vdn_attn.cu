@@ -634,7 +634,8 @@ __global__ void __launch_bounds__(256) stream_temporal_attn_vec_kernel(const Str
 template <int DH>
 static int launch_stream_vec(const StreamAttnParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)(64 * DH + 8 * 32) * sizeof(float);
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured && smem > 48 * 1024) {
     cudaFuncSetAttribute(stream_temporal_attn_vec_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(stream_temporal_attn_vec_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -890,7 +891,8 @@ static int launch_temporal_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVT, 
   constexpr int CU = DH < 64 ? 64 : DH;
   constexpr int STAGE = 2 * (CU / 64) * 16384 + 2 * CU * 128;
   constexpr int SMEM = 2 * STAGE + 256;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};  // function attributes are per device
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(temporal_attn_tc_kernel<DH, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(temporal_attn_tc): ") + cudaGetErrorString(e));
@@ -939,7 +941,8 @@ extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_st
     const uint32_t box[3] = {64, (uint32_t)FA_D, 1};
     if (make_tensor_map(&tmVT, vT, fmt, 3, dims, strides, box)) return 1;
   }
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};  // function attributes are per device
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);

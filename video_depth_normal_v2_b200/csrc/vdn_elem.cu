@@ -609,6 +609,55 @@ crossfade_kernel(const float* __restrict__ pre, const float* __restrict__ post, 
   }
 }
 
+// One launch finalises the output frames a window owns (video_depth.py:131-152, utils/util.py:65-74): slots 2..9 of window
+// k >= 1 are cross-faded with the previous window's aligned slots 24..31, every later slot is scale * d + shift clamped at 0;
+// window 0 is copied as it is.  (scale, shift) pairs are read from device memory: no host round trip.  VEC = floats per access.
+template <int VEC>
+struct FVec { float v[VEC]; };
+template <> struct __align__(16) FVec<4> { float v[4]; };
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+window_finalize_kernel(const float* __restrict__ cur, const float* __restrict__ prev_tail, const float* __restrict__ ss_cur,
+                       const float* __restrict__ ss_prev, float* __restrict__ out, long long nv, int first_slot, int count, int is_first) {
+  typedef FVec<VEC> V;
+  float sc = 1.0f, sh = 0.0f, psc = 1.0f, psh = 0.0f;
+  if (!is_first) { sc = ss_cur[0]; sh = ss_cur[1]; }
+  const bool prev_affine = ss_prev != nullptr;
+  if (prev_affine) { psc = ss_prev[0]; psh = ss_prev[1]; }
+  const long long total = nv * count;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int fr = int(idx / nv);
+    const long long px = idx - (long long)fr * nv;
+    const int slot = first_slot + fr;
+    V o = reinterpret_cast<const V*>(cur)[(long long)slot * nv + px];
+    if (!is_first) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o.v[i] = fmaxf(o.v[i] * sc + sh, 0.0f);
+      if (slot < 10) {  // OVERLAP: slots ALIGN_LEN .. OVERLAP-1 blend with the predecessor's last INTERP_LEN frames
+        const int j = slot - 2;
+        const float w = j == 0 ? 0.0f : (j == 7 ? 1.0f : (float)(j * (1.0 / 7.0)));
+        V p = reinterpret_cast<const V*>(prev_tail)[(long long)j * nv + px];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float pv = prev_affine ? fmaxf(p.v[i] * psc + psh, 0.0f) : p.v[i];
+          o.v[i] = pv * (1.0f - w) + o.v[i] * w;
+        }
+      }
+    }
+    reinterpret_cast<V*>(out)[idx] = o;
+  }
+}
+
+// the three key-frame depth maps the scale/shift chain needs from every window (slots 0, 1, 12): [3, n]
+__global__ void __launch_bounds__(256) window_keys_kernel(const float* __restrict__ cur, float* __restrict__ keys, long long n) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 3 * n; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = int(idx / n);
+    const long long px = idx - (long long)j * n;
+    keys[idx] = cur[(long long)(j == 2 ? 12 : j) * n + px];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Sobel normals (reflect padding, kernel / 8): n = normalize(-Ix, -Iy, 1)
 // ------------------------------------------------------------------------------------------------
@@ -881,6 +930,32 @@ extern "C" int vdn_affine_clamp(const float* x, float* out, int64_t n, const flo
   affine_clamp_kernel<<<grid_for(n, 256 * 4), 256, 0, stream>>>(x, out, n, scale_shift);
   count_launch();
   return check_launch("affine_clamp_kernel");
+}
+
+extern "C" int vdn_window_finalize(const float* cur, const float* prev_tail, const float* ss_cur, const float* ss_prev, float* out, int64_t n,
+                                   int first_slot, int count, int is_first, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!cur || !out) return set_error("vdn_window_finalize: null pointer");
+  if (n <= 0) return set_error("vdn_window_finalize: empty frame");
+  if (first_slot < 0 || count < 0 || first_slot + count > 32) return set_error("vdn_window_finalize: slots out of range");
+  if (!is_first && (!ss_cur || (first_slot < 10 && (!prev_tail || first_slot < 2)))) return set_error("vdn_window_finalize: missing operand for the cross-fade");
+  if (count == 0) return 0;
+  const bool vec = n % 4 == 0 && (reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(prev_tail)) % 16 == 0;
+  if (vec)
+    window_finalize_kernel<4><<<grid_for(n / 4 * count, 256 * 2), 256, 0, stream>>>(cur, prev_tail, ss_cur, ss_prev, out, n / 4, first_slot, count, is_first);
+  else
+    window_finalize_kernel<1><<<grid_for(n * count, 256 * 4), 256, 0, stream>>>(cur, prev_tail, ss_cur, ss_prev, out, n, first_slot, count, is_first);
+  count_launch();
+  return check_launch("window_finalize_kernel");
+}
+
+extern "C" int vdn_window_keys(const float* cur, float* keys, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!cur || !keys) return set_error("vdn_window_keys: null pointer");
+  if (n <= 0) return set_error("vdn_window_keys: empty frame");
+  window_keys_kernel<<<grid_for(3 * n, 256 * 4), 256, 0, stream>>>(cur, keys, n);
+  count_launch();
+  return check_launch("window_keys_kernel");
 }
 
 extern "C" int vdn_crossfade(const float* pre, const float* post, float* out, int64_t n, const float* scale_shift, float w, void* stream_v) {

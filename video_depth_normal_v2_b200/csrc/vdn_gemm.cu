@@ -804,11 +804,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static bool no_tma_epi_env() {
+  static const bool v = getenv("VDN_NO_TMA_EPI") != nullptr;  // read once per process, like the other switches
+  return v;
+}
+
 template <int BLOCK_N, int EPI, int FMT, int HALO = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKParams& p, cudaStream_t stream,
                        const CUtensorMap* tmBh = nullptr) {
   using Cfg = GemmCfg<BLOCK_N, EPI, HALO>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};  // function attributes are per device
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, EPI, FMT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
@@ -1039,7 +1045,7 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
     if (make_tensor_map(&tmB, d->w, fmt, 2, dims, strides, box)) return 1;
   }
   CUtensorMap tmC = tmB;  // placeholder unless the TMA epilogue is used
-  if (epi == EPI_QKV && p.qkv_tpo == d->rm0 && p.qkv_toff == 0 && (d->ldc * 2) % 16 == 0 && p.qkv_split % 32 == 0 && getenv("VDN_NO_TMA_EPI") == nullptr) {
+  if (epi == EPI_QKV && p.qkv_tpo == d->rm0 && p.qkv_toff == 0 && (d->ldc * 2) % 16 == 0 && p.qkv_split % 32 == 0 && !no_tma_epi_env()) {
     // q|k rows land at their own row index: one 32 x 32 box per warp chunk
     const uint64_t dims[2] = {(uint64_t)p.qkv_split, (uint64_t)d->M};
     const uint64_t strides[1] = {(uint64_t)d->ldc * 2};

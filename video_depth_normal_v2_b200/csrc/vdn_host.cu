@@ -21,15 +21,21 @@ int check_launch(const char* what) {
   if (e != cudaSuccess) return set_error(std::string(what) + ": " + cudaGetErrorString(e));
   return 0;
 }
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];  // zero-initialised; one process may drive several GPUs
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int get_operand_format() { return g_fmt.load(); }

@@ -9,7 +9,9 @@
 namespace vdn {
 int set_error(const std::string& msg);  // records msg, returns 1
 int check_launch(const char* what);     // cudaGetLastError() -> 0 / set_error
-int num_sms();
+constexpr int kMaxDevices = 64;
+int current_device();                    // cudaGetDevice(), clamped to [0, kMaxDevices)
+int num_sms();                           // of the current device
 void count_launch();
 int get_operand_format();
 // Encode a tiled, 128B-swizzled tensor map for a 16-bit tensor. dims/box innermost first; strides (bytes) for dims 1..rank-1.

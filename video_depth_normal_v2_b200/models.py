@@ -55,17 +55,24 @@ class GraphRunner:
     def clear(self):
         self.entries.clear()
 
-    def run(self, key, fn, inputs):
+    def run(self, key, fn, inputs, static_inputs: bool = False):
+        """``static_inputs``: the caller passes the same persistent tensors on every call (their addresses are baked into the graph),
+        so nothing is copied; otherwise the inputs are copied into graph-owned buffers before every replay."""
         if not GraphRunner.enabled or ops._profiler is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
+        if static_inputs:
+            key = key + tuple(t.data_ptr() for t in inputs)
         e = self.entries.get(key)
         if e is None:
             self.entries[key] = {"calls": 1}
             return fn(*inputs)
         if "graph" not in e:
-            static_in = [torch.empty_like(t) for t in inputs]
-            for s_, t in zip(static_in, inputs):
-                s_.copy_(t, non_blocking=True)
+            if static_inputs:
+                static_in = list(inputs)
+            else:
+                static_in = [torch.empty_like(t) for t in inputs]
+                for s_, t in zip(static_in, inputs):
+                    s_.copy_(t, non_blocking=True)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
@@ -73,8 +80,9 @@ class GraphRunner:
                 out = fn(*static_in)
             e.update(graph=g, inputs=static_in, out=out, launches=ops.launch_count() - n0)
             ops.lib().vdn_add_launch_count(-e["launches"])  # capture issued no work; every replay (below) counts them
-        for s_, t in zip(e["inputs"], inputs):
-            s_.copy_(t, non_blocking=True)
+        if not static_inputs:
+            for s_, t in zip(e["inputs"], inputs):
+                s_.copy_(t, non_blocking=True)
         e["graph"].replay()
         ops.lib().vdn_add_launch_count(e["launches"])
         return e["out"]
@@ -543,12 +551,15 @@ class VideoDepthAnything(_PackedModule):
         return [f.clone() for f in feats] if clone else list(feats)  # the long-video driver keeps per-frame views of these across windows
 
     @torch.no_grad()
-    def head_from_features(self, feats: List[torch.Tensor], T: int, ph: int, pw: int) -> torch.Tensor:
-        """4 x [T*ph*pw, C] -> depth (T, 14*ph, 14*pw) fp32 (one video, T <= 32 frames)."""
+    def head_from_features(self, feats: List[torch.Tensor], T: int, ph: int, pw: int, static_inputs: bool = False, clone: bool = True) -> torch.Tensor:
+        """4 x [T*ph*pw, C] -> depth (T, 14*ph, 14*pw) fp32 (one video, T <= 32 frames).  ``static_inputs``: ``feats`` are persistent
+        buffers handed over on every call (the long-video driver's window buffers): the captured graph reads them in place."""
         w = self._weights()
         if T > 32:
             raise RuntimeError("temporal attention supports at most 32 frames per window")
-        return self._graphs.run(("head", T, ph, pw), lambda *f: head_forward(w["head"], list(f), T, ph, pw, T), [f.contiguous() for f in feats]).clone()
+        feats = [f.contiguous() for f in feats]
+        d = self._graphs.run(("head", T, ph, pw), lambda *f: head_forward(w["head"], list(f), T, ph, pw, T), feats, static_inputs=static_inputs)
+        return d.clone() if clone else d
 
     # ------------------------------------------------------------------------------------------------
     # streaming: drop-in for video_depth_anything/video_depth_stream.py:76-160 (same class name there; one model serves both here)

@@ -311,6 +311,22 @@ def crossfade(pre, post, out, scale_shift, w: float):
     return out
 
 
+def window_finalize(cur, prev_tail, ss_cur, ss_prev, out, first_slot: int, count: int, is_first: bool):
+    """out [count, H, W] = the aligned / cross-faded output frames of slots first_slot.. of one window (see vdn_window_finalize)."""
+    n = cur[0].numel()
+    _check(_run("window_finalize", "hbm", 8.0 * n * count + 4.0 * n * max(0, min(10, first_slot + count) - first_slot), lib().vdn_window_finalize,
+                _ptr(cur, torch.float32, "cur"), _ptr(prev_tail, torch.float32, "prev_tail"), _ptr(ss_cur, torch.float32, "ss_cur"),
+                _ptr(ss_prev, torch.float32, "ss_prev"), _ptr(out, torch.float32, "out"), n, first_slot, count, 1 if is_first else 0, _stream()),
+           "vdn_window_finalize")
+    return out
+
+
+def window_keys(cur, keys):
+    """keys [3, H, W] = slots (0, 1, 12) of cur [32, H, W]."""
+    _check(lib().vdn_window_keys(_ptr(cur, torch.float32, "cur"), _ptr(keys, torch.float32, "keys"), cur[0].numel(), _stream()), "vdn_window_keys")
+    return keys
+
+
 def sobel_normals(depth, normals, N, H, W, channels_out=3):
     _check(lib().vdn_sobel_normals(_ptr(depth, torch.float32, "depth"), _ptr(normals, torch.float32, "normals"), N, H, W, channels_out, _stream()),
            "vdn_sobel_normals")

@@ -2,20 +2,28 @@
 
 Same semantics as the reference — 32-slot windows every 22 frames, first 10 slots overwritten with the previous window's
 input key frames, per-window forward, least-squares scale/shift alignment on key frames, 8-frame linear cross-fade —
-re-organised for the GPU:
-  * every source frame is pre-processed once (the reference transforms each frame up to 32/22 times, identically);
-  * the encoder is per-frame, so the features of the 10 key frames a window shares with its predecessor are reused: a
-    steady-state window runs the ViT on 22 new frames and the temporal head on all 32 slots (``reuse_features``);
-  * the window schedule is unrolled up front (the forward of window k depends only on raw frames), so windows
-    are independent units that shard across ranks in contiguous blocks.  NCCL is used for exactly three
-    things: the 9 overlap key-frame feature sets at each rank boundary, the three key-frame depth maps per window that the
-    (sequential) scale/shift chain needs, and the gather of the output shards;
-  * resize-to-frame-size, the scale/shift solve, affine alignment, clamp and cross-fade are device kernels on
-    device-resident depth maps (the reference does them in numpy after a per-frame ``.cpu()``): no host round trip per
-    window, one D2H copy of the final result.
+re-organised for the GPU as a three-stream pipeline:
+
+  copy-in stream   raw uint8 frames of window k+1, host -> device (one async copy per contiguous run of frames)
+  compute stream   cubic resize + normalise (vdn_preprocess_u8) -> ViT on the frames the window does not share with its
+                   predecessor (the encoder is per-frame, so a steady-state window encodes 22 frames, not 32) -> temporal
+                   head on all 32 slots -> resize to the frame size -> scale/shift fit -> ONE kernel that writes every
+                   output frame the window owns (affine + clamp + cross-fade, vdn_window_finalize)
+  copy-out stream  the frames window k finalised, device -> pinned host result, while window k+1 computes
+
+Windows are independent units (the forward of window k depends only on raw frames): ``shard=True`` / ``group=``
+partitions them over the ranks of a ``torch.distributed`` group in contiguous blocks.  NCCL is used for
+exactly three things: the 9 overlap key-frame feature sets at each rank boundary, the three key-frame depth maps per window
+that the (sequential) scale/shift chain needs, and the previous rank's last 8 raw depth maps for the boundary cross-fade.
+Every rank copies the frames it owns to its own host memory (``gather='shard'``); ``'rank0'`` / ``'all'`` assemble the one
+array the reference returns, through a shared host segment when the ranks share a node, else through NCCL.
+Sharding is opt-in: a plain drop-in call never communicates (the reference's never does).
 """
 from __future__ import annotations
 
+import mmap
+import os
+import zlib
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -67,6 +75,14 @@ def owned_output_range(k: int, n_windows: int, n_out: int) -> Tuple[int, int]:
     return min(lo, n_out), min(hi, n_out)
 
 
+def rank_output_range(bounds: Sequence[Tuple[int, int]], rank: int, n_windows: int, n_out: int) -> Tuple[int, int]:
+    """Output frames owned by the windows of one rank (empty for a rank without windows)."""
+    k0, k1 = bounds[rank]
+    if k1 <= k0:
+        return 0, 0
+    return owned_output_range(k0, n_windows, n_out)[0], owned_output_range(k1 - 1, n_windows, n_out)[1]
+
+
 def _target_size(width: int, height: int, input_size: int) -> Tuple[int, int]:
     """util/transform.py:56-105 with keep_aspect_ratio=True, ensure_multiple_of=14, resize_method='lower_bound'."""
     scale_h, scale_w = input_size / height, input_size / width
@@ -85,8 +101,8 @@ def _target_size(width: int, height: int, input_size: int) -> Tuple[int, int]:
 
 def preprocess_frames(frames: np.ndarray, input_size: int, indices: Optional[Sequence[int]] = None, pinned: bool = False):
     """uint8 RGB (N, H, W, 3) -> float32 (N, 3, h, w): /255, cubic resize to a multiple of 14, ImageNet normalise
-    (video_depth.py:74-86,98-99; util/transform.py).  Host-side, like the reference (boundary).
-    ``indices``: only these frames are transformed (a rank's shard), into consecutive rows of the result, in the given order.
+    (video_depth.py:74-86,98-99; util/transform.py).  The reference's host-side transform, kept for ``device_preprocess=False``.
+    ``indices``: only these frames are transformed, into consecutive rows of the result, in the given order.
     ``pinned``: write into page-locked memory and return a torch tensor (so that the per-window H2D copies are asynchronous)."""
     import cv2
     n, fh, fw = frames.shape[:3]
@@ -118,7 +134,7 @@ CROSSFADE_W = [0.0] + [i * (1.0 / (INTERP_LEN - 1)) for i in range(1, INTERP_LEN
 
 
 class DeviceAlignOps:
-    """The four alignment primitives on device tensors, through the C ABI (no host synchronisation)."""
+    """The alignment primitives on device tensors, through the C ABI (no host synchronisation)."""
 
     def scale_shift(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         sums = torch.empty(5, dtype=torch.float64, device=pred.device)
@@ -132,9 +148,14 @@ class DeviceAlignOps:
         ops.affine_clamp(x.contiguous(), out, ss)
         return out
 
-    def crossfade(self, pre: torch.Tensor, post: torch.Tensor, ss: torch.Tensor, w: float, out: torch.Tensor) -> torch.Tensor:
-        ops.crossfade(pre.contiguous(), post.contiguous(), out, ss, w)
-        return out
+    def keys(self, d: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """out [3, H, W] = slots (0, 1, 12) of a window's raw depth d [32, H, W]."""
+        return ops.window_keys(d, out)
+
+    def finalize(self, d: torch.Tensor, prev_tail: Optional[torch.Tensor], ss: Optional[torch.Tensor], ss_prev: Optional[torch.Tensor],
+                 out: torch.Tensor, first_slot: int, is_first: bool) -> torch.Tensor:
+        """out [count, H, W] = output frames of slots first_slot.. of one window: cross-fade (slots 2..9) / affine + clamp."""
+        return ops.window_finalize(d, prev_tail, ss, ss_prev, out, first_slot, out.shape[0], is_first)
 
 
 def scale_shift_chain(keys: torch.Tensor, aops) -> torch.Tensor:
@@ -151,118 +172,272 @@ def scale_shift_chain(keys: torch.Tensor, aops) -> torch.Tensor:
     return table
 
 
-class WindowAligner:
-    """Sequential affine alignment + cross-fade of window outputs on the device (video_depth.py:118-154)."""
+class HostSink:
+    """Device -> host copies of finalised output frames on their own stream, into one page-locked result.  The pinned block
+    comes from torch's caching host allocator: when the caller drops the returned array the block is reused by the next call."""
 
-    def __init__(self, n_windows: int, H: int, W: int, device, aops=None):
-        self.H, self.W = H, W
-        n_out = INFER_LEN + STEP * (n_windows - 1)
-        self.aligned = torch.empty((n_out, H, W), dtype=torch.float32, device=device)
-        self.pos = 0
+    def __init__(self, n_rows: int, H: int, W: int, device, host: Optional[torch.Tensor] = None):
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        if host is not None:
+            self.host = host
+        else:
+            self.host = torch.empty((n_rows, H, W), dtype=torch.float32, pin_memory=self.cuda)
+        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.bytes = 0
+
+    def push(self, rows: torch.Tensor, row0: int):
+        if rows.shape[0] == 0:
+            return
+        dst = self.host[row0:row0 + rows.shape[0]]
+        self.bytes += rows.numel() * 4
+        if not self.cuda:
+            dst.copy_(rows)
+            return
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            dst.copy_(rows, non_blocking=True)
+
+    def finish(self) -> torch.Tensor:
+        if self.cuda:
+            self.stream.synchronize()
+        return self.host
+
+
+class WindowAligner:
+    """Sequential affine alignment + cross-fade of window outputs on the device (video_depth.py:118-154), streaming: window k's
+    owned output frames are final as soon as window k has been pushed (its scale/shift needs only windows < k)."""
+
+    def __init__(self, n_windows: int, H: int, W: int, device, aops=None, n_frames: Optional[int] = None, sink: Optional[HostSink] = None):
+        self.K, self.H, self.W = n_windows, H, W
+        self.n_out = INFER_LEN + STEP * (n_windows - 1) if n_frames is None else n_frames
+        self.aligned = torch.empty((self.n_out, H, W), dtype=torch.float32, device=device)
+        self.k = 0
         self.ref = None
+        self.prev = None      # raw depth of the previous window (its slots 24..31 are the cross-fade operands)
+        self.ss_prev = None   # None while the previous window is window 0 (never re-scaled)
         self.aops = aops or DeviceAlignOps()
+        self.sink = sink
 
     def push(self, d: torch.Tensor):
         """d: [32, H, W] fp32 device tensor of one window (already resized to the output size)."""
-        if self.pos == 0:
-            self.aligned[:INFER_LEN].copy_(d)
-            self.pos = INFER_LEN
-            self.ref = torch.stack([d[k] for k in KF_ALIGN]).contiguous()
-            return
-        ss = self.aops.scale_shift(d[:ALIGN_LEN], self.ref)
-        for i in range(INTERP_LEN):
-            tgt = self.aligned[self.pos - INTERP_LEN + i]
-            self.aops.crossfade(tgt, d[ALIGN_LEN + i], ss, CROSSFADE_W[i], out=tgt)
-        self.aops.affine_clamp(d[OVERLAP:], ss, out=self.aligned[self.pos:self.pos + STEP])
-        self.pos += STEP
-        self.aops.affine_clamp(d[KF_ALIGN[1]], ss, out=self.ref[1])
+        k = self.k
+        ss = None
+        if k == 0:
+            self.ref = torch.stack([d[j] for j in KF_ALIGN]).contiguous()
+        else:
+            ss = self.aops.scale_shift(d[:ALIGN_LEN], self.ref)
+            self.aops.affine_clamp(d[KF_ALIGN[1]], ss, out=self.ref[1])
+        lo, hi = owned_output_range(k, self.K, self.n_out)
+        if hi > lo:
+            out = self.aligned[lo:hi]
+            tail = self.prev[INFER_LEN - INTERP_LEN:] if k > 0 else None
+            self.aops.finalize(d, tail, ss, self.ss_prev, out, lo - STEP * k, k == 0)
+            if self.sink is not None:
+                self.sink.push(out, lo)
+        self.prev, self.ss_prev = d, ss
+        self.k += 1
 
     def result(self, n_frames: int) -> torch.Tensor:
         return self.aligned[:n_frames]
 
 
-class WindowForwarder:
-    """Forwards windows (lists of source-frame indices into ``frames_t``: (N, 3, h, w) fp32 host tensor) through the model
-    and resizes to ``out_hw``.  With ``reuse`` the encoder features of frames shared with the previous window are kept."""
+class FrameSource:
+    """The clip as the caller handed it over — raw uint8 RGB (N, H, W, 3) or pre-processed fp32 (N, 3, h, w); numpy or torch;
+    pageable, page-locked or already on the device — and the upload of selected frames on a copy stream.  Nothing is copied
+    on the host: a page-locked array is read by the DMA engine directly, a pageable one goes through the driver's staging."""
 
-    def __init__(self, model, frames_t: torch.Tensor, out_hw: Tuple[int, int], device, reuse: bool = True,
-                 frame_rows: Optional[Dict[int, int]] = None, net_hw: Optional[Tuple[int, int]] = None):
-        """``frame_rows``: source-frame index -> row of ``frames_t`` when only a rank's shard of the clip is resident.
-        ``frames_t`` is either pre-processed fp32 (N, 3, h, w) or raw uint8 RGB (N, H, W, 3) with ``net_hw`` = (h, w): raw frames are
-        uploaded as bytes and resized / normalised on the device (``vdn_preprocess_u8``), 4x less H2D traffic and no host cv2 loop."""
-        self.model, self.frames_t, self.out_hw, self.device = model, frames_t, out_hw, device
+    def __init__(self, frames, device, frame_rows: Optional[Dict[int, int]] = None):
+        if isinstance(frames, torch.Tensor):
+            t = frames
+        else:
+            a = np.asarray(frames)
+            if not a.flags["C_CONTIGUOUS"]:
+                a = np.ascontiguousarray(a)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")  # a read-only array is fine: the frames are only read
+                t = torch.from_numpy(a)
+        if t.dtype not in (torch.uint8, torch.float32):
+            raise RuntimeError(f"frames must be uint8 (raw RGB) or float32 (pre-processed), got {t.dtype}")
+        self.t = t
+        self.raw = t.dtype == torch.uint8
+        self.device = torch.device(device)
         self.frame_rows = frame_rows
-        self.raw = frames_t.dtype == torch.uint8
-        self.net_hw = tuple(net_hw) if net_hw is not None else tuple(frames_t.shape[-2:])
+        self.resident = t.is_cuda
+        self.stream = torch.cuda.Stream(device=self.device) if (self.device.type == "cuda" and not self.resident) else None
+        self.h2d_bytes = 0
+
+    def upload(self, idx: Sequence[int]) -> Tuple[torch.Tensor, Optional["torch.cuda.Event"]]:
+        """-> (device tensor of the listed frames in order, event to wait for before reading it)."""
+        rows = [self.frame_rows[f] for f in idx] if self.frame_rows is not None else list(idx)
+        if self.resident:
+            if rows and rows == list(range(rows[0], rows[0] + len(rows))):
+                return self.t[rows[0]:rows[0] + len(rows)], None
+            return self.t[torch.tensor(rows, device=self.t.device)], None
+        x = torch.empty((len(rows),) + tuple(self.t.shape[1:]), dtype=self.t.dtype, device=self.device)
+        self.h2d_bytes += x.numel() * x.element_size()
+
+        def copy_runs():
+            pos = 0
+            while pos < len(rows):
+                run = 1
+                while pos + run < len(rows) and rows[pos + run] == rows[pos] + run:
+                    run += 1
+                x[pos:pos + run].copy_(self.t[rows[pos]:rows[pos] + run], non_blocking=True)
+                pos += run
+
+        if self.stream is None:
+            copy_runs()
+            return x, None
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)  # x's memory may have been in use by earlier work on the compute stream
+        with torch.cuda.stream(self.stream):
+            copy_runs()
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        x.record_stream(self.stream)
+        return x, ev
+
+
+class WindowForwarder:
+    """Forwards windows (lists of source-frame indices) through the model and resizes to ``out_hw``.  With ``reuse`` the tapped
+    encoder features of one window live in slot order in persistent buffers (the static inputs of the captured head graph): a new
+    window moves the rows of the frames it shares with its predecessor (slots 0, 12, 24..31 -> 0..9), encodes the rest and writes
+    them into their slots — three device copies per tap and window in the steady state."""
+
+    def __init__(self, model, frames, out_hw: Tuple[int, int], device, reuse: bool = True,
+                 frame_rows: Optional[Dict[int, int]] = None, net_hw: Optional[Tuple[int, int]] = None):
+        """``frames``: anything FrameSource takes.  Raw uint8 frames need ``net_hw`` = (h, w), the network input size: they are
+        uploaded as bytes and resized / normalised on the device (``vdn_preprocess_u8``), 4x less H2D traffic and no host cv2 loop.
+        ``frame_rows``: source-frame index -> row of ``frames`` when only a rank's shard of the clip was handed over."""
+        self.model, self.out_hw, self.device = model, out_hw, torch.device(device)
+        self.src = frames if isinstance(frames, FrameSource) else FrameSource(frames, device, frame_rows)
+        self.raw = self.src.raw
+        self.net_hw = tuple(net_hw) if net_hw is not None else tuple(self.src.t.shape[-2:])
         self.reuse = reuse and hasattr(model, "encode_frames")
-        self.cache: Dict[int, List[torch.Tensor]] = {}
+        self.win_feats: Optional[List[torch.Tensor]] = None  # per tap [32*P, C], slot order of ``self.prev_win``
+        self.prev_win: Optional[List[int]] = None
+        self.seeded: Dict[int, List[torch.Tensor]] = {}      # frame -> per tap [P, C] features computed on another rank
         self.encoded_frames = 0  # bookkeeping: encoder work actually done (frames)
+        self._pending = None     # (window, upload) issued ahead of its forward
 
-    def _load(self, idx: Sequence[int]) -> torch.Tensor:
-        """Host -> device copy of the listed frames, one (asynchronous, if ``frames_t`` is pinned) copy per contiguous run."""
-        idx = [self.frame_rows[f] for f in idx] if self.frame_rows is not None else list(idx)
-        x = torch.empty((len(idx),) + tuple(self.frames_t.shape[1:]), dtype=self.frames_t.dtype, device=self.device)
-        pos = 0
-        while pos < len(idx):
-            run = 1
-            while pos + run < len(idx) and idx[pos + run] == idx[pos] + run:
-                run += 1
-            x[pos:pos + run].copy_(self.frames_t[idx[pos]:idx[pos] + run], non_blocking=True)
-            pos += run
+    # ---- host -> device ------------------------------------------------------------------------------------------------
+    def _need(self, win: Sequence[int]) -> List[int]:
+        if not self.reuse:
+            return list(win)
+        have = set(self.prev_win or ()) | set(self.seeded)
+        return [f for f in dict.fromkeys(win) if f not in have]
+
+    def prefetch(self, win: Sequence[int], arriving: Sequence[int] = ()):
+        """Start the upload of the frames ``win`` will need — called right after the kernels of the window before it were queued, so
+        the copy overlaps them.  ``arriving``: frames whose features another rank is about to deliver (not uploaded)."""
+        skip = set(arriving)
+        need = [f for f in self._need(win) if f not in skip]
+        self._pending = (list(win), need, self.src.upload(need) if need else (None, None))
+
+    def _load(self, win: Sequence[int]) -> Tuple[List[int], Optional[torch.Tensor]]:
+        need = self._need(win)
+        if self._pending is not None and self._pending[0] == list(win) and self._pending[1] == need:
+            x, ev = self._pending[2]
+        else:
+            x, ev = self.src.upload(need) if need else (None, None)
+        self._pending = None
+        if x is None:
+            return need, None
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            x.record_stream(torch.cuda.current_stream(self.device))
         if self.raw:
-            out = torch.empty((len(idx), 3) + self.net_hw, dtype=torch.float32, device=self.device)
+            out = torch.empty((len(need), 3) + self.net_hw, dtype=torch.float32, device=self.device)
             ops.preprocess_u8(x, out, self.net_hw[0], self.net_hw[1])
-            return out
-        return x
+            return need, out
+        return need, x
 
-    def seed(self, feats: Dict[int, List[torch.Tensor]]):
+    # ---- rank-boundary feature exchange (collective (1) of sharded_video_depth) -------------------------------------------
+    def export_features(self, frames: Sequence[int]) -> List[torch.Tensor]:
+        """Packed copies [len(frames)*P, C] per tap of frames of the last forwarded window (what a rank boundary ships)."""
+        slots = [self.prev_win.index(f) for f in frames]
+        out = []
+        for t in range(4):
+            P = self.win_feats[t].shape[0] // INFER_LEN
+            v = self.win_feats[t].view(INFER_LEN, P, -1)
+            out.append(torch.cat([v[s] for s in slots]).contiguous() if slots != list(range(slots[0], slots[0] + len(slots)))
+                       else v[slots[0]:slots[0] + len(slots)].reshape(len(slots) * P, -1).clone())
+        return out
+
+    def feature_buffers(self, n_frames: int) -> List[torch.Tensor]:
+        """Empty receive buffers shaped like ``export_features`` of n_frames frames."""
+        return [torch.empty((n_frames * (t.shape[0] // INFER_LEN), t.shape[1]), dtype=t.dtype, device=t.device) for t in self.win_feats]
+
+    def import_features(self, frames: Sequence[int], packed: List[torch.Tensor]):
         """Adopt features computed elsewhere (the next rank's copy of this rank's last key frames)."""
-        self.cache.update(feats)
+        P = [t.shape[0] // len(frames) for t in packed]
+        for j, f in enumerate(frames):
+            self.seeded[f] = [packed[t][j * P[t]:(j + 1) * P[t]] for t in range(4)]
 
-    def features_of(self, frames: Sequence[int]) -> List[torch.Tensor]:
-        """Packed [len(frames)*P, C] per tap for cached frames (what a rank boundary ships)."""
-        return [torch.cat([self.cache[f][t] for f in frames]).contiguous() for t in range(4)]
-
+    # ---- one window ---------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, win: Sequence[int]) -> torch.Tensor:
+        win = list(win)
         h, w = self.net_hw
         H, W = self.out_hw
         if not self.reuse:
-            d = self.model.forward(self._load(win).unsqueeze(0))[0]
+            _, x = self._load(win)
+            d = self.model.forward(x.unsqueeze(0))[0]
             self.encoded_frames += len(win)
         else:
-            need = [f for f in dict.fromkeys(win) if f not in self.cache]
-            if need:
-                new = self.model.encode_frames(self._load(need))
-                P = new[0].shape[0] // len(need)
-                for i, f in enumerate(need):
-                    self.cache[f] = [t[i * P:(i + 1) * P] for t in new]
-                self.encoded_frames += len(need)
-            feats = []
+            need, x = self._load(win)
+            new = self.model.encode_frames(x, clone=False) if need else None
+            self.encoded_frames += len(need)
+            if self.win_feats is None:
+                P = [t.shape[0] // len(need) for t in new]
+                self.win_feats = [torch.empty((INFER_LEN * P[t], new[t].shape[1]), dtype=new[t].dtype, device=new[t].device) for t in range(4)]
+            prev_slot = {f: s for s, f in reversed(list(enumerate(self.prev_win)))} if self.prev_win is not None else {}
+            new_row = {f: i for i, f in enumerate(need)}
+            # (kind, source index) of every slot; slots that already hold their frame are skipped; consecutive slots coalesce
+            moves = []
+            for s, f in enumerate(win):
+                if f in prev_slot:
+                    if prev_slot[f] != s:
+                        moves.append(("prev", prev_slot[f], s))
+                elif f in new_row:
+                    moves.append(("new", new_row[f], s))
+                else:
+                    moves.append(("seed", f, s))
+            # in-place moves inside the window buffers are safe when no move reads a slot that an earlier move wrote
+            written, hazard = set(), False
+            for kind, src, dst in moves:
+                if kind == "prev" and src in written:
+                    hazard = True
+                written.add(dst)
             for t in range(4):
-                P, C = self.cache[win[0]][t].shape
-                buf = torch.empty((len(win) * P, C), dtype=self.cache[win[0]][t].dtype, device=self.cache[win[0]][t].device)
-                for s, f in enumerate(win):
-                    buf[s * P:(s + 1) * P].copy_(self.cache[f][t])  # device memcpy into slot order
-                feats.append(buf)
-            d = self.model.head_from_features(feats, len(win), h // 14, w // 14)
-            keep = set(win)
-            self.cache = {f: v for f, v in self.cache.items() if f in keep}
+                buf = self.win_feats[t]
+                P = buf.shape[0] // INFER_LEN
+                old = buf.clone() if hazard else buf
+                i = 0
+                while i < len(moves):
+                    kind, src, dst = moves[i]
+                    run = 1
+                    while (kind != "seed" and i + run < len(moves) and moves[i + run][0] == kind and moves[i + run][1] == src + run
+                           and moves[i + run][2] == dst + run):
+                        run += 1
+                    if kind == "prev":
+                        buf[dst * P:(dst + run) * P].copy_(old[src * P:(src + run) * P])
+                    elif kind == "new":
+                        buf[dst * P:(dst + run) * P].copy_(new[t][src * P:(src + run) * P])
+                    else:
+                        buf[dst * P:(dst + 1) * P].copy_(self.seeded[src][t])
+                    i += run
+            self.prev_win = win
+            self.seeded = {}
+            # the head graph's output buffer is overwritten by the next window: keep a copy unless the resize below makes one anyway
+            d = self.model.head_from_features(self.win_feats, len(win), h // 14, w // 14, static_inputs=True, clone=(H, W) == (h, w))
         if (H, W) != (h, w):
             r = torch.empty((d.shape[0], H, W), dtype=torch.float32, device=d.device)
             ops.bilinear_f32(d.contiguous(), r, d.shape[0], h, w, H, W)
             d = r
         return d
-
-
-def _pinned_raw(frames: np.ndarray, indices: Optional[Sequence[int]]) -> torch.Tensor:
-    """The (selected) raw uint8 frames in page-locked memory, rows in the given order."""
-    sel = list(range(frames.shape[0])) if indices is None else list(indices)
-    t = torch.empty((len(sel),) + tuple(frames.shape[1:]), dtype=torch.uint8, pin_memory=True)
-    dst = t.numpy()
-    for row, i in enumerate(sel):
-        dst[row] = frames[i]
-    return t
 
 
 def _resolve_input_size(fh: int, fw: int, input_size: int) -> int:
@@ -273,22 +448,42 @@ def _resolve_input_size(fh: int, fw: int, input_size: int) -> int:
     return input_size
 
 
+class FrameShard(np.ndarray):
+    """The output frames one rank owns (``gather='shard'``): a float32 (hi-lo, H, W) array with ``frame_range = (lo, hi)``."""
+    frame_range: Tuple[int, int] = (0, 0)
+
+
+def _frames_fingerprint(frames, n: int) -> int:
+    """Cheap content check that every rank of a sharded call was handed the same clip: CRC of three frames."""
+    crc = 0
+    for i in sorted({0, n // 2, n - 1}):
+        f = frames[i]
+        f = f.cpu().numpy() if isinstance(f, torch.Tensor) else np.asarray(f)
+        crc = zlib.crc32(np.ascontiguousarray(f).view(np.uint8).reshape(-1), crc)
+    return crc
+
+
 @torch.no_grad()
 def infer_video_depth(model, frames, target_fps, input_size=518, device="cuda", fp32=False, preprocessed: Optional[torch.Tensor] = None,
-                      reuse_features: bool = True, group=None, gather: str = "all", device_preprocess: bool = True):
+                      reuse_features: bool = True, group=None, shard: Optional[bool] = None, gather: str = "all", device_preprocess: bool = True,
+                      output: str = "numpy", stats: Optional[dict] = None):
     """video_depth.py:67-156.  ``fp32`` is accepted for signature compatibility: this path always accumulates in fp32 and its
     16-bit operands meet the fp32-reference tolerance.  Returns (np.float32 (N, H, W), target_fps).
 
+    ``frames``: uint8 RGB (N, H, W, 3), numpy or torch, pageable, page-locked or already on the device.
     ``device_preprocess``: upload the raw uint8 frames and run the cubic resize + normalisation on the GPU (default); False keeps the
-    reference's host-side cv2 transform.
+    reference's host-side cv2 transform.  ``preprocessed``: already transformed fp32 (N, 3, h, w) frames (skips both).
 
-    When ``torch.distributed`` is initialised with more than one rank (or ``group`` is given) the windows are sharded across
-    the ranks; every rank must call with the same ``frames``.  ``gather='all'`` returns the full result on every rank,
-    ``'rank0'`` only on rank 0 (None elsewhere)."""
+    Sharding over ``torch.distributed`` is opt-in (``shard=True`` for the default group, or ``group=``): every rank of the group must
+    call with the same clip (checked).  ``gather='all'`` returns the full result on every rank, ``'rank0'`` only on rank 0 (None
+    elsewhere), ``'shard'`` the frames the rank owns as a ``FrameShard`` (no gather at all).  Without ``shard`` / ``group`` the
+    call never communicates, whatever process groups exist.  ``output='device'`` leaves the result on the GPU (a torch tensor; with
+    ``shard`` only ``gather='shard'``).  ``stats`` (optional dict) receives bookkeeping of the call."""
     if str(device).split(":")[0] != "cuda":
         raise RuntimeError("infer_video_depth runs on CUDA only (no CPU fallback)")
     import torch.distributed as dist
-    frames = np.asarray(frames)
+    if not isinstance(frames, torch.Tensor):
+        frames = np.asarray(frames)
     n = frames.shape[0]
     fh, fw = frames.shape[1:3]
     input_size = _resolve_input_size(fh, fw, input_size)
@@ -296,46 +491,145 @@ def infer_video_depth(model, frames, target_fps, input_size=518, device="cuda", 
     if model._dev.type != "cuda":
         model.to(model_dev)
     windows = window_schedule(n)
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    if world > 1:
-        rank = dist.get_rank(group)
-        k0, k1 = partition_windows(len(windows), world)[rank]
-        frame_rows, net_hw = None, None
-        if preprocessed is None:  # only this rank's frames are kept resident (raw bytes, or transformed on the host)
-            mine = sorted({f for win in windows[k0:k1] for f in win})
-            frame_rows = {f: i for i, f in enumerate(mine)}
-            if device_preprocess:
-                preprocessed, net_hw = _pinned_raw(frames, mine), _target_size(fw, fh, input_size)[::-1]
-            else:
-                preprocessed = preprocess_frames(frames, input_size, indices=mine, pinned=True)
-        fwd = WindowForwarder(model, preprocessed, (fh, fw), model_dev, reuse=reuse_features, frame_rows=frame_rows, net_hw=net_hw)
-        out = sharded_video_depth(fwd.forward, windows, n, (fh, fw), model_dev, DeviceAlignOps(), group=group, gather=gather,
-                                  forwarder=fwd if fwd.reuse else None)
-        return (out.cpu().numpy() if out is not None else None), target_fps
+    sharded = bool(shard) or group is not None
+    if sharded and not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("shard=True needs an initialised torch.distributed process group")
+    if gather not in ("all", "rank0", "shard"):
+        raise ValueError(f"gather must be 'all', 'rank0' or 'shard', got {gather!r}")
+    if output not in ("numpy", "device"):
+        raise ValueError(f"output must be 'numpy' or 'device', got {output!r}")
     net_hw = None
     if preprocessed is not None:
-        ft = preprocessed
+        source = preprocessed
     elif device_preprocess:
-        ft, net_hw = _pinned_raw(frames, None), _target_size(fw, fh, input_size)[::-1]
+        source, net_hw = frames, _target_size(fw, fh, input_size)[::-1]
     else:
-        ft = preprocess_frames(frames, input_size, pinned=True)
-    fwd = WindowForwarder(model, ft, (fh, fw), model_dev, reuse=reuse_features, net_hw=net_hw)
-    aligner = WindowAligner(len(windows), fh, fw, model_dev)
-    for win in windows:
-        aligner.push(fwd.forward(win))
-    return aligner.result(n).cpu().numpy(), target_fps
+        source = None  # host transform below, only for the frames this rank needs
+    with torch.cuda.device(model_dev):
+        if sharded and dist.get_world_size(group) > 1:
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            sig = torch.tensor([n, fh, fw, input_size, _frames_fingerprint(frames, n)], dtype=torch.int64, device=model_dev)
+            sigs = torch.empty((world, 5), dtype=torch.int64, device=model_dev)
+            dist.all_gather_into_tensor(sigs, sig, group=group)
+            if not bool((sigs == sig).all()):
+                raise RuntimeError("sharded infer_video_depth: the ranks of the group were handed different clips "
+                                   f"(n, H, W, input_size, crc per rank: {sigs.tolist()}); pass shard=False for independent per-rank videos")
+            k0, k1 = partition_windows(len(windows), world)[rank]
+            frame_rows = None
+            if source is None:
+                mine = sorted({f for win in windows[k0:k1] for f in win})
+                frame_rows = {f: i for i, f in enumerate(mine)}
+                source = preprocess_frames(frames, input_size, indices=mine, pinned=True)
+            fwd = WindowForwarder(model, source, (fh, fw), model_dev, reuse=reuse_features, frame_rows=frame_rows, net_hw=net_hw)
+            out = sharded_video_depth(fwd.forward, windows, n, (fh, fw), model_dev, DeviceAlignOps(), group=group, gather=gather,
+                                      forwarder=fwd if fwd.reuse else None, to_host=output == "numpy", stats=stats)
+            if stats is not None:
+                stats.update(encoded_frames=fwd.encoded_frames, h2d_bytes=fwd.src.h2d_bytes)
+            return out, target_fps
+        if source is None:
+            source = preprocess_frames(frames, input_size, pinned=True)
+        fwd = WindowForwarder(model, source, (fh, fw), model_dev, reuse=reuse_features, net_hw=net_hw)
+        sink = HostSink(n, fh, fw, model_dev) if output == "numpy" else None
+        aligner = WindowAligner(len(windows), fh, fw, model_dev, n_frames=n, sink=sink)
+        fwd.prefetch(windows[0])
+        for k, win in enumerate(windows):
+            d = fwd.forward(win)
+            if k + 1 < len(windows):
+                fwd.prefetch(windows[k + 1])  # H2D of the next window's frames while this one computes
+            aligner.push(d)
+        if stats is not None:
+            stats.update(encoded_frames=fwd.encoded_frames, h2d_bytes=fwd.src.h2d_bytes, d2h_bytes=sink.bytes if sink is not None else 0, windows=len(windows))
+        if sink is None:
+            return aligner.result(n), target_fps
+        out = sink.finish().numpy()
+        if sharded and gather == "shard":
+            out = out.view(FrameShard)
+            out.frame_range = (0, n)
+        return out, target_fps
+
+
+_SHM_SEQ = [0]
+_PAGE = mmap.PAGESIZE
+
+
+class _SharedHostResult:
+    """One host array visible to every rank of a single-node group: a POSIX shared-memory segment mapped by all of them, each
+    rank page-locking only the part it will fill, so that every rank copies the frames it owns straight to their final place over
+    its own PCIe link.  ``tensor`` is None when the ranks are not on one node or the segment cannot be created / registered
+    (callers fall back to NCCL).  The set-up is collective; it runs while the windows are being forwarded."""
+
+    def __init__(self, n_out: int, H: int, W: int, own_rows: Tuple[int, int], group, device):
+        import socket
+        import torch.distributed as dist
+        self.tensor, self.mm, self._registered = None, None, None
+        rank = dist.get_rank(group)
+        nbytes = n_out * H * W * 4
+        name, ok, fd = None, 1, None
+        if rank == 0:
+            _SHM_SEQ[0] += 1
+            name = f"/dev/shm/vdn_{os.getpid()}_{_SHM_SEQ[0]}"
+            try:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize < nbytes + (64 << 20):
+                    raise OSError("not enough room in /dev/shm")
+                fd = os.open(name, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                os.ftruncate(fd, nbytes)
+            except OSError:
+                ok = 0
+        info = [(socket.gethostname(), name, ok)] if rank == 0 else [None]
+        dist.broadcast_object_list(info, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        host0, name, ok = info[0]
+        t = None
+        if ok and socket.gethostname() == host0:
+            try:
+                if rank != 0:
+                    fd = os.open(name, os.O_RDWR)
+                self.mm = mmap.mmap(fd, nbytes)
+                os.close(fd)
+                t = torch.frombuffer(self.mm, dtype=torch.float32).view(n_out, H, W)
+            except (OSError, ValueError):
+                t = None
+        if t is not None and device.type == "cuda" and own_rows[1] > own_rows[0]:
+            lo_b = own_rows[0] * H * W * 4 // _PAGE * _PAGE
+            hi_b = min(nbytes, -(-(own_rows[1] * H * W * 4) // _PAGE) * _PAGE)
+            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr() + lo_b, hi_b - lo_b, 0)
+            if int(rc) != 0:
+                t = None
+            else:
+                self._registered = t.data_ptr() + lo_b
+        flag = torch.tensor([1 if t is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if rank == 0 and name is not None and ok:
+            try:
+                os.unlink(name)  # the mappings keep the segment alive; nothing is left behind in /dev/shm
+            except OSError:
+                pass
+        if int(flag.item()) == 0:
+            self.release()
+            t = None
+        self.tensor = t
+
+    def release(self):
+        if self._registered is not None:
+            torch.cuda.cudart().cudaHostUnregister(self._registered)
+            self._registered = None
 
 
 def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int, out_hw: Tuple[int, int], device, aops, group=None,
-                        gather: str = "all", forwarder: Optional[WindowForwarder] = None) -> Optional[torch.Tensor]:
+                        gather: str = "all", forwarder: Optional[WindowForwarder] = None, to_host: bool = False, stats: Optional[dict] = None):
     """Window-sharded long-video inference over ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests, which inject a
-    stand-in ``forward`` / ``aops``).  ``forward(win) -> [32, H, W]`` depth of one window at the output size.
+    stand-in ``forward`` / ``aops`` / ``forwarder``).  ``forward(win) -> [32, H, W]`` depth of one window at the output size.
 
     Collectives: (1) boundary key-frame features, rank r+1 -> rank r, so that rank r's last window does not
     re-encode the 9 frames rank r+1 needs anyway [only with a ``forwarder``]; (2) all-gather of the slots (0, 1, 12) depth
-    maps, scale/shift chain on rank 0, broadcast of the [K, 2] table; (3) the last window's raw slots 24..31, rank r -> r+1,
-    for the cross-fade at the boundary; (4) gather of the owned output frames."""
+    maps of every window — every rank then runs the same sequential scale/shift chain on the same data up to its own last
+    window, so all ranks apply bit-identical coefficients without a broadcast; (3) the last window's raw slots 24..31,
+    rank r -> r+1, for the cross-fade at the boundary.  No output frame crosses NVLink for ``gather='shard'``; ``'rank0'`` /
+    ``'all'`` assemble one array (``to_host``: in a shared host segment on one node, else on the device through NCCL).
+
+    Returns a device tensor (``to_host=False``; the CPU tests) or a numpy array / ``FrameShard`` / None (``to_host=True``)."""
     import torch.distributed as dist
+    device = torch.device(device)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     K = len(windows)
     H, W = out_hw
@@ -348,90 +642,105 @@ def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int
     def _grank(r):  # group rank -> global rank for p2p
         return dist.get_global_rank(group, r) if group is not None else r
 
+    n_out = n_frames
+    ranges = [rank_output_range(bounds, r, K, n_out) for r in range(world)]
+    lo, hi = ranges[rank]
+    shared = _SharedHostResult(n_out, H, W, (lo, hi), group, device) if (to_host and gather in ("rank0", "all")) else None
+
     # ---- forward all own windows; (1) key-frame feature exchange at the rank boundaries ---------------------------------
+    per_rank = max(b[1] - b[0] for b in bounds)
+    keys = torch.zeros((per_rank, 3, H, W), dtype=torch.float32, device=device)
     depths: List[torch.Tensor] = []
-    recv_req, recv_buf, recv_frames = None, None, None
+    recv_req, recv_buf, recv_frames, send_req, sent = None, None, None, [], None
+    prefetch = getattr(forwarder, "prefetch", None) if forwarder is not None else None
+    if prefetch is not None and mine:
+        prefetch(windows[k0])
     for i, k in enumerate(mine):
         last = i == len(mine) - 1
         if forwarder is not None and last and i > 0 and recv_req is not None:
             for rq in recv_req:
                 rq.wait()
-            P = recv_buf[0].shape[0] // len(recv_frames)
-            forwarder.seed({f: [t[j * P:(j + 1) * P] for t in recv_buf] for j, f in enumerate(recv_frames)})
+            forwarder.import_features(recv_frames, recv_buf)
             recv_req = None
-        depths.append(forward(windows[k]))
+        d = forward(windows[k])
+        depths.append(d)
+        aops.keys(d, keys[i])
         if forwarder is not None and i == 0:
             if prv is not None:  # ship the features of slots 1..9 (= window k0-1 slots 12, 24..31) to the previous rank
-                pack = forwarder.features_of(windows[k][1:OVERLAP])
-                send_req = [dist.isend(t, _grank(prv), group=group) for t in pack]
+                sent = forwarder.export_features(windows[k][1:OVERLAP])
+                send_req = [dist.isend(t, _grank(prv), group=group) for t in sent]
             if nxt is not None:
                 recv_frames = list(windows[k1][1:OVERLAP])
-                ref = forwarder.cache[windows[k][0]]
-                recv_buf = [torch.empty((len(recv_frames) * ref[t].shape[0], ref[t].shape[1]), dtype=ref[t].dtype, device=ref[t].device)
-                            for t in range(4)]
+                recv_buf = forwarder.feature_buffers(len(recv_frames))
                 recv_req = [dist.irecv(t, _grank(nxt), group=group) for t in recv_buf]
-            if prv is not None:
-                for rq in send_req:
-                    rq.wait()
+        if prefetch is not None and not last:
+            # H2D of the next window's frames while this one computes; the last window will not need the frames whose features
+            # arrive from the next rank
+            prefetch(windows[k + 1], arriving=recv_frames if (i + 1 == len(mine) - 1 and recv_req is not None) else ())
     if recv_req is not None:  # single-window rank: the features arrived too late to be useful, but the receive must complete
         for rq in recv_req:
             rq.wait()
 
-    # ---- (2) scale/shift chain ------------------------------------------------------------------------------------------
-    per_rank = max(b[1] - b[0] for b in bounds)
-    keys = torch.zeros((per_rank, 3, H, W), dtype=torch.float32, device=device)
-    for i, d in enumerate(depths):
-        keys[i, 0].copy_(d[0]); keys[i, 1].copy_(d[1]); keys[i, 2].copy_(d[KF_ALIGN[1]])
-    all_keys = torch.empty((world * per_rank, 3, H, W), dtype=torch.float32, device=device)
-    dist.all_gather_into_tensor(all_keys, keys, group=group)
-    table = torch.zeros((K, 2), dtype=torch.float32, device=device)
-    if rank == 0:
-        flat = torch.cat([all_keys[r * per_rank: r * per_rank + (b[1] - b[0])] for r, b in enumerate(bounds)])
-        table.copy_(scale_shift_chain(flat, aops))
-    dist.broadcast(table, _grank(0), group=group)
-
-    # ---- (3) boundary cross-fade operands -------------------------------------------------------------------------------
+    # ---- (3) boundary cross-fade operands: posted as soon as the last window is queued -----------------------------------------
     prev_tail = None
-    reqs = []
+    reqs = list(send_req)
     if prv is not None and k0 > 0:
         prev_tail = torch.empty((INTERP_LEN, H, W), dtype=torch.float32, device=device)
         reqs.append(dist.irecv(prev_tail, _grank(prv), group=group))
     if nxt is not None and mine:
         tail = depths[-1][INFER_LEN - INTERP_LEN:].contiguous()
         reqs.append(dist.isend(tail, _grank(nxt), group=group))
+
+    # ---- (2) scale/shift chain, redundantly on every rank up to its own last window -----------------------------------------------------
+    all_keys = torch.empty((world * per_rank, 3, H, W), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(all_keys, keys, group=group)
+    table = None
+    if mine:
+        parts = [all_keys[r * per_rank: r * per_rank + (min(b[1], k1) - b[0])] for r, b in enumerate(bounds) if b[0] < k1 and b[1] > b[0]]
+        flat = parts[0] if len(parts) == 1 else torch.cat(parts)
+        table = scale_shift_chain(flat, aops)
     for rq in reqs:
         rq.wait()
 
-    # ---- align the owned output frames ----------------------------------------------------------------------------------
-    n_out = n_frames
-    lo = owned_output_range(k0, K, n_out)[0] if mine else 0
-    hi = owned_output_range(k1 - 1, K, n_out)[1] if mine else 0
+    # ---- finalise the owned output frames: one launch per window, device -> host while the next window is finalised ------------------------
+    sink, row_base = None, lo
+    if to_host:
+        if shared is not None and shared.tensor is not None:
+            sink, row_base = HostSink(n_out, H, W, device, host=shared.tensor), 0
+        elif gather == "shard":
+            sink = HostSink(max(hi - lo, 0), H, W, device)
     shard = torch.empty((max(hi - lo, 0), H, W), dtype=torch.float32, device=device)
     for i, k in enumerate(mine):
-        d, ss = depths[i], table[k]
         o_lo, o_hi = owned_output_range(k, K, n_out)
         if o_hi <= o_lo:
             continue
-        for f in range(o_lo, o_hi):
-            slot = f - STEP * k
-            dst = shard[f - lo]
-            if k > 0 and slot < OVERLAP:  # cross-fade with the previous window's aligned slot 24 + j
-                j = slot - ALIGN_LEN
-                raw_prev = prev_tail[j] if i == 0 else depths[i - 1][INFER_LEN - INTERP_LEN + j]
-                pre = aops.affine_clamp(raw_prev, table[k - 1]) if k - 1 > 0 else raw_prev
-                aops.crossfade(pre, d[slot], ss, CROSSFADE_W[j], out=dst)
-            elif k > 0:
-                aops.affine_clamp(d[slot], ss, out=dst)
-            else:
-                dst.copy_(d[slot])
+        out = shard[o_lo - lo:o_hi - lo]
+        tail = None
+        if k > 0:
+            tail = prev_tail if i == 0 else depths[i - 1][INFER_LEN - INTERP_LEN:]
+        aops.finalize(depths[i], tail, table[k] if k > 0 else None, table[k - 1] if k - 1 > 0 else None, out, o_lo - STEP * k, k == 0)
+        if sink is not None:
+            sink.push(out, o_lo - row_base)
+    use_shared = shared is not None and shared.tensor is not None
+    if stats is not None:
+        stats.update(windows=len(mine), frame_range=(lo, hi), d2h_bytes=sink.bytes if sink is not None else 0,
+                     gather_path="shard" if gather == "shard" else ("shared-host" if use_shared else "nccl"))
 
-    # ---- (4) gather ------------------------------------------------------------------------------------------------------
-    ranges = []
-    for b in bounds:
-        if b[1] > b[0]:
-            ranges.append((owned_output_range(b[0], K, n_out)[0], owned_output_range(b[1] - 1, K, n_out)[1]))
-        else:
-            ranges.append((0, 0))
+    if gather == "shard":
+        if not to_host:
+            return shard
+        res = sink.finish().numpy().view(FrameShard)
+        res.frame_range = (lo, hi)
+        return res
+    if use_shared:
+        sink.finish()
+        dist.barrier(group=group)  # every rank's part has landed in the shared segment
+        shared.release()
+        if gather == "rank0" and rank != 0:
+            return None
+        return np.frombuffer(shared.mm, dtype=np.float32).reshape(n_out, H, W)  # the array keeps the mapping alive
+
+    # ---- (4) NCCL gather (ranks on different nodes, or no shared segment) ---------------------------------------------------------------
     full = None
     if rank == 0:
         full = torch.empty((n_out, H, W), dtype=torch.float32, device=device)
@@ -445,4 +754,6 @@ def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int
         if full is None:
             full = torch.empty((n_out, H, W), dtype=torch.float32, device=device)
         dist.broadcast(full, _grank(0), group=group)
-    return full
+    if not to_host:
+        return full
+    return full.cpu().numpy() if full is not None else None
