@@ -270,7 +270,7 @@ def test_da2_timed_shape_batch16_vitl_518_matches_oracle(vdn):
     m.load_state_dict(sd)
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     bank = []
-    for i, x in enumerate(_da2_inputs(3, 518, 16, 13)):
+    for i, x in enumerate(_da2_inputs(16, 518, 3, 13)):
         y = m(x.cuda()).clone()
         ref = O.da2_forward(sd_gpu, x.cuda(), enc, bank)
         _check(f"da2 vitl 16x518 call {i}", y, ref)

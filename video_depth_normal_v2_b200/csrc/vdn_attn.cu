@@ -10,6 +10,8 @@
 //
 // 2. vdn_temporal_attn — motion-module attention over T <= 32 frames per (pixel, head): tiny 32x32 problems, CUDA cores,
 //    one warp per (pixel, head), lane = query frame, K/V broadcast from padded shared memory.
+#include <stdlib.h>
+
 #include "../../include/vdn_b200.h"
 #include "vdn_common.cuh"
 #include "vdn_host.h"
@@ -32,6 +34,62 @@ constexpr int FA_SMEM = 2 * FA_TILE /*Q*/ + 2 * FA_TILE /*K x2*/ + 2 * FA_TILE /
 constexpr int FA_POLY = VDN_FA_POLY;  // of every 8 scores, this many take 2^x on the FMA pipe (exp2_poly), the rest on the XU pipe
 constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
 
+// ---- packed fp32 arithmetic (Blackwell FFMA2 / FADD2 on 64-bit register pairs) and the 3-input FMNMX3 for the softmax warps ----
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void up2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float max3f(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+// two 2^x on the FMA pipe (same polynomial as exp2_poly): 2 FMNMX + 6 packed instructions + 2 shift-adds
+__device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
+  const f32x2_t x = pk2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const f32x2_t magic = pk2(12582912.0f, 12582912.0f);
+  const f32x2_t t = add2(x, magic);
+  const f32x2_t n = sub2(t, magic);
+  const f32x2_t f = sub2(x, n);
+  f32x2_t pq = fma2(pk2(0.05520550534129143f, 0.05520550534129143f), f, pk2(0.24261397123336792f, 0.24261397123336792f));
+  pq = fma2(pq, f, pk2(0.6932547688484192f, 0.6932547688484192f));
+  pq = fma2(pq, f, pk2(0.9999276995658875f, 0.9999276995658875f));
+  float p0, p1, t0, t1;
+  up2(pq, p0, p1);
+  up2(t, t0, t1);
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// Softmax instruction-mix variants (VDN_FA_VARIANT; measured with scripts/microbench/exp_phase3.cu and scripts/run_flash.py):
+//   packed  : scale-sub as FFMA2 and the row sum as FADD2 (two scores per instruction)
+//   max3    : row max with the 3-input FMNMX3
+//   poly16  : of every 16 scores this many take 2^x on the FMA pipe, the rest on the XU pipe (MUFU.EX2)
+//   polypk  : the polynomial runs on register pairs (exp2_poly_pair)
+//   token   : the exp phases of the two softmax groups strictly alternate (g0 tile n, g1 tile n, g0 tile n+1, ...): a group enters
+//             its exp phase only after the other group has left its own, so one group's MUFU stream runs against the other group's
+//             MUFU-free work (wait for S, TMEM loads, row max, P store) instead of both streams fighting for the XU pipe and then
+//             both leaving it idle.  This is also the order in which the in-order MMA issuer waits for the P tiles.
+//   latewait: the wait for PV(j-1) (P buffer free, O safe to rescale) moves from before the exp phase to just before the first
+//             tcgen05.st of P(j): half of the exponentials are computed while the previous P V MMA may still be queued
+struct FaVariant { int packed, max3, poly16, polypk, latewait, token, dbg; };  // dbg (timing experiments only, wrong results): 1 = no exp, 2 = no row max, 3 = neither
+__host__ __device__ constexpr FaVariant fa_variant(int v) {
+  return v == 0 ? FaVariant{0, 0, 2 * FA_POLY, 0, 0, 0}   // round-1 kernel
+       : v == 1 ? FaVariant{1, 1, 4, 1, 0, 1}
+       : v == 2 ? FaVariant{1, 0, 4, 1, 0, 1}
+       : v == 3 ? FaVariant{1, 1, 5, 1, 0, 1}
+       : v == 4 ? FaVariant{1, 1, 2, 1, 0, 1}
+       : v == 5 ? FaVariant{1, 1, 6, 1, 0, 1}
+       : v == 6 ? FaVariant{1, 1, 4, 1, 0, 0}
+       : v == 7 ? FaVariant{1, 1, 4, 1, 1, 1}
+       : v == 8 ? FaVariant{1, 1, 4, 1, 0, 0, 1}
+       : v == 9 ? FaVariant{1, 1, 4, 1, 0, 0, 2}
+                : FaVariant{1, 1, 4, 1, 0, 0, 3};
+}
+template <int VAR> constexpr FaVariant kFaVar = fa_variant(VAR);
+constexpr int FA_NUM_VARIANTS = 11;
+#ifndef VDN_FA_DEFAULT_VARIANT
+#define VDN_FA_DEFAULT_VARIANT 6
+#endif
+
 // The softmax of a head_dim-64 attention is bound by the XU pipe: one ex2 per score at 8 cycles per warp instruction per SM
 // sub-partition (measured, scripts/microbench/pipes.cu), i.e. 1024 cycles per 128x128 score tile per SM, twice the tensor-pipe
 // time of the two MMAs.  The kernel is therefore organised around keeping the XU pipe busy:
@@ -46,7 +104,7 @@ constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_
 //   * S tiles are issued two KV tiles ahead into per-group TMEM buffers, K and V^T have independent 2-stage TMA rings,
 //     O accumulates in TMEM across KV tiles (lazy rescale: only when the running max grows by more than 2^8).
 // Two independent CTAs per SM (the previous design) drifted into phase and left the XU pipe 47 % busy (ncu, profiles/).
-template <int FMT>
+template <int FMT, int VAR>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVT,
                   void* __restrict__ out, int tokens, int tokens_kv, int heads, int C, int num_units) {
@@ -66,7 +124,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* pv_done = bars + 15;  // [group]
   uint64_t* o_free = bars + 17;   // [group]
   uint64_t* q_empty = bars + 19;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* tok = bars + 20;      // [group]: exp-phase hand-over between the softmax groups
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +152,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_init(&p_full[i], 128);
         mbar_init(&pv_done[i], 1);
         mbar_init(&o_free[i], 128);
+        mbar_init(&tok[i], 128);
       }
       fence_barrier_init();
     }
@@ -219,11 +279,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
     const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_off;
     const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-    int t = 0;  // tiles processed by this group (global)
+    int t = 0;   // tiles processed by this group (global)
+    int tn = 0;  // exp-phase turns taken by this group (global; includes the empty turns of group 1 in single-tile units)
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int qp = u % nqp, h = (u / nqp) % heads, b = u / (nqp * heads);
       const int q_tile0 = qp * FA_GROUPS;
-      if (g == 1 && !((q_tile0 + 1) * FA_BM < tokens)) continue;  // this unit has a single query tile
+      if (g == 1 && !((q_tile0 + 1) * FA_BM < tokens)) {  // this unit has a single query tile
+        if constexpr (kFaVar<VAR>.token) {            // keep the hand-over going: group 0 waits for this group's turn after every tile
+          for (int j = 0; j < nt; ++j, ++tn) {
+            mbar_wait(&tok[0], tn & 1);
+            mbar_arrive(&tok[1]);
+          }
+        }
+        continue;
+      }
       float m = -INFINITY, l = 0.0f;
       for (int j = 0; j < nt; ++j, ++t) {
         const int nvalid = min(FA_BN, tokens_kv - j * FA_BN);
@@ -247,12 +316,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        if constexpr (kFaVar<VAR>.dbg & 2) {
+          mx0 = __uint_as_float(s0[0]);
+        } else if constexpr (kFaVar<VAR>.max3) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-          mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
-          mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = max3f(mx0, __uint_as_float(s0[i]), __uint_as_float(s0[i + 1]));
+            mx1 = max3f(mx1, __uint_as_float(s1[i]), __uint_as_float(s1[i + 1]));
+            mx2 = max3f(mx2, __uint_as_float(s2[i]), __uint_as_float(s2[i + 1]));
+            mx3 = max3f(mx3, __uint_as_float(s3[i]), __uint_as_float(s3[i + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+            mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+            mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+          }
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
         // lazy rescaling: keep the stale running max unless it grows by more than 2^8 (p stays <= 256, exact after the final 1/l)
@@ -261,28 +342,63 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (grow) m_new = mx;
         const bool warp_rescale = __any_sync(0xffffffffu, grow);
         // P(j) may only overwrite P(j-1) once PV(j-1) has consumed it; the same wait makes O safe to rescale
-        if (j > 0) {
-          mbar_wait(&pv_done[g], (t - 1) & 1);
-          tc_fence_after();
-          if (warp_rescale) {
-            const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move
-            l *= alpha;
+        auto wait_pv_and_rescale = [&]() {
+          if (j > 0) {
+            mbar_wait(&pv_done[g], (t - 1) & 1);
+            tc_fence_after();
+            if (warp_rescale) {
+              const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move
+              l *= alpha;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t o[32];
-              tmem_ld32(tmem_O + c * 32, o);
-              tmem_ld_wait();
+              for (int c = 0; c < 2; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tmem_O + c * 32, o);
+                tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tmem_O + c * 32, o);
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st32(tmem_O + c * 32, o);
+              }
+              tmem_st_wait();
             }
-            tmem_st_wait();
           }
+        };
+        if constexpr (!kFaVar<VAR>.latewait) wait_pv_and_rescale();
+        if constexpr (kFaVar<VAR>.token) {  // my turn on the XU pipe: after the other group's previous (g = 0) / same (g = 1) turn
+          if (g == 1) mbar_wait(&tok[0], tn & 1);
+          else if (tn > 0) mbar_wait(&tok[1], (tn - 1) & 1);
         }
-        m = m_new;
         float sum0 = 0.0f, sum1 = 0.0f;
+        f32x2_t sum2 = pk2(0.0f, 0.0f);
+        const f32x2_t sc2 = pk2(sc, sc), nm2 = pk2(-m_new, -m_new);
         uint32_t pk[32];  // 64 probabilities packed to 16 bits = 32 TMEM columns
         auto emit = [&](const uint32_t (&sv)[32], int c) {
+          if constexpr (kFaVar<VAR>.packed) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {  // 16 scores at a time
+              float pv[16];
+#pragma unroll
+              for (int i = 0; i < 16; i += 2)
+                up2(fma2(pk2(__uint_as_float(sv[16 * q + i]), __uint_as_float(sv[16 * q + i + 1])), sc2, nm2), pv[i], pv[i + 1]);
+              if constexpr (kFaVar<VAR>.dbg & 1) {
+              } else if constexpr (kFaVar<VAR>.polypk) {
+#pragma unroll
+                for (int i = 0; i + 1 < kFaVar<VAR>.poly16; i += 2) exp2_poly_pair(pv[i], pv[i + 1]);
+                if constexpr (kFaVar<VAR>.poly16 & 1) pv[kFaVar<VAR>.poly16 - 1] = exp2_poly(pv[kFaVar<VAR>.poly16 - 1]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < kFaVar<VAR>.poly16; ++i) pv[i] = exp2_poly(pv[i]);
+              }
+              if constexpr (!(kFaVar<VAR>.dbg & 1)) {
+#pragma unroll
+                for (int i = kFaVar<VAR>.poly16; i < 16; ++i) pv[i] = ex2_approx(pv[i]);
+              }
+              const f32x2_t a = add2(add2(pk2(pv[0], pv[1]), pk2(pv[2], pv[3])), add2(pk2(pv[4], pv[5]), pk2(pv[6], pv[7])));
+              const f32x2_t b2 = add2(add2(pk2(pv[8], pv[9]), pk2(pv[10], pv[11])), add2(pk2(pv[12], pv[13]), pk2(pv[14], pv[15])));
+              sum2 = add2(sum2, add2(a, b2));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[(c & 1) * 16 + q * 8 + i] = T16f<FMT>::pack(pv[2 * i], pv[2 * i + 1]);
+            }
+          } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float pv[8];
@@ -295,12 +411,21 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 4; ++i) pk[(c & 1) * 16 + q * 4 + i] = T16f<FMT>::pack(pv[2 * i], pv[2 * i + 1]);
           }
-          if (c & 1) tmem_st32(tmem_P + (c >> 1) * 32, pk);
+          }
         };
         emit(s0, 0);
         emit(s1, 1);
+        if constexpr (kFaVar<VAR>.latewait) wait_pv_and_rescale();
+        tmem_st32(tmem_P, pk);
         emit(s2, 2);
         emit(s3, 3);
+        if constexpr (kFaVar<VAR>.token) {
+          mbar_arrive(&tok[g]);
+          ++tn;
+        }
+        tmem_st32(tmem_P + 32, pk);
+        m = m_new;
+        if constexpr (kFaVar<VAR>.packed) up2(sum2, sum0, sum1);
         l += sum0 + sum1;
         tmem_st_wait();
         tc_fence_before();
@@ -909,6 +1034,39 @@ static int launch_temporal_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVT, 
 
 using namespace vdn;
 
+namespace vdn {
+template <int FMT, int VAR>
+static int launch_flash_one(int grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVT, void* out, int tokens_q,
+                            int tokens_kv, int heads, int C, int units) {
+  static bool configured_dev[kMaxDevices] = {};  // function attributes are per device
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<FMT, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(flash_attn): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  flash_attn_kernel<FMT, VAR><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units);
+  count_launch();
+  return check_launch("flash_attn_kernel");
+}
+template <int VAR>
+static int launch_flash_fmt(int fmt, int grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVT, void* out,
+                            int tokens_q, int tokens_kv, int heads, int C, int units) {
+  return fmt ? launch_flash_one<1, VAR>(grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units)
+             : launch_flash_one<0, VAR>(grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units);
+}
+static int launch_flash_variant(int variant, int fmt, int grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVT,
+                                void* out, int tokens_q, int tokens_kv, int heads, int C, int units) {
+#define VDN_FA_CASE(V) case V: return launch_flash_fmt<V>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units)
+  switch (variant) {
+    VDN_FA_CASE(0); VDN_FA_CASE(1); VDN_FA_CASE(2); VDN_FA_CASE(3); VDN_FA_CASE(4); VDN_FA_CASE(5); VDN_FA_CASE(6); VDN_FA_CASE(7); VDN_FA_CASE(8);
+    VDN_FA_CASE(9);
+    default: return launch_flash_fmt<10>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units);
+  }
+#undef VDN_FA_CASE
+}
+}  // namespace vdn
+
 extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_stride, const void* k, int64_t ld_k, int64_t k_batch_stride,
                                  const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens_q, int32_t tokens_kv, int32_t heads,
                                  void* stream_v) {
@@ -941,21 +1099,15 @@ extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_st
     const uint32_t box[3] = {64, (uint32_t)FA_D, 1};
     if (make_tensor_map(&tmVT, vT, fmt, 3, dims, strides, box)) return 1;
   }
-  static bool configured_dev[kMaxDevices] = {};  // function attributes are per device
-  bool& configured = configured_dev[current_device()];
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
-    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(flash_attn): ") + cudaGetErrorString(e));
-    configured = true;
-  }
   const long long units = (long long)((tokens_q + FA_GROUPS * FA_BM - 1) / (FA_GROUPS * FA_BM)) * heads * B;
   if (units > 0x7fffffffLL) return set_error("vdn_flash_attn: too many work units");
   const int grid = units < num_sms() ? (int)units : num_sms();
-  if (fmt) flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, (int)units);
-  else flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, (int)units);
-  count_launch();
-  return check_launch("flash_attn_kernel");
+  static const int variant = [] {
+    const char* env = getenv("VDN_FA_VARIANT");
+    const int v = env ? atoi(env) : VDN_FA_DEFAULT_VARIANT;
+    return v < 0 || v >= FA_NUM_VARIANTS ? VDN_FA_DEFAULT_VARIANT : v;
+  }();
+  return launch_flash_variant(variant, fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, (int)units);
 }
 
 extern "C" int vdn_flash_attn(const void* qk, int64_t ld_qk, const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens, int32_t heads,
