@@ -32,7 +32,7 @@ def _worker(rank, world, port, out_path):
         assert (r0 is None) == (rank != 0)
         if rank == 0:
             assert np.array_equal(r0, out)
-            print("gather path:", st["gather_path"], flush=True)
+            print("gather path:", st["gather_path"], st.get("gather_note"), flush=True)
         # a plain drop-in call inside an initialised process group stays local: no collective, full result on this rank
         if rank == 1:
             solo, _ = m.infer_video_depth(frames[:40], 30, input_size=56, device="cuda")

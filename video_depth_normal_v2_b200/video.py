@@ -172,19 +172,99 @@ def scale_shift_chain(keys: torch.Tensor, aops) -> torch.Tensor:
     return table
 
 
+class _Phases:
+    """Optional per-phase timing of a call (``stats``): CUDA events on the compute stream plus host wall-clock stamps."""
+
+    def __init__(self, device, enabled: bool):
+        self.on = enabled and torch.device(device).type == "cuda"
+        self.marks = []
+        self.device = device
+
+    def mark(self, name: str):
+        if not self.on:
+            return
+        import time
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self.marks.append((name, ev, time.perf_counter()))
+
+    def report(self) -> dict:
+        if not self.on or len(self.marks) < 2:
+            return {}
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for (n0, e0, t0), (n1, e1, t1) in zip(self.marks[:-1], self.marks[1:]):
+            out[n1] = {"gpu_ms": round(e0.elapsed_time(e1), 3), "host_ms": round((t1 - t0) * 1e3, 3)}
+        return out
+
+
+class _PinnedPool:
+    """Page-locked result buffers that outlive a call.  Locking fresh pages costs ~0.6 ms per MB (measured on the B200 hosts: 120-220 ms
+    for the 190 MB a rank owns of a 350-frame clip), more than the copies themselves, so a buffer goes back to this pool when the array
+    handed to the caller — and every view of it — has been garbage-collected, and the next call of the same size takes it from here."""
+
+    def __init__(self, max_bytes: int = 24 << 30):
+        self.free: Dict[int, List[torch.Tensor]] = {}
+        self.max_bytes = max_bytes
+        self.pooled = 0
+
+    def acquire(self, numel: int) -> torch.Tensor:
+        lst = self.free.get(numel)
+        if lst:
+            self.pooled -= numel * 4
+            return lst.pop()
+        return torch.empty((numel,), dtype=torch.float32, pin_memory=True)
+
+    def release(self, t: torch.Tensor):
+        if self.pooled + t.numel() * 4 > self.max_bytes:
+            return  # dropped: torch frees the pages
+        self.free.setdefault(t.numel(), []).append(t)
+        self.pooled += t.numel() * 4
+
+    def export(self, t: torch.Tensor, shape) -> np.ndarray:
+        """The numpy array handed to the caller; ``t`` returns to the pool when the array and all views of it are gone."""
+        import weakref
+        base = t.numpy()  # every later view / slice keeps `base` alive through .base
+        weakref.finalize(base, self.release, t)
+        return base.reshape(shape)
+
+    def clear(self):
+        self.free.clear()
+        self.pooled = 0
+
+
+pinned_pool = _PinnedPool()
+
+
+def reserve_host_result(n_frames: int, H: int, W: int):
+    """Page-lock a result buffer of this size ahead of the first call that needs it (a service does this once at start-up)."""
+    pinned_pool.release(pinned_pool.acquire(n_frames * H * W))
+
+
 class HostSink:
-    """Device -> host copies of finalised output frames on their own stream, into one page-locked result.  The pinned block
-    comes from torch's caching host allocator: when the caller drops the returned array the block is reused by the next call."""
+    """Device -> host copies of finalised output frames on their own stream, into one page-locked result (from ``pinned_pool``)."""
 
     def __init__(self, n_rows: int, H: int, W: int, device, host: Optional[torch.Tensor] = None):
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
+        self.shape = (n_rows, H, W)
+        self.flat = None
         if host is not None:
             self.host = host
+        elif self.cuda:
+            self.flat = pinned_pool.acquire(n_rows * H * W)
+            self.host = self.flat.view(n_rows, H, W)
         else:
-            self.host = torch.empty((n_rows, H, W), dtype=torch.float32, pin_memory=self.cuda)
+            self.host = torch.empty((n_rows, H, W), dtype=torch.float32)
         self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.bytes = 0
+
+    def result(self) -> np.ndarray:
+        """Wait for the copies and hand the result over as a numpy array (the pinned block returns to the pool when it is dropped)."""
+        self.finish()
+        if self.flat is not None:
+            return pinned_pool.export(self.flat, self.shape)
+        return self.host.numpy()
 
     def push(self, rows: torch.Tensor, row0: int):
         if rows.shape[0] == 0:
@@ -541,7 +621,7 @@ def infer_video_depth(model, frames, target_fps, input_size=518, device="cuda", 
             stats.update(encoded_frames=fwd.encoded_frames, h2d_bytes=fwd.src.h2d_bytes, d2h_bytes=sink.bytes if sink is not None else 0, windows=len(windows))
         if sink is None:
             return aligner.result(n), target_fps
-        out = sink.finish().numpy()
+        out = sink.result()
         if sharded and gather == "shard":
             out = out.view(FrameShard)
             out.frame_range = (0, n)
@@ -561,7 +641,7 @@ class _SharedHostResult:
     def __init__(self, n_out: int, H: int, W: int, own_rows: Tuple[int, int], group, device):
         import socket
         import torch.distributed as dist
-        self.tensor, self.mm, self._registered = None, None, None
+        self.tensor, self.mm, self._registered, self.reason = None, None, None, ""
         rank = dist.get_rank(group)
         nbytes = n_out * H * W * 4
         name, ok, fd = None, 1, None
@@ -574,8 +654,8 @@ class _SharedHostResult:
                     raise OSError("not enough room in /dev/shm")
                 fd = os.open(name, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
                 os.ftruncate(fd, nbytes)
-            except OSError:
-                ok = 0
+            except OSError as exc:
+                ok, self.reason = 0, f"create: {exc}"
         info = [(socket.gethostname(), name, ok)] if rank == 0 else [None]
         dist.broadcast_object_list(info, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         host0, name, ok = info[0]
@@ -587,14 +667,16 @@ class _SharedHostResult:
                 self.mm = mmap.mmap(fd, nbytes)
                 os.close(fd)
                 t = torch.frombuffer(self.mm, dtype=torch.float32).view(n_out, H, W)
-            except (OSError, ValueError):
-                t = None
+            except (OSError, ValueError) as exc:
+                t, self.reason = None, f"map: {exc}"
+        elif ok:
+            self.reason = "ranks on different hosts"
         if t is not None and device.type == "cuda" and own_rows[1] > own_rows[0]:
             lo_b = own_rows[0] * H * W * 4 // _PAGE * _PAGE
             hi_b = min(nbytes, -(-(own_rows[1] * H * W * 4) // _PAGE) * _PAGE)
             rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr() + lo_b, hi_b - lo_b, 0)
             if int(rc) != 0:
-                t = None
+                t, self.reason = None, f"cudaHostRegister({hi_b - lo_b} bytes): {rc}"
             else:
                 self._registered = t.data_ptr() + lo_b
         flag = torch.tensor([1 if t is not None else 0], dtype=torch.int32, device=device)
@@ -645,8 +727,11 @@ def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int
     n_out = n_frames
     ranges = [rank_output_range(bounds, r, K, n_out) for r in range(world)]
     lo, hi = ranges[rank]
+    ph = _Phases(device, stats is not None)
+    ph.mark("start")
     shared = _SharedHostResult(n_out, H, W, (lo, hi), group, device) if (to_host and gather in ("rank0", "all")) else None
 
+    ph.mark("shared_host_setup")
     # ---- forward all own windows; (1) key-frame feature exchange at the rank boundaries ---------------------------------
     per_rank = max(b[1] - b[0] for b in bounds)
     keys = torch.zeros((per_rank, 3, H, W), dtype=torch.float32, device=device)
@@ -681,6 +766,7 @@ def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int
         for rq in recv_req:
             rq.wait()
 
+    ph.mark("forward_windows")
     # ---- (3) boundary cross-fade operands: posted as soon as the last window is queued -----------------------------------------
     prev_tail = None
     reqs = list(send_req)
@@ -701,6 +787,7 @@ def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int
         table = scale_shift_chain(flat, aops)
     for rq in reqs:
         rq.wait()
+    ph.mark("exchange_and_chain")
 
     # ---- finalise the owned output frames: one launch per window, device -> host while the next window is finalised ------------------------
     sink, row_base = None, lo
@@ -709,6 +796,7 @@ def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int
             sink, row_base = HostSink(n_out, H, W, device, host=shared.tensor), 0
         elif gather == "shard":
             sink = HostSink(max(hi - lo, 0), H, W, device)
+    ph.mark("host_result_alloc")
     shard = torch.empty((max(hi - lo, 0), H, W), dtype=torch.float32, device=device)
     for i, k in enumerate(mine):
         o_lo, o_hi = owned_output_range(k, K, n_out)
@@ -722,14 +810,19 @@ def sharded_video_depth(forward, windows: Sequence[Sequence[int]], n_frames: int
         if sink is not None:
             sink.push(out, o_lo - row_base)
     use_shared = shared is not None and shared.tensor is not None
+    ph.mark("finalize")
+    if sink is not None and stats is not None:
+        sink.finish()
+        ph.mark("d2h_tail")
     if stats is not None:
         stats.update(windows=len(mine), frame_range=(lo, hi), d2h_bytes=sink.bytes if sink is not None else 0,
-                     gather_path="shard" if gather == "shard" else ("shared-host" if use_shared else "nccl"))
+                     gather_path="shard" if gather == "shard" else ("shared-host" if use_shared else "nccl"),
+                     gather_note=shared.reason if shared is not None else "", phases=ph.report())
 
     if gather == "shard":
         if not to_host:
             return shard
-        res = sink.finish().numpy().view(FrameShard)
+        res = sink.result().view(FrameShard)
         res.frame_range = (lo, hi)
         return res
     if use_shared:
