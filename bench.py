@@ -296,7 +296,7 @@ def main():
     assert np.isfinite(y_np).all()
     h2d_total, d2h_total = sum_over_ranks(st_e2e["h2d_bytes"]), sum_over_ranks(st_e2e["d2h_bytes"])
     e2e = {"value": n_lv / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d_total / (K * world), "d2h_bytes_per_step": d2h_total / (K * world),
-           "ms_per_step": e2e_ms / K, "note": "model.infer_video_depth(uint8 frames in pinned host memory) -> float32 depth in (pinned) host memory; "
+           "ms_per_step": e2e_ms / K, "phases_rank0": {k: v["gpu_ms"] for k, v in (st_e2e.get("phases") or {}).items()} or None, "note": "model.infer_video_depth(uint8 frames in pinned host memory) -> float32 depth in (pinned) host memory; "
                                               "bytes are per window-step per GPU"}
     del y_np, lv_dev
 
@@ -464,6 +464,7 @@ def main():
                    "l2": "activations per step (>2 GB) exceed the 126 MB L2, no explicit flush",
                    "operands": args.operands + " (fp32 accumulate, fp32 residual stream)", "warmup_note": f"2 untimed passes over the same clip = {2 * K} window-steps per GPU (>= the requested {args.warmup})"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "phases_rank0": {k: v["gpu_ms"] for k, v in (st_dev.get("phases") or {}).items()} or None,
         "tensor_frac_of_step": {"ref_equiv": FRAMES * GFLOP_PER_FRAME / 1e3 / (ms_per_step / 1e3) / peaks["tflops"],
                                 "executed": exec_tflop_per_step / (ms_per_step / 1e3) / peaks["tflops"], "executed_tflop_per_step": exec_tflop_per_step},
         "kernels": kernels, "stream": stream, "da2_batch16": da2, "window": window, "encoder": encoder, "lv_parity": lv_parity, "configs4": configs4,

@@ -36,7 +36,7 @@ void vdn_add_launch_count(int64_t n);
  * (layer_scale.py:27-28) and the residual adds (block.py:105-106); PatchEmbed conv (patch_embed.py:76);
  * DPT 1x1 / 3x3 / ConvTranspose convs (dpt.py:60-124, util/blocks.py:20-32,78-91,159); motion-module linears,
  * GEGLU (motion_module/attention.py:382-384) and proj_out + residual (motion_module.py:128-133).            */
-enum { VDN_ACT_NONE = 0, VDN_ACT_GELU = 1, VDN_ACT_RELU = 2 };
+enum { VDN_ACT_NONE = 0, VDN_ACT_GELU = 1, VDN_ACT_RELU = 2, VDN_ACT_SILU = 3 /* gate activation of the GLU epilogue only (SwiGLU) */ };
 enum {
   VDN_ROWMAP_IDENTITY = 0,
   VDN_ROWMAP_PIXEL_SHUFFLE = 1, /* ConvTranspose k==stride: rm0=H_in rm1=W_in rm2=stride rm3=C_out; N = stride^2*C_out, col=(i*s+j)*C_out+co */

@@ -35,6 +35,8 @@ ENCODERS = {
     "vitl": dict(embed_dim=1024, depth=24, heads=16, taps=[4, 11, 17, 23], features=256, out_channels=[256, 512, 1024, 1024]),
     # DepthAnythingV2 only (depth_anything_v2.py:24-29, dinov2.py:353-364); VideoDepthAnything knows vits / vitl (video_depth.py:48-51)
     "vitb": dict(embed_dim=768, depth=12, heads=12, taps=[2, 5, 8, 11], features=128, out_channels=[96, 192, 384, 768]),
+    # ViT-g (dinov2.py:381-395, run.py:32): SwiGLU FFN, hidden = round_up_8(int(4 C * 2 / 3)) = 4096
+    "vitg": dict(embed_dim=1536, depth=40, heads=24, taps=[9, 19, 29, 39], features=384, out_channels=[1536, 1536, 1536, 1536], ffn="swiglu"),
 }
 POS_GRID = 37  # DINOv2(img_size=518, patch 14) -> 37x37 learned pos-embed (dinov2.py:407-409)
 NUM_FRAMES = 32
@@ -108,8 +110,13 @@ def _encoder(sd, g, prefix, cfg):
         _vit_linear(sd, g, p + "attn.proj", C, C)
         sd[p + "ls1.gamma"] = g.uniform((C,), 0.5, 1.0)
         _norm_affine(sd, g, p + "norm2", C)
-        _vit_linear(sd, g, p + "mlp.fc1", 4 * C, C)
-        _vit_linear(sd, g, p + "mlp.fc2", C, 4 * C)
+        if cfg.get("ffn") == "swiglu":
+            Hd = (int(4 * C * 2 / 3) + 7) // 8 * 8
+            _vit_linear(sd, g, p + "mlp.w12", 2 * Hd, C)
+            _vit_linear(sd, g, p + "mlp.w3", C, Hd)
+        else:
+            _vit_linear(sd, g, p + "mlp.fc1", 4 * C, C)
+            _vit_linear(sd, g, p + "mlp.fc2", C, 4 * C)
         sd[p + "ls2.gamma"] = g.uniform((C,), 0.5, 1.0)
     _norm_affine(sd, g, prefix + "norm", C)
 

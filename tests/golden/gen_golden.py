@@ -40,7 +40,7 @@ V5_CASES = [("v5_vits_s4_60x80", "vits", 4, 60, 80, 3)]
 V4_CASES = [("v4_vits_s4_56x84", "vits", 4, 56, 84, 14)]  # models/video_depth_model_v4.py: network at the native resolution
 # (name, encoder, batch, H(=W), calls, seed, stride): DepthAnythingV2 is stateful -> a sequence of forward() calls on one model
 DA2_CASES = [("da2_vits_b2_70_calls8", "vits", 2, 70, 8, 5, 1), ("da2_vits_b1_518_calls2", "vits", 1, 518, 2, 6, 4), ("da2_vitl_b1_70_calls3", "vitl", 1, 70, 3, 7, 1),
-             ("da2_vitb_b2_70_calls3", "vitb", 2, 70, 3, 17, 1),
+             ("da2_vitb_b2_70_calls3", "vitb", 2, 70, 3, 17, 1), ("da2_vitg_b1_56_calls2", "vitg", 1, 56, 2, 23, 1),
              ("da2_vits_b2_70_calls3_cls", "vits", 2, 70, 3, 19, 1)]  # name ending in _cls: use_clstoken=True
 # (name, encoder, frames, H, W, seed): streaming inference, one infer_video_depth_one call per frame (window slides after frame 10)
 STREAM_CASES = [("stream_vits_n16_56x70", "vits", 16, 56, 70, 8)]
@@ -97,8 +97,11 @@ def gen_v4():
         m = RL.load_v4(enc, sd)
         d = make_input("depth", (1, S, H, W), seed)
         y = m(d)
-        np.savez_compressed(os.path.join(OUT, name + ".npz"), out=y.numpy(), meta=np.array([S, H, W, seed]))
-        print(name, tuple(y.shape), float((y - d).abs().mean()))
+        # scripts/evaluate_v4.py:186-196: the TPF loop feeds clamp(min=0)(input) through the model twice
+        d5 = make_input("depth", (2, S, H, W), seed + 1).unsqueeze(2) - 500.0
+        y2 = m(m(d5.clamp(min=0).squeeze(2)))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), out=y.numpy(), out_tpf=y2.numpy(), meta=np.array([S, H, W, seed]))
+        print(name, tuple(y.shape), float((y - d).abs().mean()), tuple(y2.shape))
         del m
 
 

@@ -119,3 +119,46 @@ def test_scale_shift_solver_matches_reference_formula():
     s_ref, b_ref = O.compute_scale_and_shift(p, t)
     assert abs(s - s_ref) < 1e-4 and abs(b - b_ref) < 1e-4
     assert V._solve_scale_shift([0, 0, 0, 0, 0]) == (1.0, 0.0)
+
+
+@pytest.mark.parametrize("process_length,target_fps,max_res", [(-1, -1, -1), (7, -1, -1), (-1, 10, -1), (9, 15, 40)])
+def test_read_video_frames_matches_the_reference_reader(tmp_path, process_length, target_fps, max_res):
+    """harness.read_video_frames against a restatement of utils/dc_utils.py:19-67 (cv2 branch) on a small generated clip."""
+    import cv2
+    from video_depth_normal_v2_b200.harness import read_video_frames
+    path = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (64, 48))
+    if not wr.isOpened():
+        pytest.skip("no MJPG writer in this cv2 build")
+    rng = np.random.RandomState(0)
+    for i in range(12):
+        wr.write(cv2.GaussianBlur(rng.randint(0, 255, (48, 64, 3), dtype=np.uint8), (7, 7), 0))
+    wr.release()
+
+    def reference(video_path, process_length, target_fps=-1, max_res=-1):  # dc_utils.py:41-67
+        cap = cv2.VideoCapture(video_path)
+        original_fps = cap.get(cv2.CAP_PROP_FPS)
+        oh, ow = int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)), int(cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+        if max_res > 0 and max(oh, ow) > max_res:
+            scale = max_res / max(oh, ow)
+            height, width = round(oh * scale), round(ow * scale)
+        fps = original_fps if target_fps < 0 else target_fps
+        stride = max(round(original_fps / fps), 1)
+        frames, count = [], 0
+        while cap.isOpened():
+            ret, frame = cap.read()
+            if not ret or (process_length > 0 and count >= process_length):
+                break
+            if count % stride == 0:
+                frame = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+                if max_res > 0 and max(oh, ow) > max_res:
+                    frame = cv2.resize(frame, (width, height))
+                frames.append(frame)
+            count += 1
+        cap.release()
+        return np.stack(frames, axis=0), fps
+
+    exp, fps_e = reference(path, process_length, target_fps, max_res)
+    got, fps_g = read_video_frames(path, process_length, target_fps, max_res)
+    assert fps_g == fps_e and got.shape == exp.shape and got.dtype == np.uint8
+    assert np.array_equal(got, exp)

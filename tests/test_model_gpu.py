@@ -225,7 +225,7 @@ def _da2_inputs(B, H, calls, seed):
 
 
 @pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl"),
-                                      ("da2_vitb_b2_70_calls3", "vitb"), ("da2_vits_b2_70_calls3_cls", "vits")])
+                                      ("da2_vitb_b2_70_calls3", "vitb"), ("da2_vits_b2_70_calls3_cls", "vits"), ("da2_vitg_b1_56_calls2", "vitg")])
 def test_da2_stateful_forward_matches_reference_golden(vdn, name, enc):
     """A sequence of forward() calls on one model against the live reference's outputs: empty bank (constant cross-attention
     term), filling bank (cross-attention over 1..6 cached entries) and the ring wrap after 6 entries."""
@@ -371,6 +371,13 @@ def test_v4_refiner_matches_reference_golden(vdn):
     assert e["max_abs"] <= 1e-3
     with pytest.raises(RuntimeError):  # patch_embed.py:73-74 through the native-resolution path
         m(make_input("depth", (1, 2, 60, 84), seed).cuda())
+    # the TPF harness of scripts/evaluate_v4.py:169-233 over this model: two refinement passes per batch, against the live reference
+    from video_depth_normal_v2_b200.harness import evaluate_tpf
+    d5 = make_input("depth", (2, S, H, W), seed + 1).unsqueeze(2) - 500.0
+    res = evaluate_tpf(m, [{"depth_anything_v2": d5}, {"depth_anything_v2": d5}], max_eval_count=1, keep_outputs=True)
+    assert res["frames"] == S and res["tpf_ms"] > 0 and len(res["outputs"]) == 1
+    e2 = _check("v4 TPF harness (two passes) vs reference", res["outputs"][0] / 65535.0, torch.from_numpy(g["out_tpf"]) / 65535.0, floor_frac=0.05)
+    assert e2["max_abs"] <= 2e-3
 
 
 # ------------------------------------------------------------------------------------------ BASELINE configs[3]: ViT-L 518x924

@@ -90,7 +90,7 @@ def _da2_inputs(B, H, calls, seed):
 
 
 @pytest.mark.parametrize("name,enc", [("da2_vits_b2_70_calls8", "vits"), ("da2_vits_b1_518_calls2", "vits"), ("da2_vitl_b1_70_calls3", "vitl"),
-                                      ("da2_vitb_b2_70_calls3", "vitb"), ("da2_vits_b2_70_calls3_cls", "vits")])
+                                      ("da2_vitb_b2_70_calls3", "vitb"), ("da2_vits_b2_70_calls3_cls", "vits"), ("da2_vitg_b1_56_calls2", "vitg")])
 def test_da2_stateful_forward_matches_reference(name, enc):
     """A sequence of forward() calls on one model (memory bank filling up, then wrapping at 6 entries)."""
     g = _load(name)
@@ -183,3 +183,9 @@ def test_v4_forward_matches_reference():
     ref = torch.from_numpy(g["out"])
     assert (y - ref).abs().max() / ref.abs().max() < 1e-4
     assert (O.v5_forward(sd, d, "vits") - ref).abs().max() / ref.abs().max() > 1e-3  # the 224x224 variant is a different function
+    # the TPF loop of scripts/evaluate_v4.py:186-196: clamp(min=0) of a (B, S, 1, H, W) batch, two refinement passes
+    d5 = make_input("depth", (2, S, H, W), seed + 1).unsqueeze(2) - 500.0
+    x = d5.clamp(min=0).squeeze(2)
+    y2 = O.v5_forward(sd, O.v5_forward(sd, x, "vits", net_size=None), "vits", net_size=None)
+    ref2 = torch.from_numpy(g["out_tpf"])
+    assert (y2 - ref2).abs().max() / ref2.abs().max() < 1e-4

@@ -148,6 +148,18 @@ __device__ __forceinline__ void gelu_fast_batch(float* v) {
   for (int i = 0; i < N; ++i) v[i] = fmaf(-fabsf(v[i]), q[i], fmaxf(v[i], 0.0f));
 }
 
+// SiLU x * sigmoid(x) = x / (1 + 2^(-x log2 e)) with the approximate MUFU ops (ex2, rcp), stage-major like gelu_fast_batch.
+template <int N>
+__device__ __forceinline__ void silu_fast_batch(float* v) {
+  float e[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = ex2_approx(v[i] * -1.4426950408889634f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = rcp_approx(1.0f + e[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] *= e[i];
+}
+
 __device__ __forceinline__ float gelu_fast(float v) {
   const float a = fabsf(v);
   const float t = rcp_approx(fmaf(a, 0.3275911f * 0.70710678118654752440f, 1.0f));

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) add_rowscalar_kernel(float* __restrict__ 
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) x[idx] += __ldg(m + idx / C);
 }
 
-constexpr int DW_MAXC = 4;  // channels per thread (C <= 1024 with 256 threads)
+constexpr int DW_MAXC = 6;  // channels per thread (C <= 1536 with 256 threads: ViT-g)
 
 __global__ void __launch_bounds__(256)
 dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ ln_w,
@@ -256,7 +256,7 @@ extern "C" int vdn_dwconv7_ln(const float* x, const float* w, const float* bias,
                               int32_t W, int32_t C, float eps, void* stream_v) {
   VDN_STREAM;
   if (!x || !w || !bias || !ln_w || !ln_b || !out) return set_error("vdn_dwconv7_ln: null pointer");
-  if (C <= 0 || C > 256 * DW_MAXC) return set_error("vdn_dwconv7_ln: C must be <= 1024");
+  if (C <= 0 || C > 256 * DW_MAXC) return set_error("vdn_dwconv7_ln: C must be <= 1536");
   dwconv7_ln_kernel<<<(unsigned)((long long)B * H * W), 256, 0, stream>>>(x, w, bias, ln_w, ln_b, out, H, W, C, eps, get_operand_format());
   count_launch();
   return check_launch("dwconv7_ln_kernel");

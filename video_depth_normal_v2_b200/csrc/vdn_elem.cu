@@ -19,9 +19,9 @@ static inline unsigned grid_for(long long work_items, int per_block, int waves =
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row held in registers (C <= 1024), fp32 statistics, 16-bit output
+// LayerNorm: one warp per row, row held in registers (C <= 1536: DINOv2 ViT-g), fp32 statistics, 16-bit output
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_MAXV = 8;  // float4 per lane -> C <= 32 * 8 * 4 = 1024
+constexpr int LN_MAXV = 12;  // float4 per lane -> C <= 32 * 12 * 4 = 1536
 
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, void* __restrict__ out, long long rows,
@@ -754,7 +754,7 @@ extern "C" int vdn_layernorm(const float* x, const float* w, const float* b, voi
                              int32_t rows_per_batch, const float* pe, int32_t pe_len, void* stream_v) {
   VDN_STREAM;
   if (!x || !w || !b || !out) return set_error("vdn_layernorm: null pointer");
-  if (C % 4 != 0 || C > 32 * LN_MAXV * 4) return set_error("vdn_layernorm: C must be a multiple of 4 and <= 1024");
+  if (C % 4 != 0 || C > 32 * LN_MAXV * 4) return set_error("vdn_layernorm: C must be a multiple of 4 and <= 1536");
   if (drop_first && (rows_per_batch < 2 || rows % rows_per_batch != 0)) return set_error("vdn_layernorm: bad rows_per_batch");
   if (pe && pe_len <= 0) return set_error("vdn_layernorm: bad pe_len");
   static const char* env = getenv("VDN_LN_V1");
@@ -762,7 +762,8 @@ extern "C" int vdn_layernorm(const float* x, const float* w, const float* b, voi
   const bool fast = !(drop_first && pe != nullptr) && rows < 0x3fffffffLL && env == nullptr;
   const long long out_rows = drop_first ? rows / rows_per_batch * (rows_per_batch - 1) : rows;
   const int rpb = drop_first ? rows_per_batch : 0;
-  if (fast && C == 1024) launch_layernorm_rows2<8>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
+  if (fast && C == 1536) launch_layernorm_rows2<12>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
+  else if (fast && C == 1024) launch_layernorm_rows2<8>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
   else if (fast && C == 768) launch_layernorm_rows2<6>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
   else if (fast && C == 384) launch_layernorm_rows2<3>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);
   else if (fast && C == 256) launch_layernorm_rows2<2>(x, w, b, out, out_rows, eps, pe, pe_len, rpb, stream);

@@ -256,12 +256,14 @@ __device__ __forceinline__ void epi_qkv(const GemmKParams& p, const RowCtx& rc, 
 
 template <int FMT>
 __device__ __forceinline__ void epi_geglu(const GemmKParams& p, const RowCtx& rc, int n0, float (&v)[32]) {
-  // interleaved (value, gate) pairs -> 16 outputs at column n0/2
+  // interleaved (value, gate) pairs -> 16 outputs at column n0/2; gate activation GELU (GEGLU, motion_module/attention.py:382-384)
+  // or SiLU (SwiGLU, dinov2_layers/swiglu_ffn.py:29-33)
   uint32_t o[8];
   float gt[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) gt[i] = v[2 * i + 1];
-  gelu_fast_batch<16>(gt);
+  if (p.act == VDN_ACT_SILU) silu_fast_batch<16>(gt);
+  else gelu_fast_batch<16>(gt);
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = pack2<FMT>(v[4 * i] * gt[2 * i], v[4 * i + 2] * gt[2 * i + 1]);
   uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + rc.out_row * p.ldc + (n0 >> 1);
@@ -980,7 +982,7 @@ extern "C" int vdn_gemm(const vdn_gemm_desc* d, void* stream_v) {
                          p.qkv_toff < 0 || p.qkv_toff + d->rm0 > p.qkv_tpo || p.qkv_tpo > d->rm1))
     return set_error("vdn_gemm: bad QKV split geometry");
   if (epi == EPI_PIXSHUF && (d->out_f32 || d->res || d->res2 || d->gamma || d->act || d->out2)) return set_error("vdn_gemm: pixel-shuffle takes bias only and a 16-bit output");
-  if (epi == EPI_GEGLU && (d->gamma || d->act || d->out2 || d->res2)) return set_error("vdn_gemm: geglu takes bias only");
+  if (epi == EPI_GEGLU && (d->gamma || (d->act != VDN_ACT_NONE && d->act != VDN_ACT_SILU) || d->out2 || d->res2)) return set_error("vdn_gemm: geglu takes bias only (act = VDN_ACT_SILU selects the SwiGLU gate)");
   if (epi != EPI_PLAIN && epi != EPI_RES && epi != EPI_HEAD && epi != EPI_TMA && d->N < 256) return set_error("vdn_gemm: QKV / GEGLU / pixel-shuffle epilogues need N >= 256");
 
   // BLOCK_N: largest tile that does not waste more than necessary

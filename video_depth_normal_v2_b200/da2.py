@@ -133,7 +133,7 @@ class _MemoryState:
 
 
 class DepthAnythingV2(_PackedModule):
-    """Drop-in for depth_anything_v2/depth_anything_v2.py:12 (encoder vits / vitb / vitl; use_bn=False)."""
+    """Drop-in for depth_anything_v2/depth_anything_v2.py:12 (encoder vits / vitb / vitl / vitg; use_bn=False)."""
 
     def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False, use_clstoken=False, max_memory_length=6):
         super().__init__()
@@ -154,13 +154,15 @@ class DepthAnythingV2(_PackedModule):
         return s
 
     def _pack(self, sd, dev, dt):
-        self._mem = None
+        self._mem = None  # (the graphs are cleared by _weights() whenever the weights are re-packed)
         return {"enc": packing.pack_encoder(sd, "pretrained.", self.cfg, dev, dt), "head": packing.pack_head(sd, "depth_head.", self.cfg, dev, dt, False, "ape", self.use_clstoken),
                 "mb": pack_memory_block(sd, "memory_block.", self.cfg["embed_dim"], dev, dt)}
 
     def clear_memory(self):
-        """depth_anything_v2.py:42-43"""
-        self._mem = None
+        """depth_anything_v2.py:42-43.  The ring buffers are kept (the captured forward graphs hold their addresses); only the
+        entry count is reset."""
+        if self._mem is not None:
+            self._mem.count = 0
 
     # ------------------------------------------------------------------------------------------------
     def _memory_attention(self, mb: dict, f3: torch.Tensor, B: int, P: int, side: int) -> torch.Tensor:
@@ -226,8 +228,6 @@ class DepthAnythingV2(_PackedModule):
             ops.gemm(y16, Fz["pw1"]["w"], hid, M=rows, N=4 * C, K=C, bias=Fz["pw1"]["b"], act=ops.ACT_GELU)
             ops.gemm(hid, Fz["pw2"]["w"], x, M=rows, N=C, K=4 * C, bias=Fz["pw2"]["b"], gamma=Fz["gamma"], res=x)
         ops.cast_f32_to_16(x, y16)
-        if self._mem is None:
-            self._mem = _MemoryState(B, P, C, heads, self.max_memory_length, dev, od)
         mem = self._mem
         slot = mem.count % mem.max_len  # ring: the oldest entry is overwritten once the bank is full (memory_bank.py:17-20)
         cs = rope_table(mb, side, dev)
@@ -249,22 +249,35 @@ class DepthAnythingV2(_PackedModule):
         side = H // 14
         P = side * side
         if self._mem is not None and (self._mem.B != B or self._mem.P != P):
-            raise RuntimeError("batch size / resolution changed while the memory bank is not empty: call clear_memory() first")
-        x = x.to(device=self._dev, dtype=torch.float32)
+            if self._mem.count > 0:
+                raise RuntimeError("batch size / resolution changed while the memory bank is not empty: call clear_memory() first")
+            self._mem = None          # empty bank of another shape: new ring buffers ...
+            self._graphs.clear()      # ... and the graphs that point into the old ones go
+        x = x.to(device=self._dev, dtype=torch.float32).contiguous()
         readout = w["head"].get("readout")
-        feats = encoder_forward(w["enc"], x, readout, defer_last_readout=True)
-        f3m = self._memory_attention(w["mb"], feats[3], B, P, side)
-        if readout is not None:
-            # use_clstoken: the last tap's readout sees the memory block's tokens and the encoder's cls token (depth_anything_v2.py:49-51)
-            C = self.cfg["embed_dim"]
-            f3 = _empty((B * P, C), ops.operand_dtype(), x.device)
-            readout_apply(readout[3], f3m, 0, P, feats[4], P + 1, f3, B, P, C)
-            feats = feats[:3] + [f3]
-        else:
-            feats[3] = f3m
-        depth = head_forward(w["head"], feats, B, side, side, None)  # [B, H, W], already through output_conv2's ReLUs
+        if self._mem is None:
+            self._mem = _MemoryState(B, P, self.cfg["embed_dim"], w["mb"]["heads"], self.max_memory_length, self._dev, ops.operand_dtype())
+
+        def run(xd):
+            feats = encoder_forward(w["enc"], xd, readout, defer_last_readout=True)
+            f3m = self._memory_attention(w["mb"], feats[3], B, P, side)
+            if readout is not None:
+                # use_clstoken: the last tap's readout sees the memory block's tokens and the encoder's cls token (depth_anything_v2.py:49-51)
+                C = self.cfg["embed_dim"]
+                f3 = _empty((B * P, C), ops.operand_dtype(), xd.device)
+                readout_apply(readout[3], f3m, 0, P, feats[4], P + 1, f3, B, P, C)
+                feats = feats[:3] + [f3]
+            else:
+                feats[3] = f3m
+            depth = head_forward(w["head"], feats, B, side, side, None)  # [B, H, W], already through output_conv2's ReLUs
+            return [depth, f3m]
+
+        # encoder + memory attention + head replay as one CUDA graph per (shape, number of bank entries): with a full bank every
+        # call has the same launch sequence (the ring buffers keep their addresses); the memory update below depends on the ring
+        # slot and stays eager (~20 launches)
+        depth, f3m = self._graphs.run(("da2", B, H, self._mem.entries), run, [x])
         self._update_memory(w["mb"], f3m, depth, B, side)
-        return depth
+        return depth.clone()
 
     @torch.no_grad()
     def infer_image(self, raw_image: np.ndarray, input_size: int = 518) -> np.ndarray:

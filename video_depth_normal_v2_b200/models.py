@@ -26,8 +26,15 @@ ENCODER_CONFIGS = {
     "vits": dict(embed_dim=384, depth=12, heads=6, taps=[2, 5, 8, 11]),
     "vitl": dict(embed_dim=1024, depth=24, heads=16, taps=[4, 11, 17, 23]),
 }
-# depth_anything_v2.py:24-29 also lists vitb (dinov2.py:353-364); vitg (SwiGLU FFN, embed_dim 1536) is not built
-DA2_ENCODER_CONFIGS = dict(ENCODER_CONFIGS, vitb=dict(embed_dim=768, depth=12, heads=12, taps=[2, 5, 8, 11]))
+# depth_anything_v2.py:24-29 also lists vitb (dinov2.py:353-364) and vitg (dinov2.py:381-395: 40 blocks, embed_dim 1536, 24 heads,
+# SwiGLU FFN, dinov2_layers/swiglu_ffn.py)
+DA2_ENCODER_CONFIGS = dict(ENCODER_CONFIGS, vitb=dict(embed_dim=768, depth=12, heads=12, taps=[2, 5, 8, 11]),
+                           vitg=dict(embed_dim=1536, depth=40, heads=24, taps=[9, 19, 29, 39], ffn="swiglu"))
+
+
+def swiglu_hidden(C: int) -> int:
+    """SwiGLUFFNFused: hidden = round_up_8(int(4 C * 2 / 3))  (dinov2_layers/swiglu_ffn.py:52-63 with mlp_ratio 4)."""
+    return (int(4 * C * 2 / 3) + 7) // 8 * 8
 
 # video_depth.py:29-33 — "infer settings, do not change"
 INFER_LEN = 32
@@ -116,7 +123,7 @@ def encoder_forward(enc: dict, x: torch.Tensor, readout: Optional[list] = None, 
     qk = _empty((rows, 2 * C), od, dev)
     vT = _empty((Bf * heads, 64, npad), od, dev)
     ao = _empty((rows, C), od, dev)
-    hid = _empty((rows, 4 * C), od, dev)
+    hid = _empty((rows, enc.get("hidden", 4 * C)), od, dev)
     feats = []
     for i, blk in enumerate(enc["blocks"]):
         ops.layernorm(xs, blk["ln1_w"], blk["ln1_b"], xn, 1e-6)
@@ -125,8 +132,13 @@ def encoder_forward(enc: dict, x: torch.Tensor, readout: Optional[list] = None, 
         ops.flash_attn(qk, vT, ao, Bf, N, heads)
         ops.gemm(ao, blk["proj"]["w"], xs, M=rows, N=C, K=C, bias=blk["proj"]["b"], gamma=blk["ls1"], res=xs)
         ops.layernorm(xs, blk["ln2_w"], blk["ln2_b"], xn, 1e-6)
-        ops.gemm(xn, blk["fc1"]["w"], hid, M=rows, N=4 * C, K=C, bias=blk["fc1"]["b"], act=ops.ACT_GELU)
-        ops.gemm(hid, blk["fc2"]["w"], xs, M=rows, N=C, K=4 * C, bias=blk["fc2"]["b"], gamma=blk["ls2"], res=xs)
+        if "w12" in blk:  # SwiGLU FFN (ViT-g): hidden = silu(x1) * x2 in the epilogue of the interleaved (x2, x1) projection
+            Hd = enc["hidden"]
+            ops.gemm(xn, blk["w12"]["w"], hid, M=rows, N=2 * Hd, K=C, bias=blk["w12"]["b"], geglu=True, act=ops.ACT_SILU)
+            ops.gemm(hid, blk["w3"]["w"], xs, M=rows, N=C, K=Hd, bias=blk["w3"]["b"], gamma=blk["ls2"], res=xs)
+        else:
+            ops.gemm(xn, blk["fc1"]["w"], hid, M=rows, N=4 * C, K=C, bias=blk["fc1"]["b"], act=ops.ACT_GELU)
+            ops.gemm(hid, blk["fc2"]["w"], xs, M=rows, N=C, K=4 * C, bias=blk["fc2"]["b"], gamma=blk["ls2"], res=xs)
         if i in enc["taps"]:
             f = _empty((Bf * P, C), od, dev)
             last_deferred = readout is not None and defer_last_readout and len(feats) == 3
@@ -440,8 +452,13 @@ def _encoder_shapes(prefix: str, cfg: dict) -> Dict[str, tuple]:
         s[p + "attn.qkv.weight"], s[p + "attn.qkv.bias"] = (3 * C, C), (3 * C,)
         s[p + "attn.proj.weight"], s[p + "attn.proj.bias"] = (C, C), (C,)
         s[p + "ls1.gamma"] = s[p + "ls2.gamma"] = (C,)
-        s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"] = (4 * C, C), (4 * C,)
-        s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = (C, 4 * C), (C,)
+        if cfg.get("ffn") == "swiglu":
+            Hd = swiglu_hidden(C)
+            s[p + "mlp.w12.weight"], s[p + "mlp.w12.bias"] = (2 * Hd, C), (2 * Hd,)
+            s[p + "mlp.w3.weight"], s[p + "mlp.w3.bias"] = (C, Hd), (C,)
+        else:
+            s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"] = (4 * C, C), (4 * C,)
+            s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = (C, 4 * C), (C,)
     s[prefix + "norm.weight"] = s[prefix + "norm.bias"] = (C,)
     return s
 

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import GemmDesc
 
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SILU = 0, 1, 2, 3
 ROWMAP_IDENTITY, ROWMAP_PIXEL_SHUFFLE, ROWMAP_TEMPORAL, ROWMAP_PATCH_TOKENS, ROWMAP_QKV_SPLIT = 0, 1, 2, 3, 4
 
 _FMT_DTYPE = {0: torch.float16, 1: torch.bfloat16}

@@ -70,16 +70,30 @@ def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str, cfg: dict, dev, dt) -
     enc["pos_embed_raw"] = sd[prefix + "pos_embed"].detach().float().cpu()
     enc["pos_cache"] = {}
     blocks = []
+    swiglu = cfg.get("ffn") == "swiglu"
+    if swiglu:
+        enc["hidden"] = sd[f"{prefix}blocks.0.mlp.w3.weight"].shape[1]
     for i in range(cfg["depth"]):
         p = f"{prefix}blocks.{i}."
-        blocks.append({
+        blk = {
             "ln1_w": _f32(sd[p + "norm1.weight"], dev), "ln1_b": _f32(sd[p + "norm1.bias"], dev),
             "qkv": pack_linear(sd, p + "attn.qkv", dev, dt), "proj": pack_linear(sd, p + "attn.proj", dev, dt),
             "ls1": _f32(sd[p + "ls1.gamma"], dev),
             "ln2_w": _f32(sd[p + "norm2.weight"], dev), "ln2_b": _f32(sd[p + "norm2.bias"], dev),
-            "fc1": pack_linear(sd, p + "mlp.fc1", dev, dt), "fc2": pack_linear(sd, p + "mlp.fc2", dev, dt),
             "ls2": _f32(sd[p + "ls2.gamma"], dev),
-        })
+        }
+        if swiglu:
+            # x12 = w12(x); x1, x2 = x12.chunk(2); hidden = silu(x1) * x2 (swiglu_ffn.py:29-33).  The GLU epilogue computes
+            # value * act(gate) on interleaved (value, gate) output columns: row 2i <- x2_i (value), row 2i+1 <- x1_i (gate)
+            w12, b12 = sd[p + "mlp.w12.weight"].detach().float(), sd[p + "mlp.w12.bias"].detach().float()
+            Hd = w12.shape[0] // 2
+            wi = torch.stack([w12[Hd:], w12[:Hd]], dim=1).reshape(2 * Hd, -1)
+            bi = torch.stack([b12[Hd:], b12[:Hd]], dim=1).reshape(2 * Hd)
+            blk["w12"] = {"w": _w16(wi, dev, dt), "b": _f32(bi, dev)}
+            blk["w3"] = pack_linear(sd, p + "mlp.w3", dev, dt)
+        else:
+            blk["fc1"], blk["fc2"] = pack_linear(sd, p + "mlp.fc1", dev, dt), pack_linear(sd, p + "mlp.fc2", dev, dt)
+        blocks.append(blk)
     enc["blocks"] = blocks
     enc["norm_w"], enc["norm_b"] = _f32(sd[prefix + "norm.weight"], dev), _f32(sd[prefix + "norm.bias"], dev)
     return enc

@@ -673,7 +673,7 @@ class _SharedHostResult:
             self.reason = "ranks on different hosts"
         if t is not None and device.type == "cuda" and own_rows[1] > own_rows[0]:
             lo_b = own_rows[0] * H * W * 4 // _PAGE * _PAGE
-            hi_b = min(nbytes, -(-(own_rows[1] * H * W * 4) // _PAGE) * _PAGE)
+            hi_b = -(-(own_rows[1] * H * W * 4) // _PAGE) * _PAGE  # whole pages: the mapping extends to the end of its last page
             rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr() + lo_b, hi_b - lo_b, 0)
             if int(rc) != 0:
                 t, self.reason = None, f"cudaHostRegister({hi_b - lo_b} bytes): {rc}"
@@ -681,12 +681,14 @@ class _SharedHostResult:
                 self._registered = t.data_ptr() + lo_b
         flag = torch.tensor([1 if t is not None else 0], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0 and t is not None:
+            self.reason = "another rank could not map / register the segment"
         if rank == 0 and name is not None and ok:
             try:
                 os.unlink(name)  # the mappings keep the segment alive; nothing is left behind in /dev/shm
             except OSError:
                 pass
-        if int(flag.item()) == 0:
+        if t is None or int(flag.item()) == 0:
             self.release()
             t = None
         self.tensor = t
