@@ -567,6 +567,18 @@ class VideoDepthAnything(_PackedModule):
         feats = self._graphs.run(("encode",) + tuple(x.shape), lambda xd: encoder_forward(w["enc"], xd, w["head"].get("readout")), [x])
         return [f.clone() for f in feats] if clone else list(feats)  # the long-video driver keeps per-frame views of these across windows
 
+    def window_feature_buffers(self, ph: int, pw: int) -> List[torch.Tensor]:
+        """Four persistent [32 * ph * pw, C] buffers (one per tapped layer) holding the encoder features of one window in slot order:
+        the static inputs of the captured head graph.  They live as long as the packed weights, so every long-video call of this
+        model replays the same graph (one pipeline per model at a time: not re-entrant, like the reference)."""
+        self._weights()
+        bufs = self.__dict__.setdefault("_win_bufs", {})
+        key = (ph, pw, ops.operand_dtype(), self._dev)
+        if key not in bufs:
+            C = self.cfg["embed_dim"]
+            bufs[key] = [torch.empty((INFER_LEN * ph * pw, C), dtype=ops.operand_dtype(), device=self._dev) for _ in range(4)]
+        return bufs[key]
+
     @torch.no_grad()
     def head_from_features(self, feats: List[torch.Tensor], T: int, ph: int, pw: int, static_inputs: bool = False, clone: bool = True) -> torch.Tensor:
         """4 x [T*ph*pw, C] -> depth (T, 14*ph, 14*pw) fp32 (one video, T <= 32 frames).  ``static_inputs``: ``feats`` are persistent

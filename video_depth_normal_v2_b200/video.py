@@ -471,8 +471,11 @@ class WindowForwarder:
             new = self.model.encode_frames(x, clone=False) if need else None
             self.encoded_frames += len(need)
             if self.win_feats is None:
-                P = [t.shape[0] // len(need) for t in new]
-                self.win_feats = [torch.empty((INFER_LEN * P[t], new[t].shape[1]), dtype=new[t].dtype, device=new[t].device) for t in range(4)]
+                if hasattr(self.model, "window_feature_buffers"):  # persistent per model: the captured head graph reads them in place
+                    self.win_feats = self.model.window_feature_buffers(h // 14, w // 14)
+                else:
+                    P = [t.shape[0] // len(need) for t in new]
+                    self.win_feats = [torch.empty((INFER_LEN * P[t], new[t].shape[1]), dtype=new[t].dtype, device=new[t].device) for t in range(4)]
             prev_slot = {f: s for s, f in reversed(list(enumerate(self.prev_win)))} if self.prev_win is not None else {}
             new_row = {f: i for i, f in enumerate(need)}
             # (kind, source index) of every slot; slots that already hold their frame are skipped; consecutive slots coalesce
