@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvdn_b200.so")
+LIB_PATH = os.environ.get("VDN_LIB_PATH") or os.path.join(HERE, "libvdn_b200.so")  # VDN_LIB_PATH: debug builds (scripts/build_fa_timeline.sh)
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

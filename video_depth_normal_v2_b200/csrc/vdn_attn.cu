@@ -70,7 +70,12 @@ __device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
 //             both leaving it idle.  This is also the order in which the in-order MMA issuer waits for the P tiles.
 //   latewait: the wait for PV(j-1) (P buffer free, O safe to rescale) moves from before the exp phase to just before the first
 //             tcgen05.st of P(j): half of the exponentials are computed while the previous P V MMA may still be queued
-struct FaVariant { int packed, max3, poly16, polypk, latewait, token, dbg; };  // dbg (timing experiments only, wrong results): 1 = no exp, 2 = no row max, 3 = neither
+//   mma2    : one MMA issuer warp per softmax group (warps 8 and 10) instead of a single in-order issuer
+// Round-2 experiments on the hand-off structure (profiles/r02_flash_experiments.txt has the numbers and the VDN_FA_TIMELINE
+// traces): late wait for PV(j-1), two issuers, and a software-pipelined softmax (loads + row max of tile j+1 inside the exp phase of
+// tile j, S issued as two 64-key halves) all measured slower than variant 6 — two softmax warps per sub-partition get the same
+// exp throughput whether they alternate or overlap (~1150 cycles per 128-score warp tile), so only fewer issue cycles per score help.
+struct FaVariant { int packed, max3, poly16, polypk, latewait, token, dbg, mma2; };  // dbg (timing experiments only, wrong results): 1 = no exp, 2 = no row max, 3 = neither
 __host__ __device__ constexpr FaVariant fa_variant(int v) {
   return v == 0 ? FaVariant{0, 0, 2 * FA_POLY, 0, 0, 0}   // round-1 kernel
        : v == 1 ? FaVariant{1, 1, 4, 1, 0, 1}
@@ -82,13 +87,34 @@ __host__ __device__ constexpr FaVariant fa_variant(int v) {
        : v == 7 ? FaVariant{1, 1, 4, 1, 1, 1}
        : v == 8 ? FaVariant{1, 1, 4, 1, 0, 0, 1}
        : v == 9 ? FaVariant{1, 1, 4, 1, 0, 0, 2}
-                : FaVariant{1, 1, 4, 1, 0, 0, 3};
+       : v == 10 ? FaVariant{1, 1, 4, 1, 0, 0, 3}
+       : v == 11 ? FaVariant{1, 1, 4, 1, 1, 0}            // half of tile j's exponentials before the wait for PV(j-1), no token
+       : v == 12 ? FaVariant{1, 1, 4, 1, 0, 0, 0, 1}      // one MMA issuer warp per softmax group
+                 : FaVariant{1, 1, 4, 1, 0, 0, 1, 1};     // timing only: 12 without exp
 }
 template <int VAR> constexpr FaVariant kFaVar = fa_variant(VAR);
-constexpr int FA_NUM_VARIANTS = 11;
+
+// Debug builds only (VDN_EXTRA_NVCC_FLAGS=-DVDN_FA_TIMELINE): CTA 0 records (event, SM clock) pairs per warp role; read back with
+// vdn_debug_fa_timeline (scripts/fa_timeline.py draws the hand-offs between the softmax groups and the MMA issuer).
+#ifdef VDN_FA_TIMELINE
+constexpr int FA_TL_CAP = 4096;
+__device__ unsigned long long g_fa_tl[5][FA_TL_CAP];
+__device__ int g_fa_tl_n[5];
+__device__ __forceinline__ void fa_tl(int slot, int ev, int lane, int& n) {
+  if (blockIdx.x == 0 && lane == 0 && n < FA_TL_CAP) {
+    g_fa_tl[slot][n] = ((unsigned long long)ev << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
+    g_fa_tl_n[slot] = ++n;
+  }
+}
+#define FA_TL(slot, ev) fa_tl(slot, ev, lane + (warp_idx < 8 ? (warp_idx & 3) * 32 : 0), tl_n)
+#else
+#define FA_TL(slot, ev)
+#endif
+constexpr int FA_NUM_VARIANTS = 14;
 #ifndef VDN_FA_DEFAULT_VARIANT
 #define VDN_FA_DEFAULT_VARIANT 6
 #endif
+
 
 // The softmax of a head_dim-64 attention is bound by the XU pipe: one ex2 per score at 8 cycles per warp instruction per SM
 // sub-partition (measured, scripts/microbench/pipes.cu), i.e. 1024 cycles per 128x128 score tile per SM, twice the tensor-pipe
@@ -129,6 +155,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef VDN_FA_TIMELINE
+  int tl_n = 0;
+#endif
   const int nt = (tokens_kv + FA_BN - 1) / FA_BN;  // KV tiles (cross-attention: tokens_kv != tokens)
   const int nq_tiles = (tokens + FA_BM - 1) / FA_BM;
   const int nqp = (nq_tiles + FA_GROUPS - 1) / FA_GROUPS;  // query-tile pairs per (frame, head)
@@ -140,13 +169,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmVT);
+      constexpr int consumers = kFaVar<VAR>.mma2 ? 2 : 1;  // MMA issuer warps that release the Q / K / V^T stages
       mbar_init(q_full, 1);
-      mbar_init(q_empty, 1);
+      mbar_init(q_empty, consumers);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&k_full[i], 1);
-        mbar_init(&k_empty[i], 1);
+        mbar_init(&k_empty[i], consumers);
         mbar_init(&v_full[i], 1);
-        mbar_init(&v_empty[i], 1);
+        mbar_init(&v_empty[i], consumers);
         mbar_init(&s_full[i], 1);
         mbar_init(&s_free[i], 128);
         mbar_init(&p_full[i], 128);
@@ -187,13 +217,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int j = 0; j < nt; ++j, ++kvc) {
         const int st = kvc & 1;
         const uint32_t ph = (kvc >> 1) & 1;
+        FA_TL(3, 30);
         mbar_wait(&k_empty[st], ph ^ 1);
+        FA_TL(3, 31);
         if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[st], FA_TILE);
           tma_load_4d(sK + st * FA_TILE, &tmK, &k_full[st], 0, h, j * FA_BN, b);
         }
         __syncwarp();
         mbar_wait(&v_empty[st], ph ^ 1);
+        FA_TL(3, 32);
         if (elect_one()) {
           mbar_arrive_expect_tx(&v_full[st], FA_TILE);
           tma_load_3d(sV + st * FA_TILE, &tmVT, &v_full[st], j * FA_BN, 0, b * heads + h);
@@ -202,10 +235,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         __syncwarp();
       }
     }
-  } else if (warp_idx == 8) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp_idx == 8 || (kFaVar<VAR>.mma2 && warp_idx == 10)) {
+    // ---------------- MMA issuer(s) ----------------
     // The whole warp runs the (warp-uniform) control flow and one elected lane issues: with the loops under `if (lane == 0)`
     // the compiler cannot prove the descriptors uniform and wraps every tcgen05.mma in an R2UR / ELECT / BRA.U.ANY waterfall.
+    // mma2: one issuer warp per softmax group (warps 8 and 10, on different sub-partitions).  A single in-order issuer makes each
+    // group's chain  P(j) -> PV(j) -> pv_done -> exp(j+1)  wait for the other group's PV and S batches and for the issuer's own
+    // barrier round trips (measured with VDN_FA_TIMELINE: the issuer loop, not the XU pipe, set the pace, and the two groups'
+    // exp phases strictly alternated); with two issuers a group's P V is queued the moment its P tile lands.
+    constexpr bool MMA2 = kFaVar<VAR>.mma2 != 0;
+    const int gb = MMA2 ? (warp_idx - 8) >> 1 : 0;       // first group served by this warp
+    const int ge = MMA2 ? gb + 1 : FA_GROUPS;            // one past the last
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, 128);
     constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, 64);
@@ -217,10 +257,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
       const int qp = u % nqp;
       const int ngroups = (qp * FA_GROUPS + 1) * FA_BM < tokens ? 2 : 1;
+      const int gl = ge < ngroups ? ge : ngroups;  // groups [gb, gl) of this unit are this warp's
       auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T
         const int kst = (kv0 + j) & 1;
+        FA_TL(2 + 2 * gb, 16 + g);
         if (si[g] > 0) mbar_wait(&s_free[g], (si[g] - 1) & 1);
-        if (g == 0) mbar_wait(&k_full[kst], ((kv0 + j) >> 1) & 1);
+        FA_TL(2 + 2 * gb, 18 + g);
+        if (g == gb) mbar_wait(&k_full[kst], ((kv0 + j) >> 1) & 1);
+        FA_TL(2 + 2 * gb, 20 + g);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t dq = make_sdesc_sw128(q_addr + g * FA_TILE);
@@ -228,23 +272,44 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
           for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tb + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
           umma_commit(&s_full[g]);
-          if (g == ngroups - 1) {
+          if (g == gl - 1) {
             umma_commit(&k_empty[kst]);
             if (j == nt - 1) umma_commit(q_empty);  // last S of this unit: Q may be replaced
           }
         }
         __syncwarp();
+        FA_TL(2 + 2 * gb, 24 + g);
         ++si[g];
       };
       mbar_wait(q_full, ui & 1);
+      if (MMA2 && gb >= ngroups) {
+        // single-tile unit: this warp's group has no work, but the stages are released by two arrivals
+        for (int j = 0; j < nt; ++j) {
+          const int st = (kv0 + j) & 1;
+          const uint32_t ph = ((kv0 + j) >> 1) & 1;
+          mbar_wait(&k_full[st], ph);
+          if (elect_one()) mbar_arrive(&k_empty[st]);
+          __syncwarp();
+          mbar_wait(&v_full[st], ph);
+          if (elect_one()) mbar_arrive(&v_empty[st]);
+          __syncwarp();
+        }
+        if (elect_one()) mbar_arrive(q_empty);
+        __syncwarp();
+        kv0 += nt;
+        continue;
+      }
       // prologue: S(0) and S(1) of both groups (each group's S buffer is refilled as soon as the group has pulled it into registers)
       for (int j = 0; j < 2 && j < nt; ++j)
-        for (int g = 0; g < ngroups; ++g) issue_s(g, j);
+        for (int g = gb; g < gl; ++g) issue_s(g, j);
       for (int j = 0; j < nt; ++j) {
         const int vst = (kv0 + j) & 1;
-        for (int g = 0; g < ngroups; ++g) {
+        for (int g = gb; g < gl; ++g) {
+          FA_TL(2 + 2 * gb, 10 + g);
           mbar_wait(&p_full[g], pi[g] & 1);
-          if (g == 0) mbar_wait(&v_full[vst], ((kv0 + j) >> 1) & 1);
+          FA_TL(2 + 2 * gb, 12 + g);
+          if (g == gb) mbar_wait(&v_full[vst], ((kv0 + j) >> 1) & 1);
+          FA_TL(2 + 2 * gb, 14 + g);
           if (j == 0 && ug[g] > 0) mbar_wait(&o_free[g], (ug[g] - 1) & 1);  // the group has read the previous unit's O
           tc_fence_after();
           if (elect_one()) {
@@ -257,15 +322,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               umma_f16_ts(tb + 256 + g * 64, tb + 384 + g * 64 + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
             }
             umma_commit(&pv_done[g]);
-            if (g == ngroups - 1) umma_commit(&v_empty[vst]);
+            if (g == gl - 1) umma_commit(&v_empty[vst]);
           }
           __syncwarp();
+          FA_TL(2 + 2 * gb, 22 + g);
           ++pi[g];
           if (j + 2 < nt) issue_s(g, j + 2);
         }
       }
       kv0 += nt;
-      for (int g = 0; g < ngroups; ++g) ++ug[g];
+      for (int g = gb; g < gl; ++g) ++ug[g];
     }
   }
   } else {
@@ -296,7 +362,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       float m = -INFINITY, l = 0.0f;
       for (int j = 0; j < nt; ++j, ++t) {
         const int nvalid = min(FA_BN, tokens_kv - j * FA_BN);
+        FA_TL(g, 1);
         mbar_wait(&s_full[g], t & 1);
+        FA_TL(g, 2);
         tc_fence_after();
         uint32_t s0[32], s1[32], s2[32], s3[32];
         tmem_ld32(tmem_S + 0, s0);
@@ -304,6 +372,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_ld32(tmem_S + 64, s2);
         tmem_ld32(tmem_S + 96, s3);
         tmem_ld_wait();
+        FA_TL(g, 3);
         tc_fence_before();
         mbar_arrive(&s_free[g]);  // S(j) is out of TMEM: the issuer may overwrite it with S(j+2)
         if (nvalid < FA_BN) {     // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
@@ -344,7 +413,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // P(j) may only overwrite P(j-1) once PV(j-1) has consumed it; the same wait makes O safe to rescale
         auto wait_pv_and_rescale = [&]() {
           if (j > 0) {
+            FA_TL(g, 4);
             mbar_wait(&pv_done[g], (t - 1) & 1);
+            FA_TL(g, 5);
             tc_fence_after();
             if (warp_rescale) {
               const float alpha = ex2_approx(m - m_new);  // 1 for lanes whose max did not move
@@ -427,9 +498,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         m = m_new;
         if constexpr (kFaVar<VAR>.packed) up2(sum2, sum0, sum1);
         l += sum0 + sum1;
+        FA_TL(g, 6);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[g]);
+        FA_TL(g, 7);
       }
       mbar_wait(&pv_done[g], (t - 1) & 1);
       tc_fence_after();
@@ -1060,12 +1133,22 @@ static int launch_flash_variant(int variant, int fmt, int grid, cudaStream_t str
 #define VDN_FA_CASE(V) case V: return launch_flash_fmt<V>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units)
   switch (variant) {
     VDN_FA_CASE(0); VDN_FA_CASE(1); VDN_FA_CASE(2); VDN_FA_CASE(3); VDN_FA_CASE(4); VDN_FA_CASE(5); VDN_FA_CASE(6); VDN_FA_CASE(7); VDN_FA_CASE(8);
-    VDN_FA_CASE(9);
-    default: return launch_flash_fmt<10>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units);
+    VDN_FA_CASE(9); VDN_FA_CASE(10); VDN_FA_CASE(11); VDN_FA_CASE(12);
+    default: return launch_flash_fmt<13>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units);
   }
 #undef VDN_FA_CASE
 }
 }  // namespace vdn
+
+#ifdef VDN_FA_TIMELINE
+extern "C" int vdn_debug_fa_timeline(unsigned long long* host, int* counts) {
+  int zero[5] = {0, 0, 0, 0, 0};
+  cudaDeviceSynchronize();
+  if (host == nullptr) return cudaMemcpyToSymbol(vdn::g_fa_tl_n, zero, sizeof(zero)) != cudaSuccess;  // reset
+  if (cudaMemcpyFromSymbol(counts, vdn::g_fa_tl_n, sizeof(zero)) != cudaSuccess) return 1;
+  return cudaMemcpyFromSymbol(host, vdn::g_fa_tl, sizeof(unsigned long long) * 5 * vdn::FA_TL_CAP) != cudaSuccess;
+}
+#endif
 
 extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_stride, const void* k, int64_t ld_k, int64_t k_batch_stride,
                                  const void* vT, int64_t ld_vT, void* out, int32_t B, int32_t tokens_q, int32_t tokens_kv, int32_t heads,
