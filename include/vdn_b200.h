@@ -139,6 +139,15 @@ int vdn_readout_concat(const void* tok, int64_t tok_frame_pitch, const void* cls
                        int32_t C, void* stream);
 /* im2col for the 3x3 stride-2 pad-1 conv (dpt.py:84-89): NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] */
 int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* Head tail in one kernel (dpt_temporal.py:103-111, dpt.py:179-187): [bilinear resize to (H, W), align_corners=True ->]
+ * 3x3 conv 128 -> 32 (pad 1) + bias -> ReLU -> 1x1 conv 32 -> 1 + bias -> ReLU, one fp32 value per pixel.
+ * wpacked: the 3x3 filter as pre-swizzled tensor-core B tiles (packing.py::pack_conv_tail), 73728 bytes.
+ * vdn_conv_tail reads an already resized 16-bit NHWC map x [B, H, W, 128]; vdn_conv_tail_up resizes src [B, Hs, Ws, 128] on the fly
+ * (the full-resolution 128-channel map is never written). */
+int vdn_conv_tail(const void* x, const void* wpacked, const float* bias, const float* head_w, float head_b, float* out, int32_t B, int32_t H,
+                  int32_t W, void* stream);
+int vdn_conv_tail_up(const void* src, int32_t Hs, int32_t Ws, const void* wpacked, const float* bias, const float* head_w, float head_b, float* out,
+                     int32_t B, int32_t H, int32_t W, void* stream);
 /* bilinear resize, align_corners=True, NHWC 16-bit (F.interpolate at util/blocks.py:155-157, dpt_temporal.py:104-106).
  * optional second input added before interpolation is NOT supported; relu_out writes max(x,0). */
 int vdn_bilinear_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, int32_t relu_out,

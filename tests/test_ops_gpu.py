@@ -169,6 +169,52 @@ def test_output_conv2_stage_at_518(ops):
     assert float(rel) < 5e-3
 
 
+def _tail_ref(x_up_f32, w, bias, hw, hb):
+    mid = F.relu(F.conv2d(x_up_f32, w.float(), bias, padding=1))
+    return F.relu((mid * hw.view(1, 32, 1, 1)).sum(1) + hb)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 70, 84), (1, 37, 121), (3, 16, 30), (1, 130, 259)])
+def test_conv_tail_unfused(ops, B, H, W):
+    """vdn_conv_tail on an already resized map: 3x3 128 -> 32 + ReLU + 1x1 + ReLU against fp32 PyTorch on the same 16-bit operands
+    (widths below / at / across the 120-pixel strip, heights that do not divide into the row chunks)."""
+    from video_depth_normal_v2_b200 import packing
+    od = ops.operand_dtype()
+    x = _r16(ops, B, H, W, 128, seed=1)
+    w = _f32(32, 128, 3, 3, scale=(9 * 128) ** -0.5, seed=2).to(od)
+    bias, hw = _f32(32, seed=3), _f32(32, seed=4).abs()
+    wp = packing.pack_conv_tail({"c.weight": w.float()}, "c", "cuda", od)
+    out = torch.full((B, H, W), -1.0, device="cuda", dtype=torch.float32)
+    ops.conv_tail(x, wp, bias, hw, 0.05, out, B, H, W)
+    ref = _tail_ref(x.float().permute(0, 3, 1, 2), w, bias, hw, 0.05)
+    torch.cuda.synchronize()
+    _close(f"conv_tail {B}x{H}x{W}", out, ref, rtol=1e-4, atol_frac=1e-5)
+
+
+@pytest.mark.parametrize("B,Hs,Ws,H,W", [(2, 40, 48, 70, 84), (1, 296, 296, 518, 518), (1, 148, 264, 259, 462), (2, 8, 8, 14, 14)])
+def test_conv_tail_fused_upsample(ops, B, Hs, Ws, H, W):
+    """vdn_conv_tail_up (resize inside the kernel) against (a) vdn_bilinear_nhwc + vdn_conv_tail: bit-identical, the producer warps
+    repeat the resize kernel's arithmetic; (b) fp32 PyTorch (interpolate -> conv -> ReLU -> 1x1 -> ReLU) within the stage budget."""
+    from video_depth_normal_v2_b200 import packing
+    od = ops.operand_dtype()
+    x = (_r16(ops, B, Hs, Ws, 128, seed=1).float().abs() * 0.5).to(od)
+    w = _f32(32, 128, 3, 3, scale=(9 * 128) ** -0.5, seed=2).to(od)
+    bias, hw = _f32(32, seed=3) * 0.1, _f32(32, seed=4).abs()
+    wp = packing.pack_conv_tail({"c.weight": w.float()}, "c", "cuda", od)
+    up = torch.empty(B, H, W, 128, device="cuda", dtype=od)
+    ops.bilinear_nhwc(x, up, B, Hs, Ws, H, W, 128)
+    two_step = torch.empty(B, H, W, device="cuda", dtype=torch.float32)
+    ops.conv_tail(up, wp, bias, hw, 0.05, two_step, B, H, W)
+    fused = torch.full((B, H, W), -1.0, device="cuda", dtype=torch.float32)
+    ops.conv_tail(x, wp, bias, hw, 0.05, fused, B, H, W, src_hw=(Hs, Ws))
+    torch.cuda.synchronize()
+    assert torch.equal(fused, two_step), f"fused tail differs from resize + conv: max |diff| {float((fused - two_step).abs().max()):.3e}"
+    ref = _tail_ref(F.interpolate(x.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True), w, bias, hw, 0.05)
+    rel = ((fused - ref).abs() / ref.clamp_min(1e-3 * float(ref.max()))).max()
+    print(f"fused tail {Hs}x{Ws} -> {H}x{W}: max-rel {float(rel):.3e}")
+    assert float(rel) < 5e-3
+
+
 @pytest.mark.parametrize("s,Co", [(4, 48), (2, 96), (4, 256)])
 def test_gemm_pixel_shuffle_convtranspose(ops, s, Co):
     od = ops.operand_dtype()

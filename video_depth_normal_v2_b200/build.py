@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvdn_b200.so")
-SOURCES = ["vdn_host.cu", "vdn_gemm.cu", "vdn_attn.cu", "vdn_elem.cu", "vdn_v5.cu", "vdn_da2.cu"]
+SOURCES = ["vdn_host.cu", "vdn_gemm.cu", "vdn_attn.cu", "vdn_elem.cu", "vdn_v5.cu", "vdn_da2.cu", "vdn_tail.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas=-v",

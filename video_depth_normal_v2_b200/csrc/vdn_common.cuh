@@ -202,6 +202,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// The same wait for warps that share their sub-partition with busy warps: the thread is suspended for up to `ns` per attempt instead
+// of re-issuing try_wait + branch every few cycles (a spinning waiter takes issue slots from the warps it waits for).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } while (ok == 0);
+}
 
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads into shared memory, completing on an mbarrier

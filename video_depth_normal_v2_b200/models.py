@@ -302,6 +302,9 @@ def _fusion(rf, B, H, W, Ho, Wo, x0, x0_relu=None, x1=None, x1_relu=None, relu_c
     return up
 
 
+_FUSED_TAIL = os.environ.get("VDN_FUSED_TAIL", "1") != "0"  # evaluation switch: 0 = separate bilinear + implicit-GEMM output_conv2
+
+
 def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: int, T: Optional[int], stream: Optional[dict] = None) -> torch.Tensor:
     """-> depth fp32 [Bf, 14*ph, 14*pw] (after output_conv2's ReLUs).
     ``stream`` (Bf == 1): {"cached": per motion module, per attention block, the list of cached projections or None; "new": []}
@@ -370,9 +373,12 @@ def head_forward(head: dict, feats: List[torch.Tensor], Bf: int, ph: int, pw: in
     # ---- output convs (dpt_temporal.py:103-111): 3x3 F->F/2, bilinear to 14x, fused [3x3 -> ReLU -> 1x1 -> ReLU]
     o1 = _conv3(path1, head["oc1"], Bf, 2 * H1, 2 * W1)
     Ho, Wo = 14 * ph, 14 * pw
+    depth = _empty((Bf, Ho, Wo), torch.float32, dev)
+    if "oc2_tail" in head and _FUSED_TAIL:  # resize + 3x3 + ReLU + 1x1 + ReLU in one kernel: the 128-channel full-resolution map is never written
+        ops.conv_tail(o1, head["oc2_tail"], head["oc2"]["b"], head["oc2_head_w"], head["oc2_head_b"], depth, Bf, Ho, Wo, src_hw=(2 * H1, 2 * W1))
+        return depth
     up = _empty((Bf, Ho, Wo, Fe // 2), od, dev)
     ops.bilinear_nhwc(o1, up, Bf, 2 * H1, 2 * W1, Ho, Wo, Fe // 2)
-    depth = _empty((Bf, Ho, Wo), torch.float32, dev)
     _conv3(up, head["oc2"], Bf, Ho, Wo, out=depth, head_w=head["oc2_head_w"], head_b=head["oc2_head_b"])
     return depth
 

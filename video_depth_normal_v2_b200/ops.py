@@ -254,6 +254,22 @@ def bilinear_nhwc(x, out, B, H, W, Ho, Wo, C_, relu_out=False):
     return out
 
 
+def conv_tail(x, wpacked, bias, head_w, head_b: float, out, B: int, H: int, W: int, src_hw=None):
+    """3x3 conv 128 -> 32 + ReLU + 1x1 conv 32 -> 1 + ReLU -> fp32 [B, H, W] (dpt_temporal.py:107-111).  ``src_hw`` = (Hs, Ws): ``x`` is
+    output_conv1's [B, Hs, Ws, 128] map and the align_corners bilinear resize to (H, W) happens inside the kernel (the tensor-core operand
+    is produced in shared memory); without it ``x`` is the already resized [B, H, W, 128] map."""
+    od = operand_dtype()
+    flops = 2.0 * B * H * W * (9 * 128 * 32 + 32)
+    if src_hw is None:
+        rc = _run("conv_tail", "tensor", flops, lib().vdn_conv_tail, _ptr(x, od, "x"), _ptr(wpacked, od, "wpacked"), _ptr(bias, torch.float32, "bias"),
+                  _ptr(head_w, torch.float32, "head_w"), float(head_b), _ptr(out, torch.float32, "out"), B, H, W, _stream())
+    else:
+        rc = _run("conv_tail", "tensor", flops, lib().vdn_conv_tail_up, _ptr(x, od, "x"), int(src_hw[0]), int(src_hw[1]), _ptr(wpacked, od, "wpacked"),
+                  _ptr(bias, torch.float32, "bias"), _ptr(head_w, torch.float32, "head_w"), float(head_b), _ptr(out, torch.float32, "out"), B, H, W, _stream())
+    _check(rc, "vdn_conv_tail")
+    return out
+
+
 def bilinear_nhwc2(x, out, out_relu, B, H, W, Ho, Wo, C_):
     """out = bilinear(x), out_relu = relu(out) in one pass."""
     od = operand_dtype()

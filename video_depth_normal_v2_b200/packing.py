@@ -46,6 +46,22 @@ def pack_conv3x3(sd, name, dev, dt, bias=True):
     return d
 
 
+def pack_conv_tail(sd, name, dev, dt):
+    """(32, 128, 3, 3) -> the B operand of vdn_conv_tail as the tensor core reads it from shared memory: for each vertical tap dy and
+    each 64-channel chunk a K-major tile [96 rows = (dx, co)][64 ci] of 128-byte rows, 16-byte chunk j of row n stored at j ^ (n & 7)
+    (the 128B swizzle TMA would apply).  73728 bytes."""
+    w = sd[name + ".weight"].detach().float()
+    co, ci = w.shape[:2]
+    if (co, ci) != (32, 128):
+        raise ValueError(f"vdn_conv_tail is built for the 128 -> 32 output convolution, got {ci} -> {co}")
+    t = w.permute(2, 3, 0, 1).reshape(3, 96, 2, 8, 8)          # [dy][n = dx*32 + co][chunk][j][8 ci]
+    t = t.permute(0, 2, 1, 3, 4).contiguous()                   # [dy][chunk][n][j][8]
+    n = torch.arange(96, device=t.device).view(1, 1, 96, 1, 1)
+    j = torch.arange(8, device=t.device).view(1, 1, 1, 8, 1)
+    src_j = (j ^ (n & 7)).expand(3, 2, 96, 8, 8)                # position j holds logical chunk j ^ (n & 7)
+    return _w16(torch.gather(t, 3, src_j).reshape(-1), dev, dt)
+
+
 def pack_conv3x3_im2col(sd, name, dev, dt):
     """(Co, Ci, 3, 3) -> [Co, 9*Ci] matching vdn_im2col_3x3_s2's column order (tap-major, unpadded)."""
     w = sd[name + ".weight"].detach().float()
@@ -179,6 +195,8 @@ def pack_head(sd, prefix: str, cfg: dict, dev, dt, temporal: bool, pe_type: str 
         }
     head["oc1"] = pack_conv3x3(sd, s + "output_conv1", dev, dt)
     head["oc2"] = pack_conv3x3(sd, s + "output_conv2.0", dev, dt)
+    if tuple(sd[s + "output_conv2.0.weight"].shape[:2]) == (32, 128):
+        head["oc2_tail"] = pack_conv_tail(sd, s + "output_conv2.0", dev, dt)
     head["oc2_head_w"] = _f32(sd[s + "output_conv2.2.weight"].reshape(32), dev)
     head["oc2_head_b"] = float(sd[s + "output_conv2.2.bias"].reshape(()).item())
     if temporal:
