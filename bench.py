@@ -225,6 +225,7 @@ def main():
     from video_depth_normal_v2_b200 import video as V
     ops.set_operand_dtype(torch.float16 if args.operands == "fp16" else torch.bfloat16)
     peaks = _peaks()
+    ops.RIDGE_FLOP_PER_BYTE = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
 
     model = VideoDepthAnything(encoder=ENCODER, features=FEATURES, out_channels=OUT_CHANNELS).to(dev).eval()
     model.load_state_dict(synthetic_state_dict(model, 0))
@@ -296,8 +297,7 @@ def main():
     assert np.isfinite(y_np).all()
     h2d_total, d2h_total = sum_over_ranks(st_e2e["h2d_bytes"]), sum_over_ranks(st_e2e["d2h_bytes"])
     e2e = {"value": n_lv / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d_total / (K * world), "d2h_bytes_per_step": d2h_total / (K * world),
-           "ms_per_step": e2e_ms / K, "phases_rank0": {k: v["gpu_ms"] for k, v in (st_e2e.get("phases") or {}).items()} or None, "note": "model.infer_video_depth(uint8 frames in pinned host memory) -> float32 depth in (pinned) host memory; "
-                                              "bytes are per window-step per GPU"}
+           "ms_per_step": e2e_ms / K, "phases_rank0": {k: v["gpu_ms"] for k, v in (st_e2e.get("phases") or {}).items()} or None, "note": "infer_video_depth(uint8 frames in pinned host memory) -> fp32 depth in host memory; bytes per window-step per GPU"}
     del y_np, lv_dev
 
     # ---------------- BASELINE configs[4]: the 4096-frame clip, windows sharded over the N GPUs (strong scaling), end to end ----------------
@@ -316,8 +316,7 @@ def main():
                     "windows_this_rank": st4["windows"], "encoder_frames_all_ranks": int(enc4), "slot_forwards": wins4 * FRAMES,
                     "phases_rank0": st4.get("phases"),
                     "tensor_frac_ref_equiv": wins4 * FRAMES * GFLOP_PER_FRAME * 1e9 / (ms4 / 1e3) / 1e12 / (world * peaks["tflops"]),
-                    "note": "BASELINE configs[4]: infer_video_depth(shard, gather='shard') on 4096 synthetic uint8 frames in pinned host memory, one timed "
-                            "pass, result in host memory of the owning ranks; max over ranks"}
+                    "note": "infer_video_depth(shard, gather='shard'), uint8 frames in pinned host memory -> fp32 depth in host memory of the owning ranks; one timed pass, max over ranks"}
         del y4
     del clip_t, clip_np, lv_np
 
@@ -344,7 +343,7 @@ def main():
         w_ms /= args.window_steps
         window = {"value": world * FRAMES / (w_ms / 1e3), "unit": "slot-frames/s", "ms_per_window": w_ms,
                   "tensor_frac": GFLOP_PER_FRAME * 1e9 * FRAMES / (w_ms / 1e3) / 1e12 / peaks["tflops"],
-                  "note": "model.forward on a device-resident (1, 32, 3, 518, 518) window, every rank its own window (no reuse: 32 encoder frames)"}
+                  "note": "model.forward on a device-resident (1, 32, 3, 518, 518) window per rank (32 encoder frames)"}
 
     # ---------------- encoder alone (north_star: >= 60 % of dense tensor peak on the encoder) ----------------
     xe = x_dev[0]
@@ -432,7 +431,7 @@ def main():
         da2_ms /= n_da2
         da2 = {"value": world * args.da2_batch / (da2_ms / 1e3), "unit": "frames/s", "batch": args.da2_batch, "ms_per_call_full_bank": da2_ms,
                "ms_per_call_one_entry": first_ms, "tensor_frac": 1820.9e9 * args.da2_batch / (da2_ms / 1e3) / 1e12 / peaks["tflops"],
-               "note": "DepthAnythingV2 (memory-block fork) ViT-L 518x518, device-resident batch, full 6-entry memory bank, 1820.9 GFLOP/frame ref-equiv"}
+               "note": "DepthAnythingV2 ViT-L 518x518 (BASELINE configs[1]), device-resident batch, full 6-entry memory bank, 1820.9 GFLOP/frame ref-equiv"}
         del m2, xb
         torch.cuda.empty_cache()
 
@@ -452,9 +451,16 @@ def main():
         except Exception as exc:  # the CPU arm is a reported baseline; never lose the GPU line over it
             cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(exc)[-300:]}
     exec_tflop_per_step = (enc_frames_total / (K * world) * ENCODER_GFLOP_PER_FRAME + FRAMES * HEAD_GFLOP_PER_FRAME) / 1e3
+    # key order: the blocks a reader of a truncated line needs first (e2e, roofline, encoder, configs4, lv_parity), the long ones last
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.operands == "fp16" else "bf16", "data": "synthetic",
+        "e2e": e2e, "roofline": roofline, "gpu_launches": launches, "clocks": clocks, "encoder": encoder, "configs4": configs4, "lv_parity": lv_parity,
+        "da2_batch16": da2, "window": window, "stream": stream,
+        "tensor_frac_of_step": {"ref_equiv": FRAMES * GFLOP_PER_FRAME / 1e3 / (ms_per_step / 1e3) / peaks["tflops"],
+                                "executed": exec_tflop_per_step / (ms_per_step / 1e3) / peaks["tflops"], "executed_tflop_per_step": exec_tflop_per_step},
+        "phases_rank0": {k: v["gpu_ms"] for k, v in (st_dev.get("phases") or {}).items()} or None,
+        "cpu_baseline": cpu,
         "config": {"workload": f"VideoDepthAnything {ENCODER} long synthetic video {SIZE}x{SIZE} through infer_video_depth (BASELINE configs[4] path): "
                                f"{n_lv} uint8 frames = {K * world} overlapping 32-slot windows, {K} per GPU; one step = one window = 22 output frames "
                                f"(22 ViT frames + temporal head on 32 slots + alignment); configs[4] at 4096 frames is the configs4 block",
@@ -463,11 +469,7 @@ def main():
                    if world > 1 else "single GPU",
                    "l2": "activations per step (>2 GB) exceed the 126 MB L2, no explicit flush",
                    "operands": args.operands + " (fp32 accumulate, fp32 residual stream)", "warmup_note": f"2 untimed passes over the same clip = {2 * K} window-steps per GPU (>= the requested {args.warmup})"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "phases_rank0": {k: v["gpu_ms"] for k, v in (st_dev.get("phases") or {}).items()} or None,
-        "tensor_frac_of_step": {"ref_equiv": FRAMES * GFLOP_PER_FRAME / 1e3 / (ms_per_step / 1e3) / peaks["tflops"],
-                                "executed": exec_tflop_per_step / (ms_per_step / 1e3) / peaks["tflops"], "executed_tflop_per_step": exec_tflop_per_step},
-        "kernels": kernels, "stream": stream, "da2_batch16": da2, "window": window, "encoder": encoder, "lv_parity": lv_parity, "configs4": configs4,
+        "kernels": kernels,
     }
     head = {k: line[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step")}
     head.update(_round({k: v for k, v in line.items() if k not in head}))

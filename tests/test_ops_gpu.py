@@ -699,3 +699,18 @@ def test_gemm_many_m_tiles(ops, M):
     _close("qkv split q|k", qk, qkv[:, :2 * C])
     v_ref = qkv[:, 2 * C:].reshape(3, tokens, heads, 64).permute(0, 2, 3, 1).reshape(3 * heads, 64, tokens)
     _close("qkv split vT", vT[:, :, :tokens], v_ref)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 37, 37, 1024), (1, 5, 14, 384), (2, 9, 13, 768), (1, 4, 30, 1536), (1, 6, 7, 96)])
+def test_dwconv7_layernorm2d(ops, B, H, W, C):
+    """ConvNeXt front half of the memory fuser (sam2-style CXBlock: depthwise 7x7 pad 3 + LayerNorm2d over channels): the row-segment
+    kernel (C % 128 == 0) and the block-per-pixel fallback (C = 96) against fp32 PyTorch."""
+    x = _f32(B, H, W, C, seed=1)
+    w = _f32(C, 1, 7, 7, scale=1.0 / 7.0, seed=2)
+    bias, lw, lb = _f32(C, seed=3) * 0.1, 1.0 + 0.1 * _f32(C, seed=4), 0.1 * _f32(C, seed=5)
+    out = torch.empty(B, H, W, C, device="cuda", dtype=ops.operand_dtype())
+    ops.dwconv7_ln(x, w.reshape(C, 49).t().contiguous(), bias, lw, lb, out, B, H, W, C, 1e-6)
+    y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    ref = F.layer_norm(y, (C,), lw, lb, 1e-6)
+    torch.cuda.synchronize()
+    _close(f"dwconv7+LN {B}x{H}x{W}x{C}", out, ref)

@@ -4,6 +4,8 @@
 //   vdn_add_rowscalar  : x[r, :] += m[r]             (pix_feat + downsampled mask, memory_encoder.py:173)
 //   vdn_dwconv7_ln     : depthwise 7x7 conv + LayerNorm2d over channels, NHWC fp32 -> 16-bit rows (memory_encoder.py:96-99)
 //   vdn_mask_down1 / 2 : the two MaskDownSamplers on the 1-channel sigmoid(depth) map (memory_encoder.py:17-60, memory_block.py:68-71)
+#include <stdlib.h>
+
 #include "../../include/vdn_b200.h"
 #include "vdn_common.cuh"
 #include "vdn_host.h"
@@ -120,6 +122,92 @@ dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
   for (int i = 0; i < DW_MAXC; ++i) {
     const int c = threadIdx.x + i * 256;
     if (c < C) store16(out, pix * C + c, (acc[i] - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c), fmt);
+  }
+}
+
+// Row-segment form of the same op: a block owns DW_P consecutive pixels of one image row, a thread four channels.  Every input
+// vector of the 7 x (DW_P + 6) neighbourhood is loaded once and feeds up to 7 output pixels (the block-per-pixel kernel above read
+// 49 neighbours per output from L2: 8 TB/s of L2 traffic, 247 GB/s of algorithmic bytes).  LayerNorm2d over the channels of each pixel:
+// two block reductions for all DW_P pixels at once.  Needs C % 128 == 0 (blockDim = C / 4).
+constexpr int DW_P = 13;
+__global__ void __launch_bounds__(384)
+dwconv7_ln_row_kernel(const float4* __restrict__ x, const float4* __restrict__ w, const float4* __restrict__ bias, const float4* __restrict__ ln_w,
+                      const float4* __restrict__ ln_b, void* __restrict__ out, int H, int W, int C4, float eps, int fmt) {
+  const int segs = (W + DW_P - 1) / DW_P;
+  const int seg = blockIdx.x % segs;
+  const int yy = (blockIdx.x / segs) % H;
+  const long long img = blockIdx.x / ((long long)segs * H);
+  const int x0 = seg * DW_P;
+  const int c = threadIdx.x;  // channel vector
+  const float4* base = x + img * (long long)H * W * C4 + c;
+  float4 acc[DW_P];
+  const float4 b4 = __ldg(bias + c);
+#pragma unroll
+  for (int p = 0; p < DW_P; ++p) acc[p] = b4;
+  for (int dy = 0; dy < 7; ++dy) {
+    const int y2 = yy + dy - 3;
+    if (y2 < 0 || y2 >= H) continue;
+    float4 wt[7];
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) wt[dx] = __ldg(w + (dy * 7 + dx) * C4 + c);
+    const float4* row = base + (long long)y2 * W * C4;
+#pragma unroll
+    for (int xi = 0; xi < DW_P + 6; ++xi) {  // input column x0 - 3 + xi feeds output pixel p = xi - dx with tap dx
+      const int x2 = x0 - 3 + xi;
+      if (x2 < 0 || x2 >= W) continue;
+      const float4 v = __ldg(row + (long long)x2 * C4);
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        const int p = xi - dx;
+        if (p >= 0 && p < DW_P) {
+          acc[p].x = fmaf(v.x, wt[dx].x, acc[p].x);
+          acc[p].y = fmaf(v.y, wt[dx].y, acc[p].y);
+          acc[p].z = fmaf(v.z, wt[dx].z, acc[p].z);
+          acc[p].w = fmaf(v.w, wt[dx].w, acc[p].w);
+        }
+      }
+    }
+  }
+  __shared__ float red[12][DW_P];
+  __shared__ float stat[DW_P];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float invC = 1.0f / (float)(4 * C4);
+#pragma unroll
+  for (int p = 0; p < DW_P; ++p) {
+    const float s = warp_sum((acc[p].x + acc[p].y) + (acc[p].z + acc[p].w));
+    if (lane == 0) red[warp][p] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < DW_P) {
+    float t = 0.0f;
+    for (int i = 0; i < nwarps; ++i) t += red[i][threadIdx.x];
+    stat[threadIdx.x] = t * invC;
+  }
+  __syncthreads();
+  float mean[DW_P];
+#pragma unroll
+  for (int p = 0; p < DW_P; ++p) {
+    mean[p] = stat[p];
+    const float dx_ = acc[p].x - mean[p], dy_ = acc[p].y - mean[p], dz_ = acc[p].z - mean[p], dw_ = acc[p].w - mean[p];
+    const float q = warp_sum((dx_ * dx_ + dy_ * dy_) + (dz_ * dz_ + dw_ * dw_));
+    if (lane == 0) red[warp][p] = q;  // every warp has read stat[] into registers and red[] was consumed before the barrier above
+  }
+  __syncthreads();
+  if (threadIdx.x < DW_P) {
+    float t = 0.0f;
+    for (int i = 0; i < nwarps; ++i) t += red[i][threadIdx.x];
+    stat[threadIdx.x] = rsqrtf(t * invC + eps);
+  }
+  __syncthreads();
+  const float4 g = __ldg(ln_w + c), be = __ldg(ln_b + c);
+#pragma unroll
+  for (int p = 0; p < DW_P; ++p) {
+    if (x0 + p >= W) break;
+    const float rstd = stat[p];
+    const long long pix = (img * H + yy) * (long long)W + x0 + p;
+    const uint32_t lo = pack16((acc[p].x - mean[p]) * rstd * g.x + be.x, (acc[p].y - mean[p]) * rstd * g.y + be.y, fmt);
+    const uint32_t hi = pack16((acc[p].z - mean[p]) * rstd * g.z + be.z, (acc[p].w - mean[p]) * rstd * g.w + be.w, fmt);
+    reinterpret_cast<uint2*>(out)[pix * C4 + c] = make_uint2(lo, hi);
   }
 }
 
@@ -257,6 +345,15 @@ extern "C" int vdn_dwconv7_ln(const float* x, const float* w, const float* bias,
   VDN_STREAM;
   if (!x || !w || !bias || !ln_w || !ln_b || !out) return set_error("vdn_dwconv7_ln: null pointer");
   if (C <= 0 || C > 256 * DW_MAXC) return set_error("vdn_dwconv7_ln: C must be <= 1536");
+  static const bool v1 = [] { const char* e = getenv("VDN_DWCONV_V1"); return e && atoi(e) != 0; }();
+  if (C % 128 == 0 && !v1) {
+    const long long blocks = (long long)B * H * ((W + DW_P - 1) / DW_P);
+    dwconv7_ln_row_kernel<<<(unsigned)blocks, C / 4, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(w),
+                                                                reinterpret_cast<const float4*>(bias), reinterpret_cast<const float4*>(ln_w),
+                                                                reinterpret_cast<const float4*>(ln_b), out, H, W, C / 4, eps, get_operand_format());
+    count_launch();
+    return check_launch("dwconv7_ln_row_kernel");
+  }
   dwconv7_ln_kernel<<<(unsigned)((long long)B * H * W), 256, 0, stream>>>(x, w, bias, ln_w, ln_b, out, H, W, C, eps, get_operand_format());
   count_launch();
   return check_launch("dwconv7_ln_kernel");

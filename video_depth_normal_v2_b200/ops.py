@@ -97,6 +97,9 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
     return t.data_ptr()
 
 
+RIDGE_FLOP_PER_BYTE = 219.0  # MEASURED_PEAKS.json: 1417.6 TFLOP/s sustained / 6469.9 GB/s; bench.py overwrites it with the box's own figures
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: Optional[int] = None, ldw: Optional[int] = None,
          ldc: Optional[int] = None, conv: Optional[Tuple[int, int, int]] = None, bias=None, gamma=None, res=None, ld_res=None, res2=None,
          ld_res2=None, out2=None, out2_relu=False, ld_out2=None, act=ACT_NONE, geglu=False, row_map=ROWMAP_IDENTITY,
@@ -139,10 +142,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         d.head_w = _ptr(head_w, torch.float32, "head_w")
         d.head_b = float(head_b)
     flops = 2.0 * M * N * K * (9 if conv is not None else 1)
-    name = "gemm_conv3x3" if conv is not None else "gemm"
-    if _profiler is not None and _profiler.by_shape:
-        name = f"{name}[{M}x{N}x{K}{',f32out' if d.out_f32 else ''}{',act' + str(act) if act else ''}{',geglu' if geglu else ''}{',map' + str(row_map) if row_map else ''}]"
-    _check(_run(name, "tensor", flops, lib().vdn_gemm, C.byref(d), _stream()), "vdn_gemm")
+    name, kind, work = ("gemm_conv3x3" if conv is not None else "gemm"), "tensor", flops
+    if _profiler is not None:
+        # algorithmic bytes (every operand / result once); a GEMM whose arithmetic intensity is below the machine's ridge point
+        # (tensor peak / HBM peak, ~219 FLOP/B on B200) is bound by HBM: it is reported against that roofline, as its own family
+        nbytes = 2.0 * M * K + 2.0 * N * K * (9 if conv is not None else 1) + M * n_out * (4.0 if d.out_f32 else 2.0)
+        if res is not None:
+            nbytes += M * n_out * (4.0 if d.res_f32 else 2.0)
+        if res2 is not None:
+            nbytes += 2.0 * M * n_out
+        if out2 is not None:
+            nbytes += 2.0 * M * n_out
+        if flops / nbytes < RIDGE_FLOP_PER_BYTE:
+            name, kind, work = name + "_lowk", "hbm", nbytes
+        if _profiler.by_shape:
+            name = f"{name}[{M}x{N}x{K}{',f32out' if d.out_f32 else ''}{',act' + str(act) if act else ''}{',geglu' if geglu else ''}{',map' + str(row_map) if row_map else ''}]"
+    _check(_run(name, kind, work, lib().vdn_gemm, C.byref(d), _stream()), "vdn_gemm")
     return out
 
 
