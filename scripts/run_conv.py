@@ -25,6 +25,13 @@ conv_case("oc2   518x518 128->32 +head", 518, 518, 128, 32, head=True)
 conv_case("oc1   296x296 256->128", 296, 296, 256, 128)
 conv_case("rcu   148x148 256->256 relu", 148, 148, 256, 256, act=ops.ACT_RELU)
 conv_case("rcu    74x74  256->256 relu", 74, 74, 256, 256, act=ops.ACT_RELU)
+# what the residual epilogue of an RCU's second convolution costs (res = x, res2 = the other branch, out2 = relu copy for the next RCU)
+_res, _res2, _o2 = r16(B, 148, 148, 256), r16(B, 148, 148, 256), torch.empty(B, 148, 148, 256, device="cuda", dtype=od)
+conv_case("rcu   148x148 256->256 plain", 148, 148, 256, 256)
+conv_case("rcu   148x148 256->256 +out2relu", 148, 148, 256, 256, out2=_o2, out2_relu=True)
+conv_case("rcu   148x148 256->256 +res", 148, 148, 256, 256, res=_res)
+conv_case("rcu   148x148 256->256 +res+out2", 148, 148, 256, 256, res=_res, out2=_o2, out2_relu=True)
+conv_case("rcu   148x148 256->256 +res+res2+out2", 148, 148, 256, 256, res=_res, res2=_res2, out2=_o2, out2_relu=True)
 which = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, flops, fn in cases:
     if which and which not in name:

@@ -297,7 +297,7 @@ __device__ __forceinline__ void epi_head(const GemmKParams& p, const RowCtx& rc,
 }
 
 template <int BLOCK_N, int EPI, int FMT, int HALO = 0>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 1)  // registers are granted per warpgroup: 320 threads count as 384, i.e. 168 registers per thread (__maxnreg__(192) does not launch)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const __grid_constant__ CUtensorMap tmBh, const GemmKParams p) {
   // HALO == 2: plain GEMM on clusters of two CTAs that work on two M tiles of the same N block in lockstep; each CTA loads half of
