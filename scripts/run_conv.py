@@ -32,6 +32,9 @@ conv_case("rcu   148x148 256->256 +out2relu", 148, 148, 256, 256, out2=_o2, out2
 conv_case("rcu   148x148 256->256 +res", 148, 148, 256, 256, res=_res)
 conv_case("rcu   148x148 256->256 +res+out2", 148, 148, 256, 256, res=_res, out2=_o2, out2_relu=True)
 conv_case("rcu   148x148 256->256 +res+res2+out2", 148, 148, 256, 256, res=_res, res2=_res2, out2=_o2, out2_relu=True)
+# the same with both residuals read from ONE row (ld = 0: L1 / L2 hits, no DRAM latency): separates load latency from instruction / store cost
+conv_case("rcu   148x148 256->256 +res+res2+out2 (residual rows cached)", 148, 148, 256, 256, res=_res, ld_res=0, res2=_res2, ld_res2=0, out2=_o2, out2_relu=True)
+conv_case("rcu   148x148 256->256 +res (cached)", 148, 148, 256, 256, res=_res, ld_res=0)
 which = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, flops, fn in cases:
     if which and which not in name:
