@@ -541,6 +541,17 @@ def test_torch_ops_dispatch_to_the_kernels(ops):
     o2 = torch.empty(100, 384, device="cuda", dtype=od)
     torch.ops.vdn.layernorm(x, torch.ones(384, device="cuda"), torch.zeros(384, device="cuda"), o2, 1e-6)
     _close("torch.ops.vdn.layernorm", o2, F.layer_norm(x, (384,), eps=1e-6))
+    # the fused head tail through torch.ops against the ctypes wrapper
+    from video_depth_normal_v2_b200 import packing
+    xs = (_r16(ops, 1, 16, 24, 128, seed=5).float().abs() * 0.5).to(od)
+    w3 = _f32(32, 128, 3, 3, scale=(9 * 128) ** -0.5, seed=6).to(od)
+    wp = packing.pack_conv_tail({"c.weight": w3.float()}, "c", "cuda", od)
+    bias, hw = _f32(32, seed=7) * 0.1, _f32(32, seed=8).abs()
+    d1, d2 = torch.empty(1, 28, 42, device="cuda"), torch.empty(1, 28, 42, device="cuda")
+    torch.ops.vdn.head_tail_up(xs, wp, d1, bias, hw, 0.05)
+    ops.conv_tail(xs, wp, bias, hw, 0.05, d2, 1, 28, 42, src_hw=(16, 24))
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2)
 
 
 @pytest.mark.parametrize("H,W,size", [(90, 120, 84), (240, 426, 112), (56, 70, 56), (61, 47, 70)])

@@ -16,6 +16,7 @@ _DEFS = {
     "conv3x3": "(Tensor x, Tensor w, Tensor(a!) out, Tensor? bias=None, Tensor? res=None, int act=0) -> Tensor(a!)",
     "convT_ps": "(Tensor x, Tensor w, Tensor(a!) out, Tensor bias, int stride) -> Tensor(a!)",
     "head_tail": "(Tensor x, Tensor w, Tensor(a!) out, Tensor bias, Tensor head_w, float head_b) -> Tensor(a!)",
+    "head_tail_up": "(Tensor x, Tensor wpacked, Tensor(a!) out, Tensor bias, Tensor head_w, float head_b) -> Tensor(a!)",
     "layernorm": "(Tensor x, Tensor w, Tensor b, Tensor(a!) out, float eps) -> Tensor(a!)",
     "flash_attn": "(Tensor qk, Tensor vT, Tensor(a!) out, int B, int tokens, int heads) -> Tensor(a!)",
     "temporal_attn": "(Tensor qkv, Tensor(a!) out, int D, int T, int heads) -> Tensor(a!)",
@@ -52,6 +53,12 @@ def _convT_ps(x, w, out, bias, stride):
 def _head_tail(x, w, out, bias, head_w, head_b):
     B, H, W, Ci = x.shape
     return ops.gemm(x, w, out, M=B * H * W, N=w.shape[0], K=Ci, conv=(B, H, W), bias=bias, head_w=head_w, head_b=head_b)
+
+
+def _head_tail_up(x, wpacked, out, bias, head_w, head_b):
+    """x: output_conv1's [B, Hs, Ws, 128] map; out: [B, H, W] fp32; wpacked: packing.pack_conv_tail of output_conv2.0 (dpt_temporal.py:103-111)."""
+    B, Hs, Ws, _ = x.shape
+    return ops.conv_tail(x, wpacked, bias, head_w, head_b, out, B, out.shape[1], out.shape[2], src_hw=(Hs, Ws))
 
 
 def _layernorm(x, w, b, out, eps):
