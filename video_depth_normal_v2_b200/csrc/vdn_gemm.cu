@@ -28,7 +28,11 @@ namespace vdn {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int kNumEpiWarps = 8;
-constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
+// Three warpgroups: control (warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle) and two of epilogue warps.  Registers are granted
+// per warpgroup (a 320-thread block is budgeted as 384: 168 registers each, and __maxnreg__(192) does not launch), so the control
+// warpgroup hands most of its share to the epilogue with setmaxnreg: 128 x 56 + 256 x 224 = 64512 registers (no spills left, room for
+// two chunks of look-ahead on both residual streams).
+constexpr int kNumThreads = 128 + kNumEpiWarps * 32;
 constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - 2 * 256 * 4 /*bias+gamma*/;
 
 // EPI_PLAIN: bias / act / out (+out2), no residual operands (keeps registers free so the GELU chains interleave);
@@ -362,6 +366,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int it_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int it_end = CL ? ((p.num_m_tiles + 1) / 2) * p.num_n_blocks : num_tiles;
 
+  if (warp_idx < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");  // inside the branch it governs, or ptxas budgets every role for the minimum
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     // Producer and issuer warps run their (warp-uniform) loops with all lanes and elect one lane per issue: under a plain
@@ -563,9 +569,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     }
+  }
   } else {
     // ===================== epilogue warps =====================
-    const int e = warp_idx - 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+    const int e = warp_idx - 4;
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
     const int half = e >> 2;           // column half handled by this warp
     constexpr int kChunks = BLOCK_N / 32;
@@ -629,7 +637,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // stage this tile's bias / gamma slices in shared memory (all epilogue warps; named barrier 1)
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
       {
-        const int t = threadIdx.x - 64;
+        const int t = threadIdx.x - 128;
         if (t < BLOCK_N) {
           const int n = n_blk * BLOCK_N + t;
           if (p.bias != nullptr) sbias[t] = n < p.N ? __ldg(p.bias + n) : 0.0f;
@@ -716,20 +724,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       uint32_t accr[32];
       ResBuf rb0, rb1;  // only live in the EPI_RES instantiation
-      uint4 r2[4];
+      uint4 r2[4], r2b[4];  // second residual: two buffers, two chunks of look-ahead like the first (one chunk was not enough for DRAM latency)
       if constexpr (EPI == EPI_RES) {
         // residual operands of the first two chunks are requested before the accumulator is even ready
         if (c_begin < c_end) {
           prefetch_res(p, rc, nb + c_begin * 32, rb0);
           prefetch_res2(p, rc, nb + c_begin * 32, r2);
         }
-        if (c_begin + 1 < c_end) prefetch_res(p, rc, nb + (c_begin + 1) * 32, rb1);
+        if (c_begin + 1 < c_end) {
+          prefetch_res(p, rc, nb + (c_begin + 1) * 32, rb1);
+          prefetch_res2(p, rc, nb + (c_begin + 1) * 32, r2b);
+        }
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       if (c_begin < c_end) tmem_ld32(t_row + c_begin * 32, accr);
 
-      auto chunk = [&](int c, ResBuf& rb) {
+      auto chunk = [&](int c, ResBuf& rb, uint4 (&r2x)[4]) {
         tmem_ld_wait();
         const int n0 = nb + c * 32;
         float v[32];
@@ -764,7 +775,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (rc.valid && n0 < p.N) {
           if constexpr (EPI == EPI_RES) {
-            epi_plain<FMT>(p, rc, n0, c * 32, v, rb, r2, (c + 2 < c_end) ? nb + (c + 2) * 32 : -1, (c + 1 < c_end) ? nb + (c + 1) * 32 : -1, sgamma);
+            epi_plain<FMT>(p, rc, n0, c * 32, v, rb, r2x, (c + 2 < c_end) ? nb + (c + 2) * 32 : -1, (c + 2 < c_end) ? nb + (c + 2) * 32 : -1, sgamma);
           } else if constexpr (EPI == EPI_PLAIN) {
             epi_noresidual<FMT>(p, rc, n0, v);
           } else if constexpr (EPI == EPI_QKV) {
@@ -780,8 +791,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
 #pragma unroll 1
       for (int c = c_begin; c < c_end; c += 2) {
-        chunk(c, rb0);
-        if (c + 1 < c_end) chunk(c + 1, rb1);
+        chunk(c, rb0, r2);
+        if (c + 1 < c_end) chunk(c + 1, rb1, r2b);
       }
       tc_fence_before();
       if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty_bar[acc]), 0));
