@@ -27,12 +27,13 @@ constexpr int FA_D = 64;       // head dim
 constexpr int FA_GROUPS = 2;   // query tiles per CTA, processed ping-pong by two softmax warpgroups
 constexpr int FA_THREADS = FA_GROUPS * 128 + 128;  // + one control warpgroup: MMA issuer warp, TMA producer warp, 2 idle warps
 constexpr int FA_TILE = FA_BM * FA_D * 2;         // 16 KB : one Q / K / V^T tile
-constexpr int FA_SMEM = 2 * FA_TILE /*Q*/ + 2 * FA_TILE /*K x2*/ + 2 * FA_TILE /*V^T x2*/ + 256;
+constexpr int FA_VSTAGE_MAX = 2 * 80 * 128;        // a V^T stage of the ones-column form: 2 chunks of [80 rows x 64 keys]
+constexpr int FA_SMEM = 2 * FA_TILE /*Q*/ + 2 * FA_TILE /*K x2*/ + 2 * FA_VSTAGE_MAX /*V^T x2*/ + 256;
 #ifndef VDN_FA_POLY
 #define VDN_FA_POLY 2
 #endif
 constexpr int FA_POLY = VDN_FA_POLY;  // of every 8 scores, this many take 2^x on the FMA pipe (exp2_poly), the rest on the XU pipe
-constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
+constexpr int FA_TMEM_COLS = 512;  // 128-key tiles: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512); 112-key (ones-column) tiles: S 2 x 112, O 2 x 80, P 2 x 56
 
 // ---- packed fp32 arithmetic (Blackwell FFMA2 / FADD2 on 64-bit register pairs) and the 3-input FMNMX3 for the softmax warps ----
 typedef unsigned long long f32x2_t;
@@ -75,7 +76,10 @@ __device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
 // traces): late wait for PV(j-1), two issuers, and a software-pipelined softmax (loads + row max of tile j+1 inside the exp phase of
 // tile j, S issued as two 64-key halves) all measured slower than variant 6 — two softmax warps per sub-partition get the same
 // exp throughput whether they alternate or overlap (~1150 cycles per 128-score warp tile), so only fewer issue cycles per score help.
-struct FaVariant { int packed, max3, poly16, polypk, latewait, token, dbg, mma2; };  // dbg (timing experiments only, wrong results): 1 = no exp, 2 = no row max, 3 = neither
+//   ones    : KV tiles of 112 keys and a ones row appended to every V^T tile: O gets a 65th column that accumulates the row sum of the
+//             (16-bit rounded) probabilities on the tensor core, so the softmax warps drop one packed add per two scores.  TMEM:
+//             S 2 x 112, O 2 x 80, P 2 x 56 = 496 columns (128-key tiles would need 544)
+struct FaVariant { int packed, max3, poly16, polypk, latewait, token, dbg, mma2, ones; };  // dbg (timing experiments only, wrong results): 1 = no exp, 2 = no row max, 3 = neither
 __host__ __device__ constexpr FaVariant fa_variant(int v) {
   return v == 0 ? FaVariant{0, 0, 2 * FA_POLY, 0, 0, 0}   // round-1 kernel
        : v == 1 ? FaVariant{1, 1, 4, 1, 0, 1}
@@ -90,7 +94,14 @@ __host__ __device__ constexpr FaVariant fa_variant(int v) {
        : v == 10 ? FaVariant{1, 1, 4, 1, 0, 0, 3}
        : v == 11 ? FaVariant{1, 1, 4, 1, 1, 0}            // half of tile j's exponentials before the wait for PV(j-1), no token
        : v == 12 ? FaVariant{1, 1, 4, 1, 0, 0, 0, 1}      // one MMA issuer warp per softmax group
-                 : FaVariant{1, 1, 4, 1, 0, 0, 1, 1};     // timing only: 12 without exp
+       : v == 13 ? FaVariant{1, 1, 4, 1, 0, 0, 1, 1}      // timing only: 12 without exp
+       : v == 14 ? FaVariant{1, 1, 4, 1, 0, 0, 0, 0, 1}   // row sum on the tensor core (ones column), 112-key tiles
+       : v == 15 ? FaVariant{1, 1, 3, 1, 0, 0, 0, 0, 1}
+       : v == 16 ? FaVariant{1, 1, 5, 1, 0, 0, 0, 0, 1}
+       : v == 17 ? FaVariant{1, 1, 4, 1, 0, 0, 1, 0, 1}   // timing only: 14 without exp
+       : v == 18 ? FaVariant{1, 1, 6, 1, 0, 0, 0, 0, 1}
+       : v == 19 ? FaVariant{1, 1, 7, 1, 0, 0, 0, 0, 1}
+                 : FaVariant{1, 1, 8, 1, 0, 0, 0, 0, 1};
 }
 template <int VAR> constexpr FaVariant kFaVar = fa_variant(VAR);
 
@@ -110,9 +121,9 @@ __device__ __forceinline__ void fa_tl(int slot, int ev, int lane, int& n) {
 #else
 #define FA_TL(slot, ev)
 #endif
-constexpr int FA_NUM_VARIANTS = 14;
+constexpr int FA_NUM_VARIANTS = 21;
 #ifndef VDN_FA_DEFAULT_VARIANT
-#define VDN_FA_DEFAULT_VARIANT 6
+#define VDN_FA_DEFAULT_VARIANT 16
 #endif
 
 
@@ -136,9 +147,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   void* __restrict__ out, int tokens, int tokens_kv, int heads, int C, int num_units) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                      // [group]
+  constexpr bool ONES = kFaVar<VAR>.ones != 0;
+  constexpr int BN = ONES ? 112 : FA_BN;       // keys per tile
+  constexpr int OC = ONES ? 80 : FA_D;         // O columns / V^T rows per MMA: head dim (+ the ones row, padded to 16)
+  constexpr int VCH = OC * 128;                // bytes of one V^T chunk [OC rows x 64 keys]
+  constexpr int VST = 2 * VCH;                 // bytes of one V^T stage
+  constexpr uint32_t T_O = 2 * BN, T_P = 2 * BN + 2 * OC;  // TMEM columns: S_g at g BN, O_g at T_O + g OC, P_g at T_P + g BN / 2
   uint8_t* sK = smem + 2 * FA_TILE;        // [stage]
-  uint8_t* sV = smem + 4 * FA_TILE;        // [stage], each = 2 chunks [64 d rows x 64 keys]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * FA_TILE);
+  uint8_t* sV = smem + 4 * FA_TILE;        // [stage], each = 2 chunks [OC d rows x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * FA_TILE + 2 * FA_VSTAGE_MAX);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
@@ -158,7 +175,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #ifdef VDN_FA_TIMELINE
   int tl_n = 0;
 #endif
-  const int nt = (tokens_kv + FA_BN - 1) / FA_BN;  // KV tiles (cross-attention: tokens_kv != tokens)
+  const int nt = (tokens_kv + BN - 1) / BN;  // KV tiles (cross-attention: tokens_kv != tokens)
   const int nq_tiles = (tokens + FA_BM - 1) / FA_BM;
   const int nqp = (nq_tiles + FA_GROUPS - 1) / FA_GROUPS;  // query-tile pairs per (frame, head)
 
@@ -188,6 +205,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     __syncwarp();
     tmem_alloc(tmem_ptr_smem, FA_TMEM_COLS);
+  }
+  if constexpr (ONES) {
+    // rows 64..79 of every V^T chunk are constant: row 64 = 1.0 for every key (O column 64 accumulates the row sum of P), rows 65..79
+    // = 0.  TMA only ever writes rows 0..63.
+    const uint32_t one2 = FMT ? 0x3F803F80u : 0x3C003C00u;
+    for (int i = threadIdx.x; i < 4 * 128; i += FA_THREADS) {  // 4 regions (2 stages x 2 chunks) of 16 rows x 128 B, 16 bytes per item
+      const int region = i >> 7, piece = i & 127;
+      const uint32_t v = piece < 8 ? one2 : 0u;
+      *reinterpret_cast<uint4*>(sV + (region >> 1) * VST + (region & 1) * VCH + 64 * 128 + piece * 16) = make_uint4(v, v, v, v);
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -221,16 +249,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait(&k_empty[st], ph ^ 1);
         FA_TL(3, 31);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[st], FA_TILE);
-          tma_load_4d(sK + st * FA_TILE, &tmK, &k_full[st], 0, h, j * FA_BN, b);
+          mbar_arrive_expect_tx(&k_full[st], BN * 128);
+          tma_load_4d(sK + st * FA_TILE, &tmK, &k_full[st], 0, h, j * BN, b);
         }
         __syncwarp();
         mbar_wait(&v_empty[st], ph ^ 1);
         FA_TL(3, 32);
         if (elect_one()) {
           mbar_arrive_expect_tx(&v_full[st], FA_TILE);
-          tma_load_3d(sV + st * FA_TILE, &tmVT, &v_full[st], j * FA_BN, 0, b * heads + h);
-          tma_load_3d(sV + st * FA_TILE + FA_TILE / 2, &tmVT, &v_full[st], j * FA_BN + 64, 0, b * heads + h);
+          tma_load_3d(sV + st * VST, &tmVT, &v_full[st], j * BN, 0, b * heads + h);
+          tma_load_3d(sV + st * VST + VCH, &tmVT, &v_full[st], j * BN + 64, 0, b * heads + h);
         }
         __syncwarp();
       }
@@ -247,8 +275,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int gb = MMA2 ? (warp_idx - 8) >> 1 : 0;       // first group served by this warp
     const int ge = MMA2 ? gb + 1 : FA_GROUPS;            // one past the last
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, 128);
-    constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, 64);
+    constexpr uint32_t idesc_s = make_idesc(FMT ? 1u : 0u, 128, BN);
+    constexpr uint32_t idesc_pv = make_idesc(FMT ? 1u : 0u, 128, OC);
     const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
     int kv0 = 0, ui = 0;
     int si[2] = {0, 0};  // S tiles issued per group (global): S tile n may overwrite the buffer once tile n-1 was pulled into registers
@@ -270,7 +298,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const uint64_t dq = make_sdesc_sw128(q_addr + g * FA_TILE);
           const uint64_t dk = make_sdesc_sw128(k_addr + kst * FA_TILE);
 #pragma unroll
-          for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tb + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < FA_D / 16; ++kk) umma_f16(tb + g * BN, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
           umma_commit(&s_full[g]);
           if (g == gl - 1) {
             umma_commit(&k_empty[kst]);
@@ -313,13 +341,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (j == 0 && ug[g] > 0) mbar_wait(&o_free[g], (ug[g] - 1) & 1);  // the group has read the previous unit's O
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t dv0 = make_sdesc_sw128(v_addr + vst * FA_TILE);
+            const uint64_t dv0 = make_sdesc_sw128(v_addr + vst * VST);
 #pragma unroll
-            for (int kk = 0; kk < FA_BN / 16; ++kk) {
+            for (int kk = 0; kk < BN / 16; ++kk) {
               // B = V^T chunk (kk >> 2), 16 keys further per MMA; A = P_g from TMEM (16 keys = 8 packed columns per MMA);
               // O accumulates in TMEM across KV tiles
-              const uint64_t dv = dv0 + uint64_t(((kk >> 2) * (FA_TILE / 2)) >> 4) + 2 * (kk & 3);
-              umma_f16_ts(tb + 256 + g * 64, tb + 384 + g * 64 + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+              const uint64_t dv = dv0 + uint64_t(((kk >> 2) * VCH) >> 4) + 2 * (kk & 3);
+              umma_f16_ts(tb + T_O + g * OC, tb + T_P + g * (BN / 2) + kk * 8, dv, idesc_pv, (j | kk) != 0 ? 1u : 0u);
             }
             umma_commit(&pv_done[g]);
             if (g == gl - 1) umma_commit(&v_empty[vst]);
@@ -341,9 +369,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int g = warp_idx >> 2;
     const int r = threadIdx.x & 127;  // row in the query tile == TMEM lane
     const uint32_t lane_off = uint32_t((warp_idx & 3) * 32) << 16;
-    const uint32_t tmem_S = tmem_base + g * 128 + lane_off;
-    const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
-    const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_off;
+    const uint32_t tmem_S = tmem_base + g * BN + lane_off;
+    const uint32_t tmem_O = tmem_base + T_O + g * OC + lane_off;
+    const uint32_t tmem_P = tmem_base + T_P + g * (BN / 2) + lane_off;
+    constexpr int N3 = ONES ? 16 : 32;  // scores of the fourth register block
     const float sc = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     int t = 0;   // tiles processed by this group (global)
     int tn = 0;  // exp-phase turns taken by this group (global; includes the empty turns of group 1 in single-tile units)
@@ -361,7 +390,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       float m = -INFINITY, l = 0.0f;
       for (int j = 0; j < nt; ++j, ++t) {
-        const int nvalid = min(FA_BN, tokens_kv - j * FA_BN);
+        const int nvalid = min(BN, tokens_kv - j * BN);
         FA_TL(g, 1);
         mbar_wait(&s_full[g], t & 1);
         FA_TL(g, 2);
@@ -370,18 +399,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_ld32(tmem_S + 0, s0);
         tmem_ld32(tmem_S + 32, s1);
         tmem_ld32(tmem_S + 64, s2);
-        tmem_ld32(tmem_S + 96, s3);
+        if constexpr (ONES) tmem_ld16(tmem_S + 96, reinterpret_cast<uint32_t (&)[16]>(s3));
+        else tmem_ld32(tmem_S + 96, s3);
         tmem_ld_wait();
         FA_TL(g, 3);
         tc_fence_before();
         mbar_arrive(&s_free[g]);  // S(j) is out of TMEM: the issuer may overwrite it with S(j+2)
-        if (nvalid < FA_BN) {     // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
+        if (nvalid < BN) {     // last KV tile: keys beyond the sequence are zero-filled by TMA -> mask them out
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i >= nvalid) s0[i] = 0xff800000u;
             if (32 + i >= nvalid) s1[i] = 0xff800000u;
             if (64 + i >= nvalid) s2[i] = 0xff800000u;
-            if (96 + i >= nvalid) s3[i] = 0xff800000u;
+            if (i < N3 && 96 + i >= nvalid) s3[i] = 0xff800000u;
           }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -393,7 +423,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mx0 = max3f(mx0, __uint_as_float(s0[i]), __uint_as_float(s0[i + 1]));
             mx1 = max3f(mx1, __uint_as_float(s1[i]), __uint_as_float(s1[i + 1]));
             mx2 = max3f(mx2, __uint_as_float(s2[i]), __uint_as_float(s2[i + 1]));
-            mx3 = max3f(mx3, __uint_as_float(s3[i]), __uint_as_float(s3[i + 1]));
+            if (i < N3) mx3 = max3f(mx3, __uint_as_float(s3[i]), __uint_as_float(s3[i + 1]));
           }
         } else {
 #pragma unroll
@@ -401,7 +431,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
             mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
             mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
-            mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+            if (i < N3) mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
           }
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
@@ -429,6 +459,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                 tmem_st32(tmem_O + c * 32, o);
               }
+              if constexpr (ONES) {  // the row-sum column (and its padding) is rescaled with O
+                uint32_t o[16];
+                tmem_ld16(tmem_O + 64, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st16(tmem_O + 64, o);
+              }
               tmem_st_wait();
             }
           }
@@ -445,7 +483,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         auto emit = [&](const uint32_t (&sv)[32], int c) {
           if constexpr (kFaVar<VAR>.packed) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {  // 16 scores at a time
+            for (int q = 0; q < ((ONES && c == 3) ? 1 : 2); ++q) {  // 16 scores at a time (112-key tiles: the fourth block has 16)
               float pv[16];
 #pragma unroll
               for (int i = 0; i < 16; i += 2)
@@ -465,7 +503,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               }
               const f32x2_t a = add2(add2(pk2(pv[0], pv[1]), pk2(pv[2], pv[3])), add2(pk2(pv[4], pv[5]), pk2(pv[6], pv[7])));
               const f32x2_t b2 = add2(add2(pk2(pv[8], pv[9]), pk2(pv[10], pv[11])), add2(pk2(pv[12], pv[13]), pk2(pv[14], pv[15])));
-              sum2 = add2(sum2, add2(a, b2));
+              if constexpr (!ONES) sum2 = add2(sum2, add2(a, b2));  // ONES: the tensor core sums the rounded probabilities (O column 64)
 #pragma unroll
               for (int i = 0; i < 8; ++i) pk[(c & 1) * 16 + q * 8 + i] = T16f<FMT>::pack(pv[2 * i], pv[2 * i + 1]);
             }
@@ -494,7 +532,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_arrive(&tok[g]);
           ++tn;
         }
-        tmem_st32(tmem_P + 32, pk);
+        if constexpr (ONES) {  // 48 probabilities = 24 words
+          tmem_st16(tmem_P + 32, reinterpret_cast<const uint32_t (&)[16]>(pk));
+          tmem_st8(tmem_P + 48, reinterpret_cast<const uint32_t (&)[8]>(pk[16]));
+        } else {
+          tmem_st32(tmem_P + 32, pk);
+        }
         m = m_new;
         if constexpr (kFaVar<VAR>.packed) up2(sum2, sum0, sum1);
         l += sum0 + sum1;
@@ -508,6 +551,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       const int q_row = (q_tile0 + g) * FA_BM + r;
       const bool ok = q_row < tokens;
+      if constexpr (ONES) {
+        uint32_t v16[16];
+        tmem_ld16(tmem_O + 64, v16);
+        tmem_ld_wait();
+        l = __uint_as_float(v16[0]);
+      }
       const float inv = 1.0f / l;
       uint16_t* o = reinterpret_cast<uint16_t*>(out) + ((long long)b * tokens + q_row) * C + h * FA_D;
 #pragma unroll
@@ -1133,8 +1182,9 @@ static int launch_flash_variant(int variant, int fmt, int grid, cudaStream_t str
 #define VDN_FA_CASE(V) case V: return launch_flash_fmt<V>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units)
   switch (variant) {
     VDN_FA_CASE(0); VDN_FA_CASE(1); VDN_FA_CASE(2); VDN_FA_CASE(3); VDN_FA_CASE(4); VDN_FA_CASE(5); VDN_FA_CASE(6); VDN_FA_CASE(7); VDN_FA_CASE(8);
-    VDN_FA_CASE(9); VDN_FA_CASE(10); VDN_FA_CASE(11); VDN_FA_CASE(12);
-    default: return launch_flash_fmt<13>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units);
+    VDN_FA_CASE(9); VDN_FA_CASE(10); VDN_FA_CASE(11); VDN_FA_CASE(12); VDN_FA_CASE(13); VDN_FA_CASE(14); VDN_FA_CASE(15); VDN_FA_CASE(16);
+    VDN_FA_CASE(17); VDN_FA_CASE(18); VDN_FA_CASE(19);
+    default: return launch_flash_fmt<20>(fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, units);
   }
 #undef VDN_FA_CASE
 }
@@ -1161,6 +1211,12 @@ extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_st
   if ((q_batch_stride * 2) % 16 != 0 || (k_batch_stride * 2) % 16 != 0) return set_error("vdn_flash_attn: batch strides must be 16-byte aligned");
   if (ld_vT < tokens_kv || (ld_vT * 2) % 16 != 0) return set_error("vdn_flash_attn: ld_vT must be >= tokens_kv and a multiple of 8");
   const int fmt = get_operand_format();
+  static const int variant = [] {
+    const char* env = getenv("VDN_FA_VARIANT");
+    const int v = env ? atoi(env) : VDN_FA_DEFAULT_VARIANT;
+    return v < 0 || v >= FA_NUM_VARIANTS ? VDN_FA_DEFAULT_VARIANT : v;
+  }();
+  const int bn = fa_variant(variant).ones ? 112 : FA_BN;  // keys per tile of the chosen kernel
   CUtensorMap tmQ, tmK, tmVT;
   {
     // element (b, t, h, d); innermost first: d, h, t, b
@@ -1172,7 +1228,7 @@ extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_st
   {
     const uint64_t dims[4] = {(uint64_t)FA_D, (uint64_t)heads, (uint64_t)tokens_kv, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)FA_D * 2, (uint64_t)ld_k * 2, (uint64_t)k_batch_stride * 2};
-    const uint32_t box[4] = {(uint32_t)FA_D, 1, (uint32_t)FA_BN, 1};
+    const uint32_t box[4] = {(uint32_t)FA_D, 1, (uint32_t)bn, 1};
     if (make_tensor_map(&tmK, k, fmt, 4, dims, strides, box)) return 1;
   }
   {
@@ -1185,11 +1241,6 @@ extern "C" int vdn_flash_attn_ex(const void* q, int64_t ld_q, int64_t q_batch_st
   const long long units = (long long)((tokens_q + FA_GROUPS * FA_BM - 1) / (FA_GROUPS * FA_BM)) * heads * B;
   if (units > 0x7fffffffLL) return set_error("vdn_flash_attn: too many work units");
   const int grid = units < num_sms() ? (int)units : num_sms();
-  static const int variant = [] {
-    const char* env = getenv("VDN_FA_VARIANT");
-    const int v = env ? atoi(env) : VDN_FA_DEFAULT_VARIANT;
-    return v < 0 || v >= FA_NUM_VARIANTS ? VDN_FA_DEFAULT_VARIANT : v;
-  }();
   return launch_flash_variant(variant, fmt, grid, stream, tmQ, tmK, tmVT, out, tokens_q, tokens_kv, heads, C, (int)units);
 }
 
