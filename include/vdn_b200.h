@@ -126,6 +126,12 @@ int vdn_groupnorm_stats(const void* x, float* stats, int32_t frames, int32_t D, 
 int vdn_groupnorm_apply_tc(const void* x, const float* stats, const float* w, const float* b, void* out, int32_t Bv, int32_t T, int32_t D,
                            int32_t C, int32_t groups, void* stream);
 
+/* both of the above in one call: statistics (written to stats[frames*groups*2] as well) + affine + transpose.  One cluster launch
+   (8 CTAs per frame, distributed-shared-memory merge of the statistics) for C in {256, 512, 1024, 2048} with 8 or more frames;
+   every other shape runs the two kernels above.  motion_module.py:103-115 */
+int vdn_groupnorm_to_tc(const void* x, const float* w, const float* b, void* out, float* stats, int32_t Bv, int32_t T, int32_t D, int32_t C,
+                        int32_t groups, float eps, void* stream);
+
 /* ---- layout / elementwise ------------------------------------------------------------------------ */
 /* fp32 NCHW image [B,3,H,W] -> 16-bit patch rows [B*ph*pw, Kp] (Kp >= 588, zero padded), col = c*196 + i*14 + j. patch_embed.py:76 */
 int vdn_patch_im2col(const float* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Kp, void* stream);

@@ -361,6 +361,50 @@ def test_groupnorm_transpose(ops, Bv, T, D, C):
     _close("groupnorm+transpose", out, ref)
 
 
+@pytest.mark.parametrize("Bv,T,D,C", [(1, 32, 361, 1024), (2, 8, 50, 256), (1, 9, 5, 512), (1, 32, 1369, 256), (1, 16, 1369, 1024), (1, 8, 64, 2048),
+                                      (1, 4, 30, 192), (1, 2, 100, 1024), (1, 12, 33, 768)])
+def test_groupnorm_to_tc_single_launch(ops, Bv, T, D, C):
+    """vdn_groupnorm_to_tc (one cluster launch for C in {256, 512, 1024, 2048} with >= 8 frames, the two kernels otherwise) against
+    F.group_norm, with a mean far from zero (the single-pass statistics are Welford / Chan merges, not E[x^2] - mean^2) and against the
+    two-kernel form's statistics."""
+    od = ops.operand_dtype()
+    x = (_f32(Bv * T, D, C, scale=0.5, seed=1) + 6.0).to(od)
+    x[:, :, : C // 2] *= -0.25  # groups with different means and spreads
+    w, b = _f32(C, seed=2), _f32(C, seed=3)
+    stats = torch.zeros(Bv * T * 32 * 2, device="cuda")
+    out = torch.empty(Bv * D * T, C, device="cuda", dtype=od)
+    ops.groupnorm_to_tc(x, w, b, out, stats, Bv, T, D, C, 32, 1e-6)
+    stats2 = torch.empty_like(stats)
+    ops.groupnorm_stats(x, stats2, Bv * T, D, C, 32, 1e-6)
+    torch.cuda.synchronize()
+    xf = x.float().reshape(Bv * T, D, 32, C // 32).permute(0, 2, 1, 3).reshape(Bv * T, 32, -1).double()
+    mean, var = xf.mean(-1), xf.var(-1, unbiased=False)
+    st = stats.reshape(Bv * T, 32, 2).double()
+    assert float((st[..., 0] - mean).abs().max()) < 1e-5 * float(mean.abs().max())
+    assert float((st[..., 1] * torch.sqrt(var + 1e-6) - 1).abs().max()) < 2e-5
+    assert float((stats - stats2).abs().max()) < 1e-4 * float(stats2.abs().max())
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, w, b, 1e-6).permute(0, 2, 1)
+    ref = ref.reshape(Bv, T, D, C).permute(0, 2, 1, 3).reshape(Bv * D * T, C)
+    _close("groupnorm_to_tc", out, ref)
+    out2 = torch.empty_like(out)
+    ops.groupnorm_to_tc(x, w, b, out2, stats2, Bv, T, D, C, 32, 1e-6)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and torch.equal(stats, stats2)  # fixed merge order: bit-identical run to run
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 42, 56), (1, 28, 630), (3, 14, 14), (2, 70, 1148)])
+def test_patch_im2col_row_form(ops, B, H, W):
+    """one, two (45 = 23 + 22 patches per row) and three segments per patch row; bit-identical to the rounded unfold"""
+    img = _f32(B, 3, H, W, seed=5)
+    P = (H // 14) * (W // 14)
+    out = torch.full((B * P, 592), 7.0, device="cuda", dtype=ops.operand_dtype())
+    ops.patch_im2col(img, out, B, H, W, 592)
+    torch.cuda.synchronize()
+    ref = F.unfold(img, kernel_size=14, stride=14).transpose(1, 2).reshape(B * P, 588).to(ops.operand_dtype())
+    assert torch.equal(out[:, :588], ref)
+    assert (out[:, 588:] == 0).all()
+
+
 def test_patch_im2col_and_cls(ops):
     B, H, W, C = 2, 42, 56, 384
     img = _f32(B, 3, H, W, seed=1)
@@ -379,9 +423,9 @@ def test_patch_im2col_and_cls(ops):
     assert (x.reshape(B, P + 1, C)[:, 1:] == 0).all()
 
 
-def test_im2col_3x3_s2(ops):
+@pytest.mark.parametrize("B,H,W,C", [(2, 37, 23, 64), (1, 9, 7, 1024), (1, 5, 6, 2048), (3, 4, 4, 8), (1, 37, 37, 384), (2, 1, 1, 256)])
+def test_im2col_3x3_s2(ops, B, H, W, C):
     od = ops.operand_dtype()
-    B, H, W, C = 2, 37, 23, 64
     x = _r16(ops, B, H, W, C, seed=1)
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty(B * Ho * Wo, 9 * C, device="cuda", dtype=od)
@@ -668,6 +712,21 @@ def test_outputs_stay_inside_their_buffers(ops):
     out, chk = _guarded((Bv * D * T, C), od)
     ops.groupnorm_apply_tc(x, stats, _f32(C, seed=4), _f32(C, seed=5), out, Bv, T, D, C, 32)
     chk("groupnorm_apply_tc")
+    Bv, T, D, C = 1, 9, 11, 256  # the single-launch form: 8 CTAs per frame, three of them without a row
+    x = _r16(ops, Bv * T, D, C, seed=3)
+    out, chk = _guarded((Bv * D * T, C), od)
+    st, chk2 = _guarded((Bv * T * 32 * 2,), torch.float32)
+    ops.groupnorm_to_tc(x, _f32(C, seed=4), _f32(C, seed=5), out, st, Bv, T, D, C, 32, 1e-6)
+    chk("groupnorm_to_tc out"); chk2("groupnorm_to_tc stats")
+    # stride-2 im2col (pixel form) and the row form of the patch im2col with two segments per patch row
+    x = _r16(ops, 2, 5, 7, 48, seed=8)
+    out, chk = _guarded((2 * 3 * 4, 9 * 48), od)
+    ops.im2col_3x3_s2(x, out, 2, 5, 7, 48)
+    chk("im2col_3x3_s2")
+    img = _f32(1, 3, 14, 14 * 41, seed=9)
+    out, chk = _guarded((41, 592), od)
+    ops.patch_im2col(img, out, 1, 14, 14 * 41, 592)
+    chk("patch_im2col rows")
     entries = [_r16(ops, 9, 3 * 256, seed=20 + j) for j in range(7)]
     out, chk = _guarded((9, 256), od)
     ops.stream_temporal_attn(entries, _f32(32, 3 * 256, seed=6), out, 9, 256, 8)

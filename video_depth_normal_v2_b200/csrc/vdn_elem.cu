@@ -314,6 +314,147 @@ groupnorm_apply_tc_kernel(const void* __restrict__ x, const float* __restrict__ 
   }
 }
 
+// Statistics + apply + transpose in ONE launch (motion_module.py:103-115: GroupNorm(32, eps 1e-6) then the (b f) d c -> (b d) f c
+// rearrange).  A cluster of GN_CLUSTER CTAs owns one frame, each CTA a contiguous slice of its pixel rows; a thread owns one
+// 16-byte channel vector (8 channels of one group) and a row lane, so every warp access is one contiguous 512-byte run.
+//   pass 1  Welford / Chan statistics: each vector contributes (8, mean8, M2_8), merged into the thread's running (n, mean, M2);
+//           threads of a group are merged through shared memory, the CTAs of the frame through distributed shared memory, in a
+//           fixed order (every CTA does the same merge: bit-identical statistics in all of them, run to run).
+//   pass 2  the CTA re-reads its own slice back to front (the rows read last are the ones most likely still in L2) and writes the
+//           normalised rows pixel-major.
+// Measured and dropped: 512 threads with the first 200 KB of the slice kept in shared memory (one CTA per SM, 3.5 waves of
+// clusters: every wave idles through the two cluster barriers) was slower than the two-kernel form (0.33 against 0.27 ms per step).
+// Against the two-kernel form (one block per (frame, group) reading 64-byte pieces at a 2 KB stride, twice; then one warp per row)
+// the tensor comes from HBM once instead of twice and no access is narrower than a full warp line.
+constexpr int GN_CLUSTER = 8;
+constexpr int GN_MAXG = 64;
+constexpr int GN_THREADS = 256;
+
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float m2b) {
+  if (nb == 0.0f) return;
+  const float nn = n + nb;
+  const float delta = mb - mean;
+  const float fb = nb / nn;
+  mean = fmaf(delta, fb, mean);
+  m2 = m2 + m2b + delta * delta * n * fb;
+  n = nn;
+}
+
+__global__ void __cluster_dims__(GN_CLUSTER, 1, 1) __launch_bounds__(GN_THREADS)
+groupnorm_fused_tc_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, uint4* __restrict__ out,
+                          float* __restrict__ stats_out, int T, int D, int C, int groups, float eps, int fmt, int reverse) {
+  __shared__ float s_n[GN_THREADS], s_mean[GN_THREADS], s_m2[GN_THREADS];
+  __shared__ float part[3][GN_MAXG];   // this CTA's (n, mean, M2) per group: read by the whole cluster
+  __shared__ float fin[2][GN_MAXG];    // (mean, rstd) per group
+  const unsigned rank = blockIdx.x % GN_CLUSTER;
+  const int frame = blockIdx.x / GN_CLUSTER;
+  const int nv = C >> 3;                 // vectors per pixel row
+  const int gv = (C / groups) >> 3;      // vectors per group per pixel row
+  const int lanes = GN_THREADS / nv;     // row lanes of the block (host guarantees GN_THREADS % nv == 0)
+  const int v = threadIdx.x % nv, rl = threadIdx.x / nv;
+  const int rows_per = (D + GN_CLUSTER - 1) / GN_CLUSTER;
+  const int r0 = min(D, (int)rank * rows_per), r1 = min(D, r0 + rows_per);
+  const uint4* xf = x + (long long)frame * D * nv + v;
+
+  // ---- pass 1
+  float n = 0.0f, mean = 0.0f, m2 = 0.0f;
+  constexpr int U = 8;
+  for (int r = r0 + rl; r < r1; r += lanes * U) {
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = r + k * lanes;
+      if (rr < r1) u[k] = xf[(long long)rr * nv];
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = r + k * lanes;
+      if (rr < r1) {
+        const float2 a = unpack16(u[k].x, fmt), c2 = unpack16(u[k].y, fmt), d2 = unpack16(u[k].z, fmt), e2 = unpack16(u[k].w, fmt);
+        const float m8 = (((a.x + a.y) + (c2.x + c2.y)) + ((d2.x + d2.y) + (e2.x + e2.y))) * 0.125f;
+        float q = 0.0f, t;
+        t = a.x - m8; q = fmaf(t, t, q);  t = a.y - m8; q = fmaf(t, t, q);
+        t = c2.x - m8; q = fmaf(t, t, q); t = c2.y - m8; q = fmaf(t, t, q);
+        t = d2.x - m8; q = fmaf(t, t, q); t = d2.y - m8; q = fmaf(t, t, q);
+        t = e2.x - m8; q = fmaf(t, t, q); t = e2.y - m8; q = fmaf(t, t, q);
+        chan_merge(n, mean, m2, 8.0f, m8, q);
+      }
+    }
+  }
+  s_n[threadIdx.x] = n; s_mean[threadIdx.x] = mean; s_m2[threadIdx.x] = m2;
+  __syncthreads();
+  if ((int)threadIdx.x < groups) {  // the GN_THREADS / groups threads of group g: row lane l, vector g*gv + j
+    const int g = threadIdx.x;
+    float gn = 0.0f, gm = 0.0f, gq = 0.0f;
+    for (int l = 0; l < lanes; ++l)
+      for (int j = 0; j < gv; ++j) {
+        const int t = l * nv + g * gv + j;
+        chan_merge(gn, gm, gq, s_n[t], s_mean[t], s_m2[t]);
+      }
+    part[0][g] = gn; part[1][g] = gm; part[2][g] = gq;
+  }
+  cluster_sync_all();  // release / acquire: every CTA's part[] is visible to the others
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float gn = 0.0f, gm = 0.0f, gq = 0.0f;
+    for (unsigned cr = 0; cr < (unsigned)GN_CLUSTER; ++cr) {
+      float pn, pm, pq;
+      const uint32_t ra = mapa_rank(smem_u32(&part[0][g]), cr), rb = mapa_rank(smem_u32(&part[1][g]), cr), rcc = mapa_rank(smem_u32(&part[2][g]), cr);
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pn) : "r"(ra) : "memory");
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pm) : "r"(rb) : "memory");
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pq) : "r"(rcc) : "memory");
+      chan_merge(gn, gm, gq, pn, pm, pq);
+    }
+    const float rstd = rsqrtf(gq / gn + eps);
+    fin[0][g] = gm; fin[1][g] = rstd;
+    if (rank == 0 && stats_out != nullptr) {
+      stats_out[2 * (frame * groups + g)] = gm;
+      stats_out[2 * (frame * groups + g) + 1] = rstd;
+    }
+  }
+  cluster_sync_all();  // no CTA leaves (or reuses part[]) while a peer still reads it; also orders fin[] inside the CTA
+
+  // ---- pass 2
+  const int g = v / gv;
+  const float mu = fin[0][g], rstd = fin[1][g];
+  float sc[8], sh[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v), g1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * v), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * v + 1);
+    sc[0] = g0.x; sc[1] = g0.y; sc[2] = g0.z; sc[3] = g0.w; sc[4] = g1.x; sc[5] = g1.y; sc[6] = g1.z; sc[7] = g1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+  }
+  const int bb = frame / T, f = frame - bb * T;
+  uint4* of = out + ((long long)bb * D * T + f) * nv + v;   // row (bb*D + d)*T + f  ->  + d * T * nv
+  const int span = r1 - r0 - rl;  // rows r0 + rl, r0 + rl + lanes, ... < r1 belong to this thread
+  const int nch = span > 0 ? (span - 1) / (lanes * U) + 1 : 0;
+  for (int it = 0; it < nch; ++it) {
+    const int ch = reverse ? nch - 1 - it : it;
+    const int r = r0 + rl + ch * lanes * U;
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = r + k * lanes;
+      if (rr < r1) u[k] = xf[(long long)rr * nv];
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = r + k * lanes;
+      if (rr < r1) {
+        const uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = unpack16(wds[i], fmt);
+          // same expression as groupnorm_apply_tc_kernel: (v - mean) * rstd * w + b
+          o[i] = pack16((a.x - mu) * rstd * sc[2 * i] + sh[2 * i], (a.y - mu) * rstd * sc[2 * i + 1] + sh[2 * i + 1], fmt);
+        }
+        of[(long long)rr * T * nv] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // layout kernels
 // ------------------------------------------------------------------------------------------------
@@ -344,6 +485,54 @@ patch_im2col_kernel(const float* __restrict__ img, void* __restrict__ out, int B
       for (int k = 0; k < Kp - 588; ++k) pad[k] = 0;
     }
   }
+}
+
+// Row form of the same layout change: a block owns the (up to 40) patches of one patch row of one image.  Work item = one
+// (image-row piece (c, i), patch) pair = 14 contiguous floats; a warp takes a 4 x 8 tile of them (4 image rows x 8 neighbouring
+// patches: four contiguous 448-byte runs), rounds them into a shared-memory copy of the output rows (row pitch Kp/2 + 4 words, so
+// that the 32 lanes of a store hit 32 banks) and the block writes that copy out as contiguous 16-byte vectors.  The
+// thread-per-(patch, c, i) kernel above reads 56-byte pieces at a 2 KB stride (0.32 of the copy peak).
+__global__ void __launch_bounds__(256)
+patch_im2col_rows_kernel(const float* __restrict__ img, uint4* __restrict__ out, int H, int W, int Kp, int pitch, int seg, int nseg, int fmt) {
+  extern __shared__ uint4 pim_smem[];
+  uint32_t* sm = reinterpret_cast<uint32_t*>(pim_smem);
+  const int ph = H / 14, pw = W / 14;
+  int bid = blockIdx.x;
+  const int sg = bid % nseg;
+  bid /= nseg;
+  const int py = bid % ph;
+  const int bimg = bid / ph;
+  const int p0 = sg * seg;
+  const int np = min(seg, pw - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int padw = (Kp - 588) >> 1;  // padding columns as 32-bit words
+  for (int i = threadIdx.x; i < np * padw; i += 256) {
+    const int p = i / padw, k = i - p * padw;
+    sm[p * pitch + 294 + k] = 0u;
+  }
+  const float* base = img + ((long long)bimg * 3 * H + py * 14) * W + p0 * 14;
+  const int lci = lane >> 3, lpp = lane & 7;
+  const int tiles_pp = (np + 7) >> 3;
+  const int ntiles = 11 * tiles_pp;  // 42 image-row pieces in groups of 4
+  for (int t = warp; t < ntiles; t += 8) {
+    const int tci = t / tiles_pp, tpp = t - tci * tiles_pp;
+    const int ci = tci * 4 + lci, pp = tpp * 8 + lpp;
+    if (ci < 42 && pp < np) {
+      const int c = ci / 14, i = ci - c * 14;
+      const float2* src = reinterpret_cast<const float2*>(base + ((long long)c * H + i) * W + pp * 14);
+      float2 v[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) v[j] = __ldg(src + j);
+      uint32_t* d = sm + pp * pitch + ci * 7;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) d[j] = pack16(v[j].x, v[j].y, fmt);
+    }
+  }
+  __syncthreads();
+  const int kv = Kp >> 3, pv = pitch >> 2;
+  uint4* dst = out + ((long long)(bimg * ph + py) * pw + p0) * kv;
+  for (int r = warp; r < np; r += 8)
+    for (int q = lane; q < kv; q += 32) dst[r * kv + q] = pim_smem[r * pv + q];
 }
 
 __global__ void write_cls_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int B, int tokens, int C) {
@@ -389,6 +578,34 @@ im2col_3x3_s2_kernel(const void* __restrict__ x, void* __restrict__ out, int B, 
     uint4 v = make_uint4(0, 0, 0, 0);
     if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = xin[((bimg * H + hi) * W + wi) * cv + c8];
     o[idx] = v;
+  }
+}
+
+// Pixel form: a block owns one (or, for narrow C, several) output pixels, a thread one 16-byte channel vector of all nine taps: the
+// (b, ho, wo) decode happens once per thread in 32-bit arithmetic and the nine loads are independent (the element-per-thread kernel
+// above does four 64-bit divisions per 16 bytes moved).
+template <int NT>
+__global__ void __launch_bounds__(NT)
+im2col_3x3_s2_pix_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, int H, int W, int Ho, int Wo, int cv, int total_pix) {
+  const int ppb = cv >= NT ? 1 : NT / cv;
+  const int pl = cv >= NT ? 0 : (int)threadIdx.x / cv;
+  const int c0 = cv >= NT ? (int)threadIdx.x : (int)threadIdx.x - pl * cv;
+  const int pix = blockIdx.x * ppb + pl;
+  if (pl >= ppb || pix >= total_pix) return;
+  const int wo = pix % Wo;
+  const int t = pix / Wo;
+  const int ho = t % Ho;
+  const int bimg = t / Ho;
+  uint4* orow = o + (long long)pix * 9 * cv;
+  for (int c8 = c0; c8 < cv; c8 += NT) {
+    uint4 v[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hi = ho * 2 - 1 + tap / 3, wi = wo * 2 - 1 + tap % 3;
+      v[tap] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? xin[((long long)(bimg * H + hi) * W + wi) * cv + c8] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) orow[tap * cv + c8] = v[tap];
   }
 }
 
@@ -745,6 +962,25 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, float* __restrict__ out
   }
 }
 
+// Equal source and network size (cv2.resize returns the source unchanged): four pixels per thread, 12 bytes in as three 32-bit
+// words, one float4 per channel plane out; same arithmetic as the identity branch above.
+__global__ void __launch_bounds__(256)
+preprocess_u8_identity_kernel(const uint32_t* __restrict__ frames, float4* __restrict__ out, unsigned nquads, unsigned hw4, float m0, float m1, float m2,
+                              float is0, float is1, float is2) {
+  for (unsigned q = blockIdx.x * 256u + threadIdx.x; q < nquads; q += gridDim.x * 256u) {
+    const unsigned n = q / hw4, p4 = q - n * hw4;
+    const uint32_t a = __ldg(frames + 3ull * q), b = __ldg(frames + 3ull * q + 1), c = __ldg(frames + 3ull * q + 2);
+    // little endian: a = R0 G0 B0 R1, b = G1 B1 R2 G2, c = B2 R3 G3 B3
+    const float r[4] = {(float)(a & 255u), (float)(a >> 24), (float)((b >> 16) & 255u), (float)((c >> 8) & 255u)};
+    const float g[4] = {(float)((a >> 8) & 255u), (float)(b & 255u), (float)(b >> 24), (float)((c >> 16) & 255u)};
+    const float bl[4] = {(float)((a >> 16) & 255u), (float)((b >> 8) & 255u), (float)(c & 255u), (float)(c >> 24)};
+    float4* o = out + (size_t)n * 3u * hw4 + p4;
+    o[0] = make_float4((r[0] / 255.0f - m0) * is0, (r[1] / 255.0f - m0) * is0, (r[2] / 255.0f - m0) * is0, (r[3] / 255.0f - m0) * is0);
+    o[hw4] = make_float4((g[0] / 255.0f - m1) * is1, (g[1] / 255.0f - m1) * is1, (g[2] / 255.0f - m1) * is1, (g[3] / 255.0f - m1) * is1);
+    o[2 * (size_t)hw4] = make_float4((bl[0] / 255.0f - m2) * is2, (bl[1] / 255.0f - m2) * is2, (bl[2] / 255.0f - m2) * is2, (bl[3] / 255.0f - m2) * is2);
+  }
+}
+
 }  // namespace vdn
 
 using namespace vdn;
@@ -795,12 +1031,51 @@ extern "C" int vdn_groupnorm_apply_tc(const void* x, const float* stats, const f
   return check_launch("groupnorm_apply_tc_kernel");
 }
 
+extern "C" int vdn_groupnorm_to_tc(const void* x, const float* w, const float* b, void* out, float* stats, int32_t Bv, int32_t T, int32_t D,
+                                   int32_t C, int32_t groups, float eps, void* stream_v) {
+  VDN_STREAM;
+  if (!x || !w || !b || !out || !stats) return set_error("vdn_groupnorm_to_tc: null pointer");
+  if (Bv <= 0 || T <= 0 || D <= 0 || groups <= 0 || C % 8 != 0 || C % groups != 0) return set_error("vdn_groupnorm_to_tc: C must be a multiple of 8 and of groups");
+  const int frames = Bv * T;
+  const int nv = C / 8;
+  static const char* env = getenv("VDN_GN_V1");
+  static const char* fwd = getenv("VDN_GN_FWD");  // evaluation switch: pass 2 front to back
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  // one launch for the shapes of the ViT-L / ViT-g heads (C = 256, 512, 1024, 2048); a handful of frames (the streaming path) does not
+  // fill the machine with 8 CTAs per frame and keeps the two-kernel form
+  const bool fused = env == nullptr && aligned && (C / groups) % 8 == 0 && nv <= 256 && GN_THREADS % nv == 0 && groups <= GN_MAXG && frames >= 8 &&
+                     (long long)frames * GN_CLUSTER < 0x7fffffffLL && (long long)D * nv < 0x7fffffffLL;
+  if (!fused) {
+    if (int rc = vdn_groupnorm_stats(x, stats, frames, D, C, groups, eps, stream_v)) return rc;
+    return vdn_groupnorm_apply_tc(x, stats, w, b, out, Bv, T, D, C, groups, stream_v);
+  }
+  groupnorm_fused_tc_kernel<<<frames * GN_CLUSTER, GN_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(x), w, b, reinterpret_cast<uint4*>(out), stats, T, D, C,
+                                                                    groups, eps, get_operand_format(), fwd == nullptr ? 1 : 0);
+  count_launch();
+  return check_launch("groupnorm_fused_tc_kernel");
+}
+
 extern "C" int vdn_patch_im2col(const float* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Kp, void* stream_v) {
   VDN_STREAM;
   if (!img || !out) return set_error("vdn_patch_im2col: null pointer");
   if (H % 14 != 0 || W % 14 != 0) return set_error("vdn_patch_im2col: H and W must be multiples of the patch size 14");  // patch_embed.py:73-74
   if (Kp < 588 || Kp % 8 != 0) return set_error("vdn_patch_im2col: Kp must be >= 588 and a multiple of 8");
   if ((reinterpret_cast<uintptr_t>(img) & 7) != 0 || (reinterpret_cast<uintptr_t>(out) & 3) != 0) return set_error("vdn_patch_im2col: img must be 8-byte and out 4-byte aligned");
+  static const char* env = getenv("VDN_PATCH_V1");
+  const int ph = H / 14, pw = W / 14;
+  const int pitch = Kp / 2 + ((Kp / 2) % 8 == 0 ? 4 : 0);  // 32-bit words per shared-memory row, = 4 (mod 8): conflict-free 4 x 8 warp tiles
+  const int maxseg = (48 * 1024) / (pitch * 4);            // patches whose output rows fit 48 KB of shared memory (40 at Kp = 592)
+  if (env == nullptr && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && maxseg >= 1 && B > 0 && ph > 0 && pw > 0) {
+    const int nseg = (pw + maxseg - 1) / maxseg;
+    const int seg = (pw + nseg - 1) / nseg;
+    const long long blocks = (long long)B * ph * nseg;
+    if (blocks < 0x7fffffffLL) {
+      patch_im2col_rows_kernel<<<(unsigned)blocks, 256, (size_t)seg * pitch * 4, stream>>>(img, reinterpret_cast<uint4*>(out), H, W, Kp, pitch, seg, nseg,
+                                                                                           get_operand_format());
+      count_launch();
+      return check_launch("patch_im2col_rows_kernel");
+    }
+  }
   patch_im2col_kernel<<<grid_for((long long)B * (H / 14) * (W / 14) * 42, 256), 256, 0, stream>>>(img, out, B, H, W, Kp, get_operand_format());
   count_launch();
   return check_launch("patch_im2col_kernel");
@@ -832,6 +1107,18 @@ extern "C" int vdn_im2col_3x3_s2(const void* x, void* out, int32_t B, int32_t H,
   if (!x || !out) return set_error("vdn_im2col_3x3_s2: null pointer");
   if (C % 8 != 0) return set_error("vdn_im2col_3x3_s2: C must be a multiple of 8");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  static const char* env = getenv("VDN_IM2COL_V1");
+  const long long total_pix = (long long)B * Ho * Wo;
+  const int cv = C / 8;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (env == nullptr && aligned && total_pix > 0 && total_pix < 0x7fffffffLL) {
+    constexpr int NT = 128;
+    const int ppb = cv >= NT ? 1 : NT / cv;
+    im2col_3x3_s2_pix_kernel<NT><<<(unsigned)((total_pix + ppb - 1) / ppb), NT, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), H,
+                                                                                          W, Ho, Wo, cv, (int)total_pix);
+    count_launch();
+    return check_launch("im2col_3x3_s2_pix_kernel");
+  }
   im2col_3x3_s2_kernel<<<grid_for((long long)B * Ho * Wo * 9 * (C / 8), 256), 256, 0, stream>>>(x, out, B, H, W, C);
   count_launch();
   return check_launch("im2col_3x3_s2_kernel");
@@ -981,6 +1268,16 @@ extern "C" int vdn_preprocess_u8(const void* frames, float* out, int32_t N, int3
   VDN_STREAM;
   if (!frames || !out || !mean3 || !std3) return set_error("vdn_preprocess_u8: null pointer");
   if (N <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0) return set_error("vdn_preprocess_u8: bad shape");
+  const long long hw = (long long)h * w;
+  if (H == h && W == w && hw % 4 == 0 && (long long)N * hw / 4 < 0x7fffffffLL && (reinterpret_cast<uintptr_t>(frames) & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const unsigned nquads = (unsigned)((long long)N * hw / 4);
+    preprocess_u8_identity_kernel<<<grid_for(nquads, 256, 32), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(frames), reinterpret_cast<float4*>(out),
+                                                                                  nquads, (unsigned)(hw / 4), mean3[0], mean3[1], mean3[2],
+                                                                                  1.0f / std3[0], 1.0f / std3[1], 1.0f / std3[2]);
+    count_launch();
+    return check_launch("preprocess_u8_identity_kernel");
+  }
   const double sy = 1.0 / ((double)h / (double)H), sx = 1.0 / ((double)w / (double)W);  // OpenCV: scale = 1 / inv_scale
   preprocess_u8_kernel<<<grid_for((long long)N * h * w, 256, 32), 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(frames), out, N, H, W, h, w, sy, sx,
                                                                                       mean3[0], mean3[1], mean3[2], 1.0f / std3[0], 1.0f / std3[1],

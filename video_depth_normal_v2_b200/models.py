@@ -171,9 +171,8 @@ def motion_module_forward(mm: dict, x: torch.Tensor, Bv: int, T: int, D: int, re
     dev, od, C = x.device, ops.operand_dtype(), mm["C"]
     rows = Bv * D * T
     stats = _empty((Bv * T * 32 * 2,), torch.float32, dev)
-    ops.groupnorm_stats(x, stats, Bv * T, D, C, 32, 1e-6)
     xt = _empty((rows, C), od, dev)
-    ops.groupnorm_apply_tc(x, stats, mm["gn_w"], mm["gn_b"], xt, Bv, T, D, C, 32)
+    ops.groupnorm_to_tc(x, mm["gn_w"], mm["gn_b"], xt, stats, Bv, T, D, C, 32, 1e-6)
     h = _empty((rows, C), torch.float32, dev)  # fp32 hidden state, pixel-major rows (b*D+d)*T+f
     ops.gemm(xt, mm["proj_in"]["w"], h, M=rows, N=C, K=C, bias=mm["proj_in"]["b"])
     n16 = xt  # reuse

@@ -243,6 +243,16 @@ def groupnorm_apply_tc(x, stats, w, b, out, Bv, T, D, C_, groups):
     return out
 
 
+def groupnorm_to_tc(x, w, b, out, stats, Bv, T, D, C_, groups, eps):
+    """GroupNorm + affine + frame-major -> pixel-major transpose in one call (motion_module.py:103-115): one cluster launch for the
+    ViT-L / ViT-g head shapes, the statistics and apply kernels otherwise; ``stats`` (frames * groups * 2 fp32) receives (mean, rstd)."""
+    od = operand_dtype()
+    _check(_run("groupnorm_to_tc", "hbm", 4.0 * Bv * T * D * C_, lib().vdn_groupnorm_to_tc, _ptr(x, od, "x"), _ptr(w, torch.float32, "w"),
+                _ptr(b, torch.float32, "b"), _ptr(out, od, "out"), _ptr(stats, torch.float32, "stats"), Bv, T, D, C_, groups, eps, _stream()),
+           "vdn_groupnorm_to_tc")
+    return out
+
+
 def patch_im2col(img, out, B, H, W, Kp):
     _check(_run("patch_im2col", "hbm", B * 3.0 * H * W * 4 + B * (H // 14) * (W // 14) * Kp * 2.0, lib().vdn_patch_im2col, _ptr(img, torch.float32, "img"),
                 _ptr(out, operand_dtype(), "out"), B, H, W, Kp, _stream()), "vdn_patch_im2col")

@@ -76,8 +76,7 @@ def _temporal_attn(qkv, out, D, T, heads):
 def _groupnorm_to_tc(x, w, b, out, Bv, T, groups, eps):
     frames, D, C = x.shape
     stats = torch.empty((frames * groups * 2,), dtype=torch.float32, device=x.device)
-    ops.groupnorm_stats(x, stats, frames, D, C, groups, eps)
-    return ops.groupnorm_apply_tc(x, stats, w, b, out, Bv, T, D, C, groups)
+    return ops.groupnorm_to_tc(x, w, b, out, stats, Bv, T, D, C, groups, eps)
 
 
 def _bilinear_ac(x, out):
