@@ -10,7 +10,7 @@ col = {h: i for i, h in enumerate(hdr)}
 want = [("gpu__time_duration.sum", "us"), ("sm__cycles_elapsed.avg.per_second", "GHz"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
         ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
         ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"), ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
-        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"), ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"), ("lts__t_sector_hit_rate.pct", "l2hit%"), ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
         ("launch__block_size", "block")]
 print(f"# {rep}")
 for r in rows[2:]:

@@ -365,8 +365,8 @@ def test_groupnorm_transpose(ops, Bv, T, D, C):
                                       (1, 4, 30, 192), (1, 2, 100, 1024), (1, 12, 33, 768)])
 def test_groupnorm_to_tc_single_launch(ops, Bv, T, D, C):
     """vdn_groupnorm_to_tc (one cluster launch for C in {256, 512, 1024, 2048} with >= 8 frames, the two kernels otherwise) against
-    F.group_norm, with a mean far from zero (the single-pass statistics are Welford / Chan merges, not E[x^2] - mean^2) and against the
-    two-kernel form's statistics."""
+    F.group_norm, with a mean far from zero (the single-pass statistics are pivot-shifted sums and Chan merges, not E[x^2] - mean^2) and
+    against the two-kernel form's statistics."""
     od = ops.operand_dtype()
     x = (_f32(Bv * T, D, C, scale=0.5, seed=1) + 6.0).to(od)
     x[:, :, : C // 2] *= -0.25  # groups with different means and spreads

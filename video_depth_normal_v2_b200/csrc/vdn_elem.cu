@@ -317,9 +317,9 @@ groupnorm_apply_tc_kernel(const void* __restrict__ x, const float* __restrict__ 
 // Statistics + apply + transpose in ONE launch (motion_module.py:103-115: GroupNorm(32, eps 1e-6) then the (b f) d c -> (b d) f c
 // rearrange).  A cluster of GN_CLUSTER CTAs owns one frame, each CTA a contiguous slice of its pixel rows; a thread owns one
 // 16-byte channel vector (8 channels of one group) and a row lane, so every warp access is one contiguous 512-byte run.
-//   pass 1  Welford / Chan statistics: each vector contributes (8, mean8, M2_8), merged into the thread's running (n, mean, M2);
-//           threads of a group are merged through shared memory, the CTAs of the frame through distributed shared memory, in a
-//           fixed order (every CTA does the same merge: bit-identical statistics in all of them, run to run).
+//   pass 1  statistics: each thread sums (x - K) and (x - K)^2 around its own pivot K and turns them into (n, mean, M2); the
+//           threads of a group are Chan-merged through shared memory, the CTAs of the frame through distributed shared memory, in
+//           a fixed order (every CTA does the same merge: bit-identical statistics in all of them, run to run).
 //   pass 2  the CTA re-reads its own slice back to front (the rows read last are the ones most likely still in L2) and writes the
 //           normalised rows pixel-major.
 // Measured and dropped: 512 threads with the first 200 KB of the slice kept in shared memory (one CTA per SM, 3.5 waves of
@@ -356,29 +356,42 @@ groupnorm_fused_tc_kernel(const uint4* __restrict__ x, const float* __restrict__
   const int r0 = min(D, (int)rank * rows_per), r1 = min(D, r0 + rows_per);
   const uint4* xf = x + (long long)frame * D * nv + v;
 
-  // ---- pass 1
+  // ---- pass 1: sums of (x - K) and (x - K)^2 around a per-thread pivot K (the mean of the thread's first vector, within sigma / sqrt(8)
+  // of the mean: M2 = s2 - s1^2 / n loses nothing), turned into (n, mean, M2) once per thread.  (A Chan merge per vector cost a
+  // division and ~50 instructions per 16 bytes: the kernel was issue-bound at 51 % issue-active, ncu.)
   float n = 0.0f, mean = 0.0f, m2 = 0.0f;
   constexpr int U = 8;
-  for (int r = r0 + rl; r < r1; r += lanes * U) {
-    uint4 u[U];
+  {
+    float K = 0.0f, s1 = 0.0f, s2 = 0.0f;
+    for (int r = r0 + rl; r < r1; r += lanes * U) {
+      const uint4* px = xf + (long long)r * nv;
+      uint4 u[U];
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const int rr = r + k * lanes;
-      if (rr < r1) u[k] = xf[(long long)rr * nv];
-    }
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const int rr = r + k * lanes;
-      if (rr < r1) {
-        const float2 a = unpack16(u[k].x, fmt), c2 = unpack16(u[k].y, fmt), d2 = unpack16(u[k].z, fmt), e2 = unpack16(u[k].w, fmt);
-        const float m8 = (((a.x + a.y) + (c2.x + c2.y)) + ((d2.x + d2.y) + (e2.x + e2.y))) * 0.125f;
-        float q = 0.0f, t;
-        t = a.x - m8; q = fmaf(t, t, q);  t = a.y - m8; q = fmaf(t, t, q);
-        t = c2.x - m8; q = fmaf(t, t, q); t = c2.y - m8; q = fmaf(t, t, q);
-        t = d2.x - m8; q = fmaf(t, t, q); t = d2.y - m8; q = fmaf(t, t, q);
-        t = e2.x - m8; q = fmaf(t, t, q); t = e2.y - m8; q = fmaf(t, t, q);
-        chan_merge(n, mean, m2, 8.0f, m8, q);
+      for (int k = 0; k < U; ++k)
+        if (r + k * lanes < r1) u[k] = px[k * GN_THREADS];  // lanes * nv = GN_THREADS vectors between a thread's consecutive rows
+      if (r == r0 + rl) {
+        const float2 a = unpack16(u[0].x, fmt), c2 = unpack16(u[0].y, fmt), d2 = unpack16(u[0].z, fmt), e2 = unpack16(u[0].w, fmt);
+        K = (((a.x + a.y) + (c2.x + c2.y)) + ((d2.x + d2.y) + (e2.x + e2.y))) * 0.125f;
       }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (r + k * lanes < r1) {
+          const float2 a = unpack16(u[k].x, fmt), c2 = unpack16(u[k].y, fmt), d2 = unpack16(u[k].z, fmt), e2 = unpack16(u[k].w, fmt);
+          const float t0 = a.x - K, t1 = a.y - K, t2 = c2.x - K, t3 = c2.y - K, t4 = d2.x - K, t5 = d2.y - K, t6 = e2.x - K, t7 = e2.y - K;
+          s1 += ((t0 + t1) + (t2 + t3)) + ((t4 + t5) + (t6 + t7));
+          float qa = t0 * t0, qb = t1 * t1;
+          qa = fmaf(t2, t2, qa); qb = fmaf(t3, t3, qb);
+          qa = fmaf(t4, t4, qa); qb = fmaf(t5, t5, qb);
+          qa = fmaf(t6, t6, qa); qb = fmaf(t7, t7, qb);
+          s2 += qa + qb;
+          n += 8.0f;
+        }
+      }
+    }
+    if (n > 0.0f) {
+      const float d = s1 / n;
+      mean = K + d;
+      m2 = fmaxf(s2 - s1 * d, 0.0f);
     }
   }
   s_n[threadIdx.x] = n; s_mean[threadIdx.x] = mean; s_m2[threadIdx.x] = m2;
@@ -414,7 +427,7 @@ groupnorm_fused_tc_kernel(const uint4* __restrict__ x, const float* __restrict__
   }
   cluster_sync_all();  // no CTA leaves (or reuses part[]) while a peer still reads it; also orders fin[] inside the CTA
 
-  // ---- pass 2
+  // ---- pass 2: y = x * a + b with a = rstd * w, b = bias - mean * a (one FFMA per value)
   const int g = v / gv;
   const float mu = fin[0][g], rstd = fin[1][g];
   float sc[8], sh[8];
@@ -423,33 +436,37 @@ groupnorm_fused_tc_kernel(const uint4* __restrict__ x, const float* __restrict__
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * v), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * v + 1);
     sc[0] = g0.x; sc[1] = g0.y; sc[2] = g0.z; sc[3] = g0.w; sc[4] = g1.x; sc[5] = g1.y; sc[6] = g1.z; sc[7] = g1.w;
     sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] *= rstd;
+      sh[i] = fmaf(-mu, sc[i], sh[i]);
+    }
   }
   const int bb = frame / T, f = frame - bb * T;
   uint4* of = out + ((long long)bb * D * T + f) * nv + v;   // row (bb*D + d)*T + f  ->  + d * T * nv
+  const int ostep = T * GN_THREADS;                         // output vectors between a thread's consecutive rows
   const int span = r1 - r0 - rl;  // rows r0 + rl, r0 + rl + lanes, ... < r1 belong to this thread
   const int nch = span > 0 ? (span - 1) / (lanes * U) + 1 : 0;
   for (int it = 0; it < nch; ++it) {
     const int ch = reverse ? nch - 1 - it : it;
     const int r = r0 + rl + ch * lanes * U;
+    const uint4* px = xf + (long long)r * nv;
+    uint4* po = of + (long long)r * T * nv;
     uint4 u[U];
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const int rr = r + k * lanes;
-      if (rr < r1) u[k] = xf[(long long)rr * nv];
-    }
+    for (int k = 0; k < U; ++k)
+      if (r + k * lanes < r1) u[k] = px[k * GN_THREADS];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      const int rr = r + k * lanes;
-      if (rr < r1) {
+      if (r + k * lanes < r1) {
         const uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
         uint32_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 a = unpack16(wds[i], fmt);
-          // same expression as groupnorm_apply_tc_kernel: (v - mean) * rstd * w + b
-          o[i] = pack16((a.x - mu) * rstd * sc[2 * i] + sh[2 * i], (a.y - mu) * rstd * sc[2 * i + 1] + sh[2 * i + 1], fmt);
+          o[i] = pack16(fmaf(a.x, sc[2 * i], sh[2 * i]), fmaf(a.y, sc[2 * i + 1], sh[2 * i + 1]), fmt);
         }
-        of[(long long)rr * T * nv] = make_uint4(o[0], o[1], o[2], o[3]);
+        po[(long long)k * ostep] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
   }
