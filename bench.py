@@ -49,6 +49,29 @@ def _peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
 
 
+# Share of a kernel's algorithmic bytes that are writes, for the write-dominated bandwidth kernels of the step (2x bilinear up-sampling:
+# 4 of 5 bytes; stride-2 im2col: 9 taps out for 4 pixels in at 37^2 -> 19^2; uint8 -> fp32 pre-processing: 12 of 15).  HBM3e takes writes
+# alone at ~3.9 TB/s against 6.5 TB/s for a 1 : 1 copy (scripts/microbench/rw_mix.py, profiles/r02_rw_mix.txt), so these kernels are
+# also reported against max(write bytes / write rate, all bytes / copy rate).
+WRITE_SHARE = {"bilinear_nhwc": 0.8, "im2col_3x3_s2": 0.70, "preprocess_u8": 0.8}
+
+
+def _write_peak_gbs(dev) -> float:
+    """Write-only HBM rate of this box: ATen fill_ over 1 GiB, best of 5 (CUDA events)."""
+    buf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    best = float("inf")
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        buf.fill_(i)
+        e1.record()
+        e1.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del buf
+    return (1 << 30) / (best / 1e3) / 1e9
+
+
 def _round(x, sig=5):
     """Floats to `sig` significant digits, recursively: keeps the line short enough for the blocks at its end to survive a tail."""
     if isinstance(x, float):
@@ -397,6 +420,11 @@ def main():
         kernels[name] = {"n": a["launches"] // n_prof, "ms": a["ms"] / n_prof, "share": a["ms"] / total_prof_ms,
                          ("tflops" if a["kind"] == "tensor" else "gbs"): rate / (1e12 if a["kind"] == "tensor" else 1e9),
                          "frac": rate / (peaks["tflops"] * 1e12 if a["kind"] == "tensor" else peaks["hbm_gbs"] * 1e9)}
+    write_gbs = _write_peak_gbs(dev)
+    for name, fw in WRITE_SHARE.items():
+        if name in kernels and "gbs" in kernels[name]:
+            mix_peak = 1.0 / max(fw / write_gbs, 1.0 / peaks["hbm_gbs"])  # GB/s of all bytes when the writes alone take fw / write rate
+            kernels[name].update({"write_share": fw, "frac_write_roofline": kernels[name]["gbs"] / mix_peak})
     tname, ta = max(agg.items(), key=lambda kv: kv[1]["ms"])
     tensor = ta["kind"] == "tensor"
     achieved = ta["work"] / (ta["ms"] / 1e3) / (1e12 if tensor else 1e9)
@@ -469,6 +497,7 @@ def main():
                    if world > 1 else "single GPU",
                    "l2": "activations per step (>2 GB) exceed the 126 MB L2, no explicit flush",
                    "operands": args.operands + " (fp32 accumulate, fp32 residual stream)", "warmup_note": f"2 untimed passes over the same clip = {2 * K} window-steps per GPU (>= the requested {args.warmup})"},
+        "hbm_write_gbs": write_gbs,
         "kernels": kernels,
     }
     head = {k: line[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step")}

@@ -23,5 +23,8 @@ timeout -k 10 600 ncu --set full --clock-control none --import-source on --profi
 echo "flash capture exit $?"
 timeout -k 10 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_tail -c 1 -f -o gpurun_out/prof_tail $CMD > gpurun_out/ncu_full_tail.log 2>&1
 echo "tail capture exit $?"
-timeout -k 10 600 ncu --set full --clock-control none --profile-from-start off -k regex:"layernorm|temporal_attn_tc|bilinear|groupnorm" -s 20 -c 8 -f -o gpurun_out/prof_mem $CMD > gpurun_out/ncu_full_mem.log 2>&1
+timeout -k 10 600 ncu --set full --clock-control none --profile-from-start off -k regex:"layernorm|temporal_attn_tc" -s 20 -c 4 -f -o gpurun_out/prof_mem $CMD > gpurun_out/ncu_full_mem.log 2>&1
 echo "mem-bound capture exit $?"
+timeout -k 10 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"groupnorm|im2col|preprocess|bilinear_slide|window_finalize" -c 14 -f -o gpurun_out/prof_bw $CMD > gpurun_out/ncu_full_bw.log 2>&1
+echo "bandwidth-kernel capture exit $?"
+python scripts/microbench/rw_mix.py > gpurun_out/rw_mix.txt 2>&1; cat gpurun_out/rw_mix.txt

@@ -663,6 +663,9 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // Same coordinate arithmetic as ATen (ac_coords); the evaluation order (vertical first) differs from ATen's by fp32 rounding only.
 // History: a gather kernel (four 16-byte loads and a full 4-tap blend per output vector) was issue-bound at 2.8 TB/s; a row-staged
 // variant through shared memory reached 4.1-4.9 TB/s alone but stalled on its own shared-memory traffic; this one 4.2-5.7 TB/s.
+// A straight-line form for ~2x up-sampling (8 pixels x 4 rows per thread, the pixel-to-column-pair assignment worked out once per
+// thread as in the fused head tail's producers: 62 % -> 51 % issue-active, bit-identical outputs) took the same 384-388 us on the
+// 148^2 -> 296^2 resize (profiles/r02_bandwidth_pass.txt): the kernel is not issue-bound, 80 % of its traffic is writes.  Removed.
 template <int FMT, int RELU2>
 __global__ void __launch_bounds__(128)
 bilinear_slide_kernel(const uint4* __restrict__ xin, uint4* __restrict__ o, uint4* __restrict__ o_relu, int H, int W, int Ho, int Wo, int cv, int L,
