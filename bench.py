@@ -58,12 +58,13 @@ WRITE_SHARE = {"bilinear_nhwc": 0.8, "im2col_3x3_s2": 0.70, "preprocess_u8": 0.8
 
 def _write_peak_gbs(dev) -> float:
     """Write-only HBM rate of this box: ATen fill_ over 1 GiB, best of 5 (CUDA events)."""
-    buf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    import torch
+    buf = torch.empty(1 << 29, dtype=torch.float16, device=dev)  # 16-bit elements as in rw_mix.py (ATen's 1-byte fill reaches only 3.0 TB/s)
     best = float("inf")
     for i in range(7):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        buf.fill_(i)
+        buf.fill_(float(i))
         e1.record()
         e1.synchronize()
         if i >= 2:

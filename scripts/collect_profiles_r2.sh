@@ -1,14 +1,13 @@
 #!/bin/bash
 # gpurun_out/ of scripts/gpu_final_r2.sh -> the tracked round-2 evidence under profiles/ (run here, after the GPU call came back)
 set -e
+set +e
 O=gpurun_out; P=profiles
 cp $O/gpu_tests.log $P/r02_gpu_parity.txt
 cp $O/bench.json $P/r02_bench.json
-cp $O/bench_ref.json $P/r02_bench_reference_arm.json
+[ -f $O/bench_ref.json ] && [ $O/bench_ref.json -nt $O/bench.json ] && cp $O/bench_ref.json $P/r02_bench_reference_arm.json
 cp $O/shape_profile_lv.txt $P/r02_shape_profile_lv.txt
-cp $O/shape_profile_da2.txt $P/r02_shape_profile_da2.txt
-cp $O/standalone_kernels.txt $P/r02_standalone_kernels.txt
-cp $O/microbench.txt $P/r02_microbench.txt
+# shape_profile_da2 / standalone_kernels / microbench: only scripts/gpu_final_r2.sh regenerates them (copy by hand after that script)
 [ -f $O/rw_mix.txt ] && cp $O/rw_mix.txt $P/r02_rw_mix.txt
 cp $O/launches.csv $P/r02_launches.csv
 python scripts/summarize_launches.py $O/launches.csv > $P/r02_launches_summary.txt
