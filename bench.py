@@ -57,18 +57,21 @@ WRITE_SHARE = {"bilinear_nhwc": 0.8, "im2col_3x3_s2": 0.70, "preprocess_u8": 0.8
 
 
 def _write_peak_gbs(dev) -> float:
-    """Write-only HBM rate of this box: ATen fill_ over 1 GiB, best of 5 (CUDA events)."""
+    """Write-only HBM rate of this box: ATen fill_ over 1 GiB of 16-bit elements, ten fills back to back between two CUDA events (as
+    scripts/microbench/rw_mix.py; single timed fills read 20 % low), best of 3."""
     import torch
-    buf = torch.empty(1 << 29, dtype=torch.float16, device=dev)  # 16-bit elements as in rw_mix.py (ATen's 1-byte fill reaches only 3.0 TB/s)
+    buf = torch.empty(1 << 29, dtype=torch.float16, device=dev)
+    for i in range(3):
+        buf.fill_(float(i))
     best = float("inf")
-    for i in range(7):
+    for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        buf.fill_(float(i))
+        for i in range(10):
+            buf.fill_(float(i))
         e1.record()
         e1.synchronize()
-        if i >= 2:
-            best = min(best, e0.elapsed_time(e1))
+        best = min(best, e0.elapsed_time(e1) / 10)
     del buf
     return (1 << 30) / (best / 1e3) / 1e9
 
