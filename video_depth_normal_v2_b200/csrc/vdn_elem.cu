@@ -1,7 +1,7 @@
 // Bandwidth-bound kernels: LayerNorm, GroupNorm (+ frame->pixel-major transpose), patch im2col, stride-2 im2col,
 // bilinear resize (align_corners=True), ReLU / casts, window alignment reductions, Sobel normals.
-// All are coalesced, 16-byte vectorised where the layout allows, warp-shuffle reductions, no shared-memory staging
-// beyond block reductions (each element is touched once).
+// All are coalesced, 16-byte vectorised where the layout allows, warp-shuffle reductions; shared memory only for block reductions,
+// the GroupNorm cluster merge (distributed shared memory) and the patch im2col's transposing copy of its output rows.
 #include <stdlib.h>
 
 #include "../../include/vdn_b200.h"
