@@ -130,7 +130,8 @@ dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 // 49 neighbours per output from L2: 8 TB/s of L2 traffic, 247 GB/s of algorithmic bytes).  LayerNorm2d over the channels of each pixel:
 // two block reductions for all DW_P pixels at once.  Needs C % 128 == 0 (blockDim = C / 4).
 constexpr int DW_P = 13;
-__global__ void __launch_bounds__(384)
+template <int MAXT>  // 256 threads (C <= 1024): two blocks per SM; 384 (ViT-g, C = 1536): one
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1)
 dwconv7_ln_row_kernel(const float4* __restrict__ x, const float4* __restrict__ w, const float4* __restrict__ bias, const float4* __restrict__ ln_w,
                       const float4* __restrict__ ln_b, void* __restrict__ out, int H, int W, int C4, float eps, int fmt) {
   const int segs = (W + DW_P - 1) / DW_P;
@@ -151,19 +152,33 @@ dwconv7_ln_row_kernel(const float4* __restrict__ x, const float4* __restrict__ w
 #pragma unroll
     for (int dx = 0; dx < 7; ++dx) wt[dx] = __ldg(w + (dy * 7 + dx) * C4 + c);
     const float4* row = base + (long long)y2 * W * C4;
+    // input column x0 - 3 + xi feeds output pixel p = xi - dx with tap dx.  The columns are fetched DW_B at a time before any of them
+    // is used (columns outside the image read as zero: an exact no-op in the FMAs): with one conditional load per column right in
+    // front of its FMAs every one of the 7 x 19 loads of a block exposed its full L2 latency (ncu: 65 % of the stall samples on
+    // long-scoreboard, 236 us per launch)
+    constexpr int DW_B = 7;
 #pragma unroll
-    for (int xi = 0; xi < DW_P + 6; ++xi) {  // input column x0 - 3 + xi feeds output pixel p = xi - dx with tap dx
-      const int x2 = x0 - 3 + xi;
-      if (x2 < 0 || x2 >= W) continue;
-      const float4 v = __ldg(row + (long long)x2 * C4);
+    for (int b0 = 0; b0 < DW_P + 6; b0 += DW_B) {
+      float4 v[DW_B];
 #pragma unroll
-      for (int dx = 0; dx < 7; ++dx) {
-        const int p = xi - dx;
-        if (p >= 0 && p < DW_P) {
-          acc[p].x = fmaf(v.x, wt[dx].x, acc[p].x);
-          acc[p].y = fmaf(v.y, wt[dx].y, acc[p].y);
-          acc[p].z = fmaf(v.z, wt[dx].z, acc[p].z);
-          acc[p].w = fmaf(v.w, wt[dx].w, acc[p].w);
+      for (int i = 0; i < DW_B; ++i) {
+        const int x2 = x0 - 3 + b0 + i;
+        v[i] = (b0 + i < DW_P + 6 && x2 >= 0 && x2 < W) ? __ldg(row + (long long)x2 * C4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+#pragma unroll
+      for (int i = 0; i < DW_B; ++i) {
+        const int xi = b0 + i;
+        if (xi < DW_P + 6) {
+#pragma unroll
+          for (int dx = 0; dx < 7; ++dx) {
+            const int p = xi - dx;
+            if (p >= 0 && p < DW_P) {
+              acc[p].x = fmaf(v[i].x, wt[dx].x, acc[p].x);
+              acc[p].y = fmaf(v[i].y, wt[dx].y, acc[p].y);
+              acc[p].z = fmaf(v[i].z, wt[dx].z, acc[p].z);
+              acc[p].w = fmaf(v[i].w, wt[dx].w, acc[p].w);
+            }
+          }
         }
       }
     }
@@ -348,9 +363,14 @@ extern "C" int vdn_dwconv7_ln(const float* x, const float* w, const float* bias,
   static const bool v1 = [] { const char* e = getenv("VDN_DWCONV_V1"); return e && atoi(e) != 0; }();
   if (C % 128 == 0 && !v1) {
     const long long blocks = (long long)B * H * ((W + DW_P - 1) / DW_P);
-    dwconv7_ln_row_kernel<<<(unsigned)blocks, C / 4, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(w),
-                                                                reinterpret_cast<const float4*>(bias), reinterpret_cast<const float4*>(ln_w),
-                                                                reinterpret_cast<const float4*>(ln_b), out, H, W, C / 4, eps, get_operand_format());
+    if (C <= 1024)
+      dwconv7_ln_row_kernel<256><<<(unsigned)blocks, C / 4, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(w),
+                                                                       reinterpret_cast<const float4*>(bias), reinterpret_cast<const float4*>(ln_w),
+                                                                       reinterpret_cast<const float4*>(ln_b), out, H, W, C / 4, eps, get_operand_format());
+    else
+      dwconv7_ln_row_kernel<384><<<(unsigned)blocks, C / 4, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(w),
+                                                                       reinterpret_cast<const float4*>(bias), reinterpret_cast<const float4*>(ln_w),
+                                                                       reinterpret_cast<const float4*>(ln_b), out, H, W, C / 4, eps, get_operand_format());
     count_launch();
     return check_launch("dwconv7_ln_row_kernel");
   }
