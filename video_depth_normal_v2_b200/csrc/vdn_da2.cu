@@ -12,19 +12,22 @@
 
 namespace vdn {
 
-template <int FMT>
+// IDX: index type of the (row, head, piece) decode — unsigned 32-bit whenever the element count allows (the four 64-bit divisions per
+// 16 bytes of the long long form made the kernel issue-bound: 36 us per 45 MB call)
+template <int FMT, typename IDX>
 __global__ void __launch_bounds__(256)
 rope2d_kernel(uint4* __restrict__ x, long long rows, int ld8 /*row pitch in 16-byte units*/, int col8 /*first column / 8*/, int heads,
               const float* __restrict__ cs, int P, long long rows_per_batch, long long batch_pitch, int per_head /*table row = (pos, head)*/) {
-  const long long total = rows * heads * 8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const IDX total = (IDX)(rows * heads * 8);
+  const IDX rpb = (IDX)rows_per_batch;
+  for (IDX idx = (IDX)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IDX)gridDim.x * blockDim.x) {
     const int v = int(idx & 7);  // 16-byte piece of the 64-wide head: pairs 4v .. 4v+3
-    const long long t = idx >> 3;
-    const int h = int(t % heads);
-    const long long r = t / heads;
-    const int pos = int(r % P);
-    const long long bb = r / rows_per_batch;
-    const long long phys = bb * batch_pitch + (r - bb * rows_per_batch);  // rows of one batch are contiguous, batches batch_pitch rows apart
+    const IDX t = idx >> 3;
+    const int h = int(t % (IDX)heads);
+    const IDX r = t / (IDX)heads;
+    const int pos = int(r % (IDX)P);
+    const IDX bb = r / rpb;
+    const long long phys = (long long)bb * batch_pitch + (long long)(r - bb * rpb);  // rows of one batch are contiguous, batches batch_pitch rows apart
     uint4* p = x + phys * ld8 + col8 + h * 8 + v;
     uint4 u = *p;
     uint32_t* w = &u.x;
@@ -312,6 +315,20 @@ static inline unsigned blocks_for(long long work, int per_block) {
 using namespace vdn;
 #define VDN_STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v)
 
+static void launch_rope2d(unsigned grid, cudaStream_t stream, uint4* x, long long rows, int ld8, int col8, int heads, const float* cs, int P, long long rpb,
+                          long long pitch, int per_head) {
+  // 32-bit decode when every index (and idx + one grid stride) fits: total + grid * 256 < 2^32
+  const bool small = rows * heads * 8 + (long long)grid * 256 < 0xffffffffLL && rpb < 0xffffffffLL;
+  const int fmt = get_operand_format();
+  if (small) {
+    if (fmt) rope2d_kernel<1, unsigned><<<grid, 256, 0, stream>>>(x, rows, ld8, col8, heads, cs, P, rpb, pitch, per_head);
+    else rope2d_kernel<0, unsigned><<<grid, 256, 0, stream>>>(x, rows, ld8, col8, heads, cs, P, rpb, pitch, per_head);
+  } else {
+    if (fmt) rope2d_kernel<1, long long><<<grid, 256, 0, stream>>>(x, rows, ld8, col8, heads, cs, P, rpb, pitch, per_head);
+    else rope2d_kernel<0, long long><<<grid, 256, 0, stream>>>(x, rows, ld8, col8, heads, cs, P, rpb, pitch, per_head);
+  }
+}
+
 extern "C" int vdn_rope2d(void* x, int64_t rows, int64_t ld, int32_t col0, int32_t heads, const float* cos_sin, int32_t P, int64_t rows_per_batch,
                           int64_t batch_pitch, void* stream_v) {
   VDN_STREAM;
@@ -321,8 +338,7 @@ extern "C" int vdn_rope2d(void* x, int64_t rows, int64_t ld, int32_t col0, int32
   if (rows_per_batch <= 0) { rows_per_batch = rows; batch_pitch = rows; }
   if (rows_per_batch % P != 0 || batch_pitch < rows_per_batch) return set_error("vdn_rope2d: rows_per_batch must be a multiple of P and <= batch_pitch");
   const unsigned grid = blocks_for(rows * heads * 8, 256);
-  if (get_operand_format()) rope2d_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch, 0);
-  else rope2d_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch, 0);
+  launch_rope2d(grid, stream, reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, heads, cos_sin, P, rows_per_batch, batch_pitch, 0);
   count_launch();
   return check_launch("rope2d_kernel");
 }
@@ -333,8 +349,7 @@ extern "C" int vdn_rope_chunks(void* x, int64_t rows, int64_t ld, int32_t col0, 
   if (ld % 8 != 0 || col0 % 8 != 0 || chunks <= 0 || P <= 0 || rows <= 0) return set_error("vdn_rope_chunks: bad geometry");
   if (col0 + (int64_t)chunks * 64 > ld) return set_error("vdn_rope_chunks: chunks exceed the row");
   const unsigned grid = blocks_for(rows * chunks * 8, 256);
-  if (get_operand_format()) rope2d_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, chunks, cos_sin, P, rows, rows, 1);
-  else rope2d_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, chunks, cos_sin, P, rows, rows, 1);
+  launch_rope2d(grid, stream, reinterpret_cast<uint4*>(x), rows, (int)(ld / 8), col0 / 8, chunks, cos_sin, P, rows, rows, 1);
   count_launch();
   return check_launch("rope2d_kernel");
 }
